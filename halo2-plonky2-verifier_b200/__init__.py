@@ -1,0 +1,171 @@
+"""b200zk — B200-native KZG-BN254 proving backend (host-side Python mirror of the C ABI in include/b200zk.h).
+
+The product path is libb200zk.so (hand-written sm_100a CUDA behind an extern "C" boundary). This module only
+binds it with ctypes; there is NO CPU fallback — without the built library or without a CUDA device every entry
+point raises.
+
+Field elements are numpy uint64 arrays of shape (..., 4) (halo2curves Montgomery limbs); G1 affine points are
+(..., 8).
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__)) if "__file__" in globals() else os.getcwd()
+if os.path.basename(_HERE) == "b200zk":  # executed through the alias package
+    _HERE = os.path.join(os.path.dirname(_HERE), "halo2-plonky2-verifier_b200")
+LIB_PATH = os.path.join(_HERE, "libb200zk.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+OK, ENODEV, EINVAL, ECUDA, ESTATE, ESYNTH = 0, -1, -2, -3, -4, -5
+
+
+class B200zkError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"b200zk error {code}: {msg}")
+        self.code = code
+
+
+def build(verbose=False):
+    """Compile libb200zk.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    subprocess.check_call(["make", "-C", CSRC, "-j8"] + ([] if verbose else ["-s"]))
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200zkError(ENODEV, f"{LIB_PATH} is not built (run __graft_entry__.build()); there is no CPU fallback")
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.b200zk_last_error.restype = ctypes.c_char_p
+        _lib.b200zk_stream.restype = ctypes.c_void_p
+        _lib.b200zk_launch_count.restype = ctypes.c_ulonglong
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+def _c(a, dtype=np.uint64):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def launch_count():
+    return int(lib().b200zk_launch_count())
+
+
+class Context:
+    """One CUDA device + stream (b200zk_create). Mirrors the reference-side objects that own prover state."""
+
+    def __init__(self, device=0):
+        self._h = ctypes.c_void_p()
+        rc = lib().b200zk_create(int(device), ctypes.byref(self._h))
+        if rc != OK:
+            raise B200zkError(rc, "no usable CUDA device (libb200zk has no CPU fallback)" if rc == ENODEV else "b200zk_create failed")
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().b200zk_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != OK:
+            raise B200zkError(rc, lib().b200zk_last_error(self._h).decode())
+
+    @property
+    def stream(self):
+        return lib().b200zk_stream(self._h)
+
+    def sync(self):
+        self._check(lib().b200zk_sync(self._h))
+
+    # ---- raw device memory ----
+    def dev_alloc(self, nbytes):
+        p = ctypes.c_void_p()
+        self._check(lib().b200zk_dev_alloc(self._h, ctypes.c_size_t(nbytes), ctypes.byref(p)))
+        return p.value
+
+    def dev_free(self, ptr):
+        self._check(lib().b200zk_dev_free(self._h, ctypes.c_void_p(ptr)))
+
+    def h2d(self, dst, src):
+        src = np.ascontiguousarray(src)
+        self._check(lib().b200zk_h2d(self._h, ctypes.c_void_p(dst), _p(src), ctypes.c_size_t(src.nbytes)))
+
+    def d2h(self, src, shape, dtype=np.uint64):
+        out = np.empty(shape, dtype=dtype)
+        self._check(lib().b200zk_d2h(self._h, _p(out), ctypes.c_void_p(src), ctypes.c_size_t(out.nbytes)))
+        return out
+
+    # ---- row A ----
+    def field_vec_op(self, field, op, a, b=None):
+        a = _c(a).reshape(-1, 4)
+        bb = _c(b).reshape(-1, 4) if b is not None else None
+        out = np.empty_like(a)
+        self._check(lib().b200zk_field_vec_op(self._h, field, op, _p(a), _p(bb), _p(out), ctypes.c_size_t(len(a))))
+        return out
+
+    def g1_vec_op(self, op, a, b=None):
+        a = _c(a).reshape(-1, 8)
+        bb = _c(b) if b is not None else None
+        out = np.empty_like(a)
+        self._check(lib().b200zk_g1_vec_op(self._h, op, _p(a), _p(bb), _p(out), ctypes.c_size_t(len(a))))
+        return out
+
+    # ---- row C / D ----
+    def ntt(self, a, log_n, omega):
+        """halo2_proofs::arithmetic::best_fft(a, omega, log_n); returns the transformed copy."""
+        a = _c(a).reshape(-1, 4).copy()
+        assert len(a) == 1 << log_n
+        omega = _c(omega)
+        self._check(lib().b200zk_ntt(self._h, _p(a), ctypes.c_uint32(log_n), _p(omega)))
+        return a
+
+    def ntt_dev(self, ptr, log_n, omega, batch=1, stride=0):
+        omega = _c(omega)
+        self._check(lib().b200zk_ntt_batch_dev(self._h, ctypes.c_void_p(ptr), ctypes.c_uint32(log_n), _p(omega), ctypes.c_uint32(batch),
+                                               ctypes.c_size_t(stride)))
+
+    def lagrange_to_coeff(self, k, a):
+        a = _c(a).reshape(-1, 4).copy()
+        assert len(a) == 1 << k
+        self._check(lib().b200zk_lagrange_to_coeff(self._h, ctypes.c_uint32(k), _p(a)))
+        return a
+
+    def coeff_to_extended(self, k, a):
+        a = _c(a).reshape(-1, 4)
+        assert len(a) == 1 << k
+        out = np.empty((4 << k, 4), dtype=np.uint64)
+        self._check(lib().b200zk_coeff_to_extended(self._h, ctypes.c_uint32(k), _p(a), _p(out)))
+        return out
+
+    def extended_to_coeff(self, k, a):
+        a = _c(a).reshape(-1, 4)
+        assert len(a) == 4 << k
+        out = np.empty((3 << k, 4), dtype=np.uint64)
+        self._check(lib().b200zk_extended_to_coeff(self._h, ctypes.c_uint32(k), _p(a), _p(out)))
+        return out
+
+    def lagrange_to_coeff_dev(self, k, ptr, batch=1, stride=0):
+        self._check(lib().b200zk_lagrange_to_coeff_dev(self._h, ctypes.c_uint32(k), ctypes.c_void_p(ptr), ctypes.c_uint32(batch), ctypes.c_size_t(stride)))
+
+    def coeff_to_extended_dev(self, k, src, dst, batch=1, stride_in=0, stride_out=0):
+        self._check(lib().b200zk_coeff_to_extended_dev(self._h, ctypes.c_uint32(k), ctypes.c_void_p(src), ctypes.c_void_p(dst), ctypes.c_uint32(batch),
+                                                       ctypes.c_size_t(stride_in), ctypes.c_size_t(stride_out)))
+
+    def extended_to_coeff_dev(self, k, src, dst):
+        self._check(lib().b200zk_extended_to_coeff_dev(self._h, ctypes.c_uint32(k), ctypes.c_void_p(src), ctypes.c_void_p(dst)))

@@ -1,0 +1,298 @@
+// extern "C" surface of libb200zk (include/b200zk.h): argument checking, error mapping, host<->device staging.
+#include "../../include/b200zk.h"
+
+#include "context.cuh"
+
+using namespace b200zk;
+
+struct b200zk_ctx {
+    Context c;
+};
+
+#define API_BEGIN(ctx)                      \
+    if (!(ctx)) return B200ZK_EINVAL;       \
+    std::lock_guard<std::mutex> _lk((ctx)->c.mu); \
+    try {                                   \
+        cudaSetDevice((ctx)->c.device);
+#define API_END(ctx)                        \
+    }                                       \
+    catch (const CudaError& e) {            \
+        (ctx)->c.last_error = e.what();     \
+        return B200ZK_ECUDA;                \
+    }                                       \
+    catch (const std::invalid_argument& e) {\
+        (ctx)->c.last_error = e.what();     \
+        return B200ZK_EINVAL;               \
+    }                                       \
+    catch (const std::exception& e) {       \
+        (ctx)->c.last_error = e.what();     \
+        return B200ZK_ESTATE;               \
+    }                                       \
+    return B200ZK_OK;
+
+extern "C" {
+
+int b200zk_create(int device, b200zk_ctx** out) {
+    if (!out) return B200ZK_EINVAL;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count) return B200ZK_ENODEV;
+    if (cudaSetDevice(device) != cudaSuccess) return B200ZK_ENODEV;
+    b200zk_ctx* ctx = new b200zk_ctx;
+    ctx->c.device = device;
+    if (cudaStreamCreateWithFlags(&ctx->c.stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return B200ZK_ECUDA;
+    }
+    // keep freed blocks in the stream-ordered pool instead of returning them to the driver
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = ctx;
+    return B200ZK_OK;
+}
+int b200zk_destroy(b200zk_ctx* ctx) {
+    if (!ctx) return B200ZK_EINVAL;
+    cudaSetDevice(ctx->c.device);
+    cudaStreamSynchronize(ctx->c.stream);
+    cudaStream_t s = ctx->c.stream;
+    delete ctx;
+    cudaStreamSynchronize(s);
+    cudaStreamDestroy(s);
+    return B200ZK_OK;
+}
+const char* b200zk_last_error(b200zk_ctx* ctx) { return ctx ? ctx->c.last_error.c_str() : "null context"; }
+void* b200zk_stream(b200zk_ctx* ctx) { return ctx ? (void*)ctx->c.stream : nullptr; }
+int b200zk_sync(b200zk_ctx* ctx) {
+    API_BEGIN(ctx)
+    CUDA_CHECK(cudaStreamSynchronize(ctx->c.stream));
+    API_END(ctx)
+}
+unsigned long long b200zk_launch_count(void) { return g_launch_count; }
+int b200zk_dev_alloc(b200zk_ctx* ctx, size_t bytes, void** out) {
+    API_BEGIN(ctx)
+    if (!out) throw std::invalid_argument("null out");
+    CUDA_CHECK(cudaMallocAsync(out, bytes, ctx->c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->c.stream));
+    API_END(ctx)
+}
+int b200zk_dev_free(b200zk_ctx* ctx, void* p) {
+    API_BEGIN(ctx)
+    CUDA_CHECK(cudaFreeAsync(p, ctx->c.stream));
+    API_END(ctx)
+}
+int b200zk_h2d(b200zk_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    API_BEGIN(ctx)
+    CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->c.stream));
+    API_END(ctx)
+}
+int b200zk_d2h(b200zk_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    API_BEGIN(ctx)
+    CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->c.stream));
+    API_END(ctx)
+}
+
+}  // extern "C"
+
+// ---- field / curve vector ops -------------------------------------------------------------------------------
+template <class C>
+__global__ void field_vec_kernel(int op, const Field<C>* a, const Field<C>* b, Field<C>* out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Field<C> x = f_load(a + i), y = b ? f_load(b + i) : f_zero<C>(), r;
+    switch (op) {
+        case 0: r = f_add(x, y); break;
+        case 1: r = f_sub(x, y); break;
+        case 2: r = f_mul(x, y); break;
+        case 3: r = f_inv(x); break;
+        case 4: r = f_neg(x); break;
+        case 5: r = f_from_mont(x); break;
+        default: r = f_to_mont(x); break;
+    }
+    f_store(out + i, r);
+}
+__global__ void g1_vec_kernel(int op, const G1Affine* a, const void* b, G1Affine* out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1Affine p;
+    p.x = f_load(&a[i].x);
+    p.y = f_load(&a[i].y);
+    G1X r;
+    if (op == 0) {
+        const G1Affine* bb = (const G1Affine*)b;
+        G1Affine q;
+        q.x = f_load(&bb[i].x);
+        q.y = f_load(&bb[i].y);
+        r = g1x_add_affine(g1x_from_affine(p), q);
+    } else if (op == 1) {
+        Fr s = f_from_mont(f_load((const Fr*)b + i));
+        r = g1x_mul_bits(g1x_from_affine(p), s.l, 256);
+    } else {
+        r = g1x_dbl(g1x_from_affine(p));
+    }
+    G1Affine o = g1x_to_affine(r);
+    f_store(&out[i].x, o.x);
+    f_store(&out[i].y, o.y);
+}
+
+extern "C" {
+
+int b200zk_field_vec_op(b200zk_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+    API_BEGIN(ctx)
+    if (!a || !out || op < 0 || op > 6 || (op <= 2 && !b)) throw std::invalid_argument("field_vec_op: bad arguments");
+    if (n == 0) return B200ZK_OK;
+    cudaStream_t s = ctx->c.stream;
+    DevBuf<Fr> da(n, s), db(b ? n : 0, s), dout(n, s);
+    CUDA_CHECK(cudaMemcpyAsync(da.get(), a, 32 * n, cudaMemcpyHostToDevice, s));
+    if (b) CUDA_CHECK(cudaMemcpyAsync(db.get(), b, 32 * n, cudaMemcpyHostToDevice, s));
+    unsigned blocks = (unsigned)((n + 127) / 128);
+    if (field == 0)
+        field_vec_kernel<FrCfg><<<blocks, 128, 0, s>>>(op, da.get(), b ? db.get() : nullptr, dout.get(), n);
+    else
+        field_vec_kernel<FqCfg><<<blocks, 128, 0, s>>>(op, (const Fq*)da.get(), b ? (const Fq*)db.get() : nullptr, (Fq*)dout.get(), n);
+    ++g_launch_count;
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(out, dout.get(), 32 * n, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    API_END(ctx)
+}
+
+int b200zk_g1_vec_op(b200zk_ctx* ctx, int op, const b200zk_g1_affine* a, const void* b, b200zk_g1_affine* out, size_t n) {
+    API_BEGIN(ctx)
+    if (!a || !out || op < 0 || op > 2 || (op <= 1 && !b)) throw std::invalid_argument("g1_vec_op: bad arguments");
+    if (n == 0) return B200ZK_OK;
+    cudaStream_t s = ctx->c.stream;
+    size_t bbytes = op == 0 ? 64 * n : op == 1 ? 32 * n : 0;
+    DevBuf<G1Affine> da(n, s), dout(n, s);
+    DevBuf<uint8_t> db(bbytes, s);
+    CUDA_CHECK(cudaMemcpyAsync(da.get(), a, 64 * n, cudaMemcpyHostToDevice, s));
+    if (bbytes) CUDA_CHECK(cudaMemcpyAsync(db.get(), b, bbytes, cudaMemcpyHostToDevice, s));
+    g1_vec_kernel<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(op, da.get(), db.get(), dout.get(), n);
+    ++g_launch_count;
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(out, dout.get(), 64 * n, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    API_END(ctx)
+}
+
+// ---- NTT ------------------------------------------------------------------------------------------------------
+static NttPlan plan_for_omega(Context& c, uint32_t log_n, const Fr& omega) {
+    if (log_n > FrConsts::S) throw std::invalid_argument("ntt: log_n exceeds the 2-adicity of Fr (28)");
+    const Fr w = FrConsts::root(log_n);
+    if (f_eq(w, omega)) return make_plan(c, log_n, false);
+    if (f_eq(f_inv(w), omega)) return make_plan(c, log_n, true);
+    // arbitrary root: private table (cached while omega and size repeat)
+    if (!c.custom_table || c.custom_table->log_n != log_n || !f_eq(c.custom_table->omega, omega)) {
+        auto t = std::make_unique<TwiddleTable>();
+        t->log_n = log_n;
+        t->omega = omega;
+        t->t.alloc(log_n == 0 ? 1 : (size_t)1 << (log_n - 1), c.stream);
+        build_twiddle_table(t->t.get(), omega, log_n, c.stream);
+        c.custom_table = std::move(t);
+    }
+    NttPlan p{};
+    p.table = c.custom_table->t.get();
+    p.table_log = log_n;
+    p.log_n = log_n;
+    p.inverse = false;
+    return p;
+}
+static Fr load_fr(const b200zk_fr* p) {
+    Fr r;
+    memcpy(r.l, p->l, 32);
+    return r;
+}
+
+int b200zk_ntt_batch_dev(b200zk_ctx* ctx, b200zk_fr* a_dev, uint32_t log_n, const b200zk_fr* omega, uint32_t batch, size_t stride) {
+    API_BEGIN(ctx)
+    if (!a_dev || !omega || batch == 0) throw std::invalid_argument("ntt: bad arguments");
+    Context& c = ctx->c;
+    NttPlan p = plan_for_omega(c, log_n, load_fr(omega));
+    const size_t n = (size_t)1 << log_n;
+    Fr* scratch = ntt_num_passes(log_n) > 1 ? c.get_scratch(n * batch) : nullptr;
+    ntt_run_batch(p, (Fr*)a_dev, (Fr*)a_dev, scratch, batch, stride, stride, n, c.stream);
+    API_END(ctx)
+}
+int b200zk_ntt_dev(b200zk_ctx* ctx, b200zk_fr* a_dev, uint32_t log_n, const b200zk_fr* omega) {
+    return b200zk_ntt_batch_dev(ctx, a_dev, log_n, omega, 1, 0);
+}
+int b200zk_ntt(b200zk_ctx* ctx, b200zk_fr* a, uint32_t log_n, const b200zk_fr* omega) {
+    if (!ctx || !a || log_n > 28) return B200ZK_EINVAL;
+    const size_t n = (size_t)1 << log_n;
+    void* d = nullptr;
+    int rc = b200zk_dev_alloc(ctx, 32 * n, &d);
+    if (rc) return rc;
+    rc = b200zk_h2d(ctx, d, a, 32 * n);
+    if (!rc) rc = b200zk_ntt_dev(ctx, (b200zk_fr*)d, log_n, omega);
+    if (!rc) rc = b200zk_d2h(ctx, a, d, 32 * n);
+    b200zk_dev_free(ctx, d);
+    return rc;
+}
+
+int b200zk_lagrange_to_coeff_dev(b200zk_ctx* ctx, uint32_t k, b200zk_fr* a_dev, uint32_t batch, size_t stride) {
+    API_BEGIN(ctx)
+    if (!a_dev || k + 2 > 28 || batch == 0) throw std::invalid_argument("lagrange_to_coeff: bad arguments");
+    dev_lagrange_to_coeff(ctx->c, k, (Fr*)a_dev, batch, stride);
+    API_END(ctx)
+}
+int b200zk_coeff_to_extended_dev(b200zk_ctx* ctx, uint32_t k, const b200zk_fr* in_dev, b200zk_fr* out_dev, uint32_t batch, size_t stride_in,
+                                 size_t stride_out) {
+    API_BEGIN(ctx)
+    if (!in_dev || !out_dev || k + 2 > 28 || batch == 0) throw std::invalid_argument("coeff_to_extended: bad arguments");
+    dev_coeff_to_extended(ctx->c, k, (const Fr*)in_dev, (Fr*)out_dev, batch, stride_in, stride_out);
+    API_END(ctx)
+}
+int b200zk_extended_to_coeff_dev(b200zk_ctx* ctx, uint32_t k, const b200zk_fr* in_dev, b200zk_fr* out_dev) {
+    API_BEGIN(ctx)
+    if (!in_dev || !out_dev || k + 2 > 28) throw std::invalid_argument("extended_to_coeff: bad arguments");
+    dev_extended_to_coeff(ctx->c, k, (const Fr*)in_dev, (Fr*)out_dev);
+    API_END(ctx)
+}
+static int staged(b200zk_ctx* ctx, const void* in, size_t in_bytes, void* out, size_t out_bytes, size_t dev_bytes,
+                  int (*fn)(b200zk_ctx*, void*, void*), bool separate_out) {
+    void *d = nullptr, *o = nullptr;
+    int rc = b200zk_dev_alloc(ctx, dev_bytes, &d);
+    if (rc) return rc;
+    if (separate_out) {
+        rc = b200zk_dev_alloc(ctx, out_bytes, &o);
+        if (rc) {
+            b200zk_dev_free(ctx, d);
+            return rc;
+        }
+    } else {
+        o = d;
+    }
+    rc = b200zk_h2d(ctx, d, in, in_bytes);
+    if (!rc) rc = fn(ctx, d, o);
+    if (!rc) rc = b200zk_d2h(ctx, out, o, out_bytes);
+    b200zk_dev_free(ctx, d);
+    if (separate_out) b200zk_dev_free(ctx, o);
+    return rc;
+}
+static thread_local uint32_t tl_k;
+int b200zk_lagrange_to_coeff(b200zk_ctx* ctx, uint32_t k, b200zk_fr* a) {
+    if (!ctx || !a || k + 2 > 28) return B200ZK_EINVAL;
+    tl_k = k;
+    const size_t n = (size_t)1 << k;
+    return staged(ctx, a, 32 * n, a, 32 * n, 32 * n, [](b200zk_ctx* c, void* d, void*) { return b200zk_lagrange_to_coeff_dev(c, tl_k, (b200zk_fr*)d, 1, 0); },
+                  false);
+}
+int b200zk_coeff_to_extended(b200zk_ctx* ctx, uint32_t k, const b200zk_fr* in, b200zk_fr* out) {
+    if (!ctx || !in || !out || k + 2 > 28) return B200ZK_EINVAL;
+    tl_k = k;
+    const size_t n = (size_t)1 << k;
+    return staged(ctx, in, 32 * n, out, 128 * n, 32 * n,
+                  [](b200zk_ctx* c, void* d, void* o) { return b200zk_coeff_to_extended_dev(c, tl_k, (const b200zk_fr*)d, (b200zk_fr*)o, 1, 0, 0); }, true);
+}
+int b200zk_extended_to_coeff(b200zk_ctx* ctx, uint32_t k, const b200zk_fr* in, b200zk_fr* out) {
+    if (!ctx || !in || !out || k + 2 > 28) return B200ZK_EINVAL;
+    tl_k = k;
+    const size_t n = (size_t)1 << k;
+    return staged(ctx, in, 128 * n, out, 96 * n, 128 * n,
+                  [](b200zk_ctx* c, void* d, void* o) { return b200zk_extended_to_coeff_dev(c, tl_k, (const b200zk_fr*)d, (b200zk_fr*)o); }, true);
+}
+
+}  // extern "C"

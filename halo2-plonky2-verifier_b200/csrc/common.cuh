@@ -1,0 +1,111 @@
+// Shared declarations of libb200zk: context, device buffers, kernel launch entry points.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "curve.cuh"
+
+namespace b200zk {
+
+struct CudaError : std::runtime_error {
+    explicit CudaError(const std::string& s) : std::runtime_error(s) {}
+};
+#define CUDA_CHECK(expr)                                                                                         \
+    do {                                                                                                         \
+        cudaError_t _e = (expr);                                                                                 \
+        if (_e != cudaSuccess)                                                                                   \
+            throw b200zk::CudaError(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " + __FILE__ + \
+                                    ":" + std::to_string(__LINE__));                                             \
+    } while (0)
+
+// 128-bit vectorised element access (Field is 2×uint4)
+template <class C>
+DEV Field<C> f_load(const Field<C>* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    Field<C> r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+template <class C>
+DEV Field<C> f_load_ro(const Field<C>* p) {  // read-only path
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    Field<C> r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+template <class C>
+DEV void f_store(Field<C>* p, const Field<C>& v) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+
+// ---- device buffer with stream-ordered allocation ----------------------------------------------------
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaStream_t stream = nullptr;
+    DevBuf() {}
+    DevBuf(size_t n_, cudaStream_t s) { alloc(n_, s); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), stream(o.stream) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) {
+            release();
+            p = o.p; n = o.n; stream = o.stream;
+            o.p = nullptr; o.n = 0;
+        }
+        return *this;
+    }
+    void alloc(size_t n_, cudaStream_t s) {
+        release();
+        n = n_;
+        stream = s;
+        if (n) CUDA_CHECK(cudaMallocAsync((void**)&p, n * sizeof(T), s));
+    }
+    void release() {
+        if (p) cudaFreeAsync(p, stream);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+    T* get() const { return p; }
+    size_t size() const { return n; }
+};
+
+// ---- NTT ---------------------------------------------------------------------------------------------
+// Twiddle table: T[i] = w^i for i < 2^(log_n-1), w a primitive 2^log_n-th root of unity.
+struct TwiddleTable {
+    DevBuf<Fr> t;
+    uint32_t log_n = 0;
+    Fr omega;
+};
+struct NttPlan {
+    const Fr* table;       // twiddle table of a 2^table_log root
+    uint32_t table_log;    // table covers exponents < 2^(table_log-1)
+    uint32_t log_n;        // transform size
+    bool inverse;          // use w^-1 (read the table mirrored and negated)
+    // fused pre/post processing (all optional)
+    const Fr* pre_scale3 = nullptr;   // device ptr to 3 factors applied to input element i by (i mod 3)
+    size_t in_len = 0;                // input elements at index >= in_len read as zero (0 = full)
+    const Fr* post_scale3 = nullptr;  // 3 factors applied to output element i by (i mod 3) (divisor folded in)
+    size_t out_len = 0;               // outputs at index >= out_len are not stored (0 = full)
+};
+// out may alias in. scratch must hold 2^log_n elements when the plan needs more than one pass.
+void ntt_run(const NttPlan& plan, const Fr* in, Fr* out, Fr* scratch, cudaStream_t stream);
+void build_twiddle_table(Fr* table, const Fr& omega, uint32_t log_n, cudaStream_t stream);
+int ntt_num_passes(uint32_t log_n);
+extern unsigned long long g_launch_count;  // kernels launched by this library (bench "gpu_launches")
+
+}  // namespace b200zk

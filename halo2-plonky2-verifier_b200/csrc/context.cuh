@@ -1,0 +1,186 @@
+// Context of libb200zk: one CUDA device, one stream, cached twiddle tables / domains / SRS / proving keys.
+#pragma once
+#include <memory>
+
+#include "common.cuh"
+
+namespace b200zk {
+
+// ---- host-side Fr helpers (the HD field code on its portable path) -------------------------------------
+inline Fr fr_from_hex(const char* s) {
+    Fr c = f_zero<FrCfg>();
+    size_t n = strlen(s);
+    for (size_t i = 0; i < n; ++i) {
+        char ch = s[n - 1 - i];
+        uint32_t v = (ch >= '0' && ch <= '9') ? ch - '0' : (ch >= 'a' && ch <= 'f') ? ch - 'a' + 10 : ch - 'A' + 10;
+        c.l[i / 8] |= v << (4 * (i % 8));
+    }
+    return f_to_mont(c);
+}
+inline Fr fr_from_u64(uint64_t v) {
+    Fr c = f_zero<FrCfg>();
+    c.l[0] = (uint32_t)v;
+    c.l[1] = (uint32_t)(v >> 32);
+    return f_to_mont(c);
+}
+struct FrConsts {
+    static constexpr uint32_t S = 28;
+    static const Fr& root_of_unity() {
+        static Fr v = fr_from_hex("03ddb9f5166d18b798865ea93dd31f743215cf6dd39329c8d34f1ed960c37c9c");
+        return v;
+    }
+    static const Fr& zeta() {
+        static Fr v = fr_from_hex("30644e72e131a029048b6e193fd84104cc37a73fec2bc5e9b8ca0b2d36636f23");
+        return v;
+    }
+    static const Fr& delta() {
+        static Fr v = fr_from_hex("09226b6e22c6f0ca64ec26aad4c86e715b5f898e5e963f25870e56bbe533e9a2");
+        return v;
+    }
+    // primitive 2^log_n-th root of unity used by EvaluationDomain
+    static Fr root(uint32_t log_n) {
+        Fr w = root_of_unity();
+        for (uint32_t i = log_n; i < S; ++i) w = f_sqr(w);
+        return w;
+    }
+};
+
+// EvaluationDomain::new(4, k) constants
+struct Domain {
+    uint32_t k = 0, extended_k = 0;
+    size_t n = 0, extended_n = 0;
+    Fr omega, omega_inv, extended_omega, extended_omega_inv, ifft_divisor, extended_ifft_divisor;
+    Fr t_inv[4];
+    // device constants: [0..3) into-coset factors {1, ζ, ζ²}; [3..6) lagrange_to_coeff post factors {1/n}×3;
+    // [6..9) extended_to_coeff post factors {1/4n, ζ²/4n, ζ/4n}; [9..13) t_inv
+    DevBuf<Fr> consts;
+    const Fr* pre_coset() const { return consts.get(); }
+    const Fr* post_l2c() const { return consts.get() + 3; }
+    const Fr* post_e2c() const { return consts.get() + 6; }
+    const Fr* t_inv_dev() const { return consts.get() + 9; }
+    Fr rotate_omega(const Fr& x, int rotation) const {
+        return rotation >= 0 ? f_mul(x, f_pow_u64(omega, (uint64_t)rotation)) : f_mul(x, f_pow_u64(omega_inv, (uint64_t)(-(int64_t)rotation)));
+    }
+};
+
+struct Srs {
+    uint32_t k = 0;
+    size_t n = 0;
+    DevBuf<G1Affine> g, g_lagrange;
+};
+
+struct MsmWorkspace;  // msm.cu
+struct ProvingKeyDev; // prover
+
+struct Context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::string last_error;
+    std::map<uint32_t, std::unique_ptr<TwiddleTable>> tables;  // standard roots, keyed by table log
+    std::unique_ptr<TwiddleTable> custom_table;                // last non-standard omega
+    std::map<uint32_t, std::unique_ptr<Domain>> domains;
+    DevBuf<Fr> scratch;
+    std::unique_ptr<Srs> srs;
+    std::shared_ptr<MsmWorkspace> msm_ws;
+
+    // table of the standard 2^t-th root with t >= log_n
+    const TwiddleTable& std_table(uint32_t log_n) {
+        for (auto& kv : tables)
+            if (kv.first >= log_n) return *kv.second;
+        auto t = std::make_unique<TwiddleTable>();
+        t->log_n = log_n;
+        t->omega = FrConsts::root(log_n);
+        t->t.alloc(log_n == 0 ? 1 : (size_t)1 << (log_n - 1), stream);
+        build_twiddle_table(t->t.get(), t->omega, log_n, stream);
+        auto& ref = tables[log_n];
+        ref = std::move(t);
+        return *ref;
+    }
+    Fr* get_scratch(size_t n) {
+        if (scratch.size() < n) {
+            CUDA_CHECK(cudaStreamSynchronize(stream));
+            scratch.alloc(n, stream);
+        }
+        return scratch.get();
+    }
+    const Domain& domain(uint32_t k) {
+        auto it = domains.find(k);
+        if (it != domains.end()) return *it->second;
+        auto d = std::make_unique<Domain>();
+        d->k = k;
+        d->extended_k = k + 2;
+        d->n = (size_t)1 << k;
+        d->extended_n = (size_t)4 << k;
+        d->extended_omega = FrConsts::root(k + 2);
+        d->omega = f_sqr(f_sqr(d->extended_omega));
+        d->omega_inv = f_inv(d->omega);
+        d->extended_omega_inv = f_inv(d->extended_omega);
+        d->ifft_divisor = f_inv(fr_from_u64(d->n));
+        d->extended_ifft_divisor = f_inv(fr_from_u64(d->extended_n));
+        const Fr zeta = FrConsts::zeta(), zeta2 = f_sqr(zeta), one = f_one<FrCfg>();
+        const Fr orig = f_pow_u64(zeta, d->n), step = f_pow_u64(d->extended_omega, d->n);
+        Fr cur = orig;
+        for (int j = 0; j < 4; ++j) {
+            d->t_inv[j] = f_inv(f_sub(cur, one));
+            cur = f_mul(cur, step);
+        }
+        Fr h[13] = {one, zeta, zeta2,
+                    d->ifft_divisor, d->ifft_divisor, d->ifft_divisor,
+                    d->extended_ifft_divisor, f_mul(d->extended_ifft_divisor, zeta2), f_mul(d->extended_ifft_divisor, zeta),
+                    d->t_inv[0], d->t_inv[1], d->t_inv[2], d->t_inv[3]};
+        d->consts.alloc(13, stream);
+        CUDA_CHECK(cudaMemcpyAsync(d->consts.get(), h, sizeof(h), cudaMemcpyHostToDevice, stream));
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        auto& ref = domains[k];
+        ref = std::move(d);
+        return *ref;
+    }
+};
+
+void ntt_run_batch(const NttPlan& plan, const Fr* in, Fr* out, Fr* scratch, uint32_t batch, size_t stride_in, size_t stride_out,
+                   size_t stride_scratch, cudaStream_t stream);
+
+// domain transforms on device buffers (ntt.cu semantics; see b200zk.h)
+inline NttPlan make_plan(Context& ctx, uint32_t log_n, bool inverse) {
+    const TwiddleTable& t = ctx.std_table(log_n);
+    NttPlan p{};
+    p.table = t.t.get();
+    p.table_log = t.log_n;
+    p.log_n = log_n;
+    p.inverse = inverse;
+    return p;
+}
+inline void dev_lagrange_to_coeff(Context& ctx, uint32_t k, Fr* a, uint32_t batch = 1, size_t stride = 0) {
+    const Domain& d = ctx.domain(k);
+    NttPlan p = make_plan(ctx, k, true);
+    p.post_scale3 = d.post_l2c();
+    Fr* scratch = ntt_num_passes(k) > 1 ? ctx.get_scratch(d.n * batch) : nullptr;
+    ntt_run_batch(p, a, a, scratch, batch, stride, stride, d.n, ctx.stream);
+}
+inline void dev_coeff_to_lagrange(Context& ctx, uint32_t k, Fr* a, uint32_t batch = 1, size_t stride = 0) {
+    const Domain& d = ctx.domain(k);
+    NttPlan p = make_plan(ctx, k, false);
+    Fr* scratch = ntt_num_passes(k) > 1 ? ctx.get_scratch(d.n * batch) : nullptr;
+    ntt_run_batch(p, a, a, scratch, batch, stride, stride, d.n, ctx.stream);
+}
+inline void dev_coeff_to_extended(Context& ctx, uint32_t k, const Fr* in, Fr* out, uint32_t batch = 1, size_t stride_in = 0,
+                                  size_t stride_out = 0) {
+    const Domain& d = ctx.domain(k);
+    NttPlan p = make_plan(ctx, k + 2, false);
+    p.pre_scale3 = d.pre_coset();
+    p.in_len = d.n;
+    // multi-pass transforms bounce through scratch; the output buffer itself can serve when batch == 1
+    Fr* scratch = ctx.get_scratch(d.extended_n * batch);
+    ntt_run_batch(p, in, out, scratch, batch, stride_in, stride_out, d.extended_n, ctx.stream);
+}
+inline void dev_extended_to_coeff(Context& ctx, uint32_t k, const Fr* in, Fr* out) {
+    const Domain& d = ctx.domain(k);
+    NttPlan p = make_plan(ctx, k + 2, true);
+    p.post_scale3 = d.post_e2c();
+    p.out_len = 3 * d.n;
+    Fr* scratch = ctx.get_scratch(d.extended_n);
+    ntt_run_batch(p, in, out, scratch, 1, 0, 0, 0, ctx.stream);
+}
+
+}  // namespace b200zk

@@ -1,0 +1,383 @@
+// BN254 Fr / Fq Montgomery arithmetic for sm_100a (replaces
+// halo2curves::bn256::{Fr,Fq} — the element type the reference names at
+// verifier/src/field/goldilocks/base.rs:472).
+//
+// Memory layout is the halo2curves one (4×u64 LE limbs, Montgomery R = 2^256, canonical) viewed as
+// 8×u32 — no conversion at the C-ABI boundary.
+//
+// Device multiply: word-serial Montgomery (CIOS) over 32-bit limbs with the accumulator split in two
+// carry-save halves — products a[j]·x for even j land in E, odd j in O (one limb higher) — so every row is
+// two independent mad.lo.cc/madc.hi.cc chains of four wide multiply-adds that ptxas fuses into
+// IMAD.WIDE.U32(.X) carry chains: 16 wide IMADs + 1 IMAD per limb of b, 136 per product. Retiring one limb per
+// row swaps the roles of E and O; the one-limb merge carry is fed into the next row's first chain.
+// The host bodies of the same row primitives (explicit carry variable) are what the CPU tests exercise and
+// what the host side of the prover uses for its handful of scalar operations.
+#pragma once
+#include <cstdint>
+#include <cstring>
+
+#if defined(__CUDACC__)
+#define HD __host__ __device__ __forceinline__
+#define DEV __device__ __forceinline__
+#else
+#define HD inline
+#define DEV inline
+#endif
+
+namespace b200zk {
+
+struct FrCfg {
+    // r = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
+    static HD constexpr uint32_t P(int i) {
+        constexpr uint32_t t[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+        return t[i];
+    }
+    static constexpr uint32_t INV = 0xefffffffu;  // -r^-1 mod 2^32
+    static HD constexpr uint32_t R1(int i) {
+        constexpr uint32_t t[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+        return t[i];
+    }
+    static HD constexpr uint32_t R2(int i) {
+        constexpr uint32_t t[8] = {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};
+        return t[i];
+    }
+    static HD constexpr uint32_t R3(int i) {
+        constexpr uint32_t t[8] = {0xb4bf0040u, 0x5e94d8e1u, 0x1cfbb6b8u, 0x2a489cbeu, 0xa19fcfedu, 0x893cc664u, 0x7fcc657cu, 0x0cf8594bu};
+        return t[i];
+    }
+};
+struct FqCfg {
+    // q = 0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47
+    static HD constexpr uint32_t P(int i) {
+        constexpr uint32_t t[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+        return t[i];
+    }
+    static constexpr uint32_t INV = 0xe4866389u;
+    static HD constexpr uint32_t R1(int i) {
+        constexpr uint32_t t[8] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u, 0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+        return t[i];
+    }
+    static HD constexpr uint32_t R2(int i) {
+        constexpr uint32_t t[8] = {0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u, 0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u};
+        return t[i];
+    }
+    static HD constexpr uint32_t R3(int i) {
+        constexpr uint32_t t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        return t[i];
+    }  // unused for Fq
+};
+
+template <class C>
+struct alignas(16) Field {
+    uint32_t l[8];
+};
+typedef Field<FrCfg> Fr;
+typedef Field<FqCfg> Fq;
+
+// ------------------------------------------------------------------------------------------------
+// row primitives: device = PTX carry chains, host = the same arithmetic with an explicit carry.
+// Every chain is ONE asm statement, so the carry flag never crosses a statement boundary.
+// ------------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+// acc[0..7] += (v0,v2,v4,v6)·x ; top = top_in + carry
+DEV void chain_mad8(uint32_t* acc, uint32_t& top, uint32_t top_in, uint32_t v0, uint32_t v2, uint32_t v4, uint32_t v6, uint32_t x) {
+    asm("mad.lo.cc.u32 %0, %10, %14, %0;\n\t"
+        "madc.hi.cc.u32 %1, %10, %14, %1;\n\t"
+        "madc.lo.cc.u32 %2, %11, %14, %2;\n\t"
+        "madc.hi.cc.u32 %3, %11, %14, %3;\n\t"
+        "madc.lo.cc.u32 %4, %12, %14, %4;\n\t"
+        "madc.hi.cc.u32 %5, %12, %14, %5;\n\t"
+        "madc.lo.cc.u32 %6, %13, %14, %6;\n\t"
+        "madc.hi.cc.u32 %7, %13, %14, %7;\n\t"
+        "addc.u32 %8, %9, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "=r"(top)
+        : "r"(top_in), "r"(v0), "r"(v2), "r"(v4), "r"(v6), "r"(x));
+}
+// same without a carry-out limb (caller guarantees no overflow past acc[7])
+DEV void chain_mad8_nocarry(uint32_t* acc, uint32_t v0, uint32_t v2, uint32_t v4, uint32_t v6, uint32_t x) {
+    asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
+        "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+        "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
+        "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+        "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+        "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+        "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+        "madc.hi.u32 %7, %11, %12, %7;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7])
+        : "r"(v0), "r"(v2), "r"(v4), "r"(v6), "r"(x));
+}
+// merge + chain: e0 += m1 (carry c); then acc[0..6] += (v1,v3,v5,v7)·x + c with acc[7] = hi(v7·x) + carry (acc[7] was 0)
+DEV void chain_merge_mad8(uint32_t& e0, uint32_t m1, uint32_t* acc, uint32_t v1, uint32_t v3, uint32_t v5, uint32_t v7, uint32_t x) {
+    asm("add.cc.u32 %0, %0, %9;\n\t"
+        "madc.lo.cc.u32 %1, %10, %14, %1;\n\t"
+        "madc.hi.cc.u32 %2, %10, %14, %2;\n\t"
+        "madc.lo.cc.u32 %3, %11, %14, %3;\n\t"
+        "madc.hi.cc.u32 %4, %11, %14, %4;\n\t"
+        "madc.lo.cc.u32 %5, %12, %14, %5;\n\t"
+        "madc.hi.cc.u32 %6, %12, %14, %6;\n\t"
+        "madc.lo.cc.u32 %7, %13, %14, %7;\n\t"
+        "madc.hi.u32 %8, %13, %14, 0;"
+        : "+r"(e0), "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "=r"(acc[7])
+        : "r"(m1), "r"(v1), "r"(v3), "r"(v5), "r"(v7), "r"(x));
+}
+// r[0..7] = a[0..7] + b[0..7], returns carry. Outputs are tied to the a-operands ("+r") so that no output
+// register can alias a later-read input.
+DEV uint32_t add8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    uint32_t c;
+    uint32_t t0 = a[0], t1 = a[1], t2 = a[2], t3 = a[3], t4 = a[4], t5 = a[5], t6 = a[6], t7 = a[7];
+    asm("add.cc.u32 %0, %0, %9;\n\t"
+        "addc.cc.u32 %1, %1, %10;\n\t"
+        "addc.cc.u32 %2, %2, %11;\n\t"
+        "addc.cc.u32 %3, %3, %12;\n\t"
+        "addc.cc.u32 %4, %4, %13;\n\t"
+        "addc.cc.u32 %5, %5, %14;\n\t"
+        "addc.cc.u32 %6, %6, %15;\n\t"
+        "addc.cc.u32 %7, %7, %16;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "+r"(t0), "+r"(t1), "+r"(t2), "+r"(t3), "+r"(t4), "+r"(t5), "+r"(t6), "+r"(t7), "=r"(c)
+        : "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    r[0] = t0; r[1] = t1; r[2] = t2; r[3] = t3; r[4] = t4; r[5] = t5; r[6] = t6; r[7] = t7;
+    return c;
+}
+// r = a - b, returns borrow (1 when a < b)
+DEV uint32_t sub8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    uint32_t c;
+    uint32_t t0 = a[0], t1 = a[1], t2 = a[2], t3 = a[3], t4 = a[4], t5 = a[5], t6 = a[6], t7 = a[7];
+    asm("sub.cc.u32 %0, %0, %9;\n\t"
+        "subc.cc.u32 %1, %1, %10;\n\t"
+        "subc.cc.u32 %2, %2, %11;\n\t"
+        "subc.cc.u32 %3, %3, %12;\n\t"
+        "subc.cc.u32 %4, %4, %13;\n\t"
+        "subc.cc.u32 %5, %5, %14;\n\t"
+        "subc.cc.u32 %6, %6, %15;\n\t"
+        "subc.cc.u32 %7, %7, %16;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "+r"(t0), "+r"(t1), "+r"(t2), "+r"(t3), "+r"(t4), "+r"(t5), "+r"(t6), "+r"(t7), "=r"(c)
+        : "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    r[0] = t0; r[1] = t1; r[2] = t2; r[3] = t3; r[4] = t4; r[5] = t5; r[6] = t6; r[7] = t7;
+    return c & 1u;
+}
+#else
+// ---- host bodies of the same primitives ----
+inline void chain_mad8(uint32_t* acc, uint32_t& top, uint32_t top_in, uint32_t v0, uint32_t v2, uint32_t v4, uint32_t v6, uint32_t x) {
+    const uint32_t v[4] = {v0, v2, v4, v6};
+    uint64_t carry = 0;
+    for (int t = 0; t < 4; ++t) {
+        uint64_t prod = (uint64_t)v[t] * x;
+        uint64_t lo = (uint64_t)acc[2 * t] + (uint32_t)prod + carry;
+        acc[2 * t] = (uint32_t)lo;
+        uint64_t hi = (uint64_t)acc[2 * t + 1] + (prod >> 32) + (lo >> 32);
+        acc[2 * t + 1] = (uint32_t)hi;
+        carry = hi >> 32;
+    }
+    top = top_in + (uint32_t)carry;
+}
+inline void chain_mad8_nocarry(uint32_t* acc, uint32_t v0, uint32_t v2, uint32_t v4, uint32_t v6, uint32_t x) {
+    uint32_t top;
+    chain_mad8(acc, top, 0, v0, v2, v4, v6, x);
+}
+inline void chain_merge_mad8(uint32_t& e0, uint32_t m1, uint32_t* acc, uint32_t v1, uint32_t v3, uint32_t v5, uint32_t v7, uint32_t x) {
+    uint64_t s = (uint64_t)e0 + m1;
+    e0 = (uint32_t)s;
+    uint64_t carry = s >> 32;
+    const uint32_t v[4] = {v1, v3, v5, v7};
+    acc[7] = 0;
+    for (int t = 0; t < 4; ++t) {
+        uint64_t prod = (uint64_t)v[t] * x;
+        uint64_t lo = (uint64_t)acc[2 * t] + (uint32_t)prod + carry;
+        acc[2 * t] = (uint32_t)lo;
+        uint64_t hi = (uint64_t)acc[2 * t + 1] + (prod >> 32) + (lo >> 32);
+        acc[2 * t + 1] = (uint32_t)hi;
+        carry = hi >> 32;
+    }
+}
+inline uint32_t add8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    uint64_t c = 0;
+    for (int i = 0; i < 8; ++i) {
+        c += (uint64_t)a[i] + b[i];
+        r[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    return (uint32_t)c;
+}
+inline uint32_t sub8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    uint64_t br = 0;
+    for (int i = 0; i < 8; ++i) {
+        uint64_t d = (uint64_t)a[i] - b[i] - br;
+        r[i] = (uint32_t)d;
+        br = (d >> 32) & 1;
+    }
+    return (uint32_t)br;
+}
+#endif
+
+// ------------------------------------------------------------------------------------------------
+template <class C>
+HD Field<C> f_zero() {
+    Field<C> r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.l[i] = 0;
+    return r;
+}
+template <class C>
+HD Field<C> f_one() {
+    Field<C> r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.l[i] = C::R1(i);
+    return r;
+}
+template <class C>
+HD bool f_is_zero(const Field<C>& a) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o |= a.l[i];
+    return o == 0;
+}
+template <class C>
+HD bool f_eq(const Field<C>& a, const Field<C>& b) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o |= a.l[i] ^ b.l[i];
+    return o == 0;
+}
+// r = (t >= P) ? t - P : t ; `carry` = a 2^256 overflow bit of t
+template <class C>
+HD Field<C> f_reduce_once(const Field<C>& t, uint32_t carry) {
+    uint32_t p[8], d[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p[i] = C::P(i);
+    uint32_t borrow = sub8(d, t.l, p);
+    bool use_d = carry | (borrow ^ 1u);
+    Field<C> r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.l[i] = use_d ? d[i] : t.l[i];
+    return r;
+}
+template <class C>
+HD Field<C> f_add(const Field<C>& a, const Field<C>& b) {
+    Field<C> t;
+    uint32_t c = add8(t.l, a.l, b.l);
+    return f_reduce_once<C>(t, c);
+}
+template <class C>
+HD Field<C> f_sub(const Field<C>& a, const Field<C>& b) {
+    Field<C> t, u;
+    uint32_t borrow = sub8(t.l, a.l, b.l);
+    uint32_t p[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p[i] = C::P(i);
+    add8(u.l, t.l, p);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t.l[i] = borrow ? u.l[i] : t.l[i];
+    return t;
+}
+template <class C>
+HD Field<C> f_neg(const Field<C>& a) {
+    if (f_is_zero(a)) return a;
+    Field<C> r;
+    uint32_t p[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p[i] = C::P(i);
+    sub8(r.l, p, a.l);
+    return r;
+}
+template <class C>
+HD Field<C> f_dbl(const Field<C>& a) {
+    return f_add<C>(a, a);
+}
+
+// Montgomery product a·b·2^-256 mod P, canonical result. Precondition: a < P (the operand that is multiplied
+// whole in every row — it bounds the running sum below 2P); b may be any value < 2^256.
+template <class C>
+HD Field<C> f_mul(const Field<C>& a, const Field<C>& b) {
+    // buf[0] and buf[1] hold the two carry-save halves; the live window slides up as limbs retire.
+    uint32_t X[20], Y[20];
+#pragma unroll
+    for (int i = 0; i < 20; ++i) X[i] = Y[i] = 0;
+    uint32_t* E = X;  // even-aligned half, 9 limbs live: E[0..8]
+    uint32_t* O = Y;  // odd-aligned half (one limb higher), 8 limbs live: O[0..7]
+    uint32_t p[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p[i] = C::P(i);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t bi = b.l[i];
+        if (i == 0) {
+            chain_mad8_nocarry(O, a.l[1], a.l[3], a.l[5], a.l[7], bi);
+            chain_mad8(E, E[8], 0, a.l[0], a.l[2], a.l[4], a.l[6], bi);
+        } else {
+            // retire limb 0 of the previous row: new E := old O (+ old E[1] at limb 0), new O := old E >> 64
+            uint32_t* nE = O;
+            uint32_t* nO = E + 2;
+            chain_merge_mad8(nE[0], E[1], nO, a.l[1], a.l[3], a.l[5], a.l[7], bi);
+            chain_mad8(nE, nE[8], 0, a.l[0], a.l[2], a.l[4], a.l[6], bi);
+            E = nE;
+            O = nO;
+        }
+        const uint32_t m = E[0] * C::INV;
+        chain_mad8(E, E[8], E[8], p[0], p[2], p[4], p[6], m);
+        chain_mad8_nocarry(O, p[1], p[3], p[5], p[7], m);
+    }
+    // E[0] == 0 now; result = (E >> 32) + O
+    Field<C> t;
+    uint32_t c = add8(t.l, E + 1, O);
+    return f_reduce_once<C>(t, c);
+}
+template <class C>
+HD Field<C> f_sqr(const Field<C>& a) {
+    return f_mul<C>(a, a);
+}
+// out of Montgomery form: a·2^-256 mod P (canonical integer limbs)
+template <class C>
+HD Field<C> f_from_mont(const Field<C>& a) {
+    Field<C> one;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) one.l[i] = i == 0 ? 1u : 0u;
+    return f_mul<C>(a, one);
+}
+template <class C>
+HD Field<C> f_to_mont(const Field<C>& a) {
+    Field<C> r2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r2.l[i] = C::R2(i);
+    return f_mul<C>(r2, a);
+}
+template <class C>
+HD Field<C> f_pow(const Field<C>& a, const uint32_t* e, int nlimbs) {
+    Field<C> r = f_one<C>();
+    for (int i = nlimbs - 1; i >= 0; --i)
+        for (int b = 31; b >= 0; --b) {
+            r = f_sqr<C>(r);
+            if ((e[i] >> b) & 1) r = f_mul<C>(r, a);
+        }
+    return r;
+}
+template <class C>
+HD Field<C> f_pow_u64(const Field<C>& a, uint64_t e) {
+    uint32_t w[2] = {(uint32_t)e, (uint32_t)(e >> 32)};
+    return f_pow<C>(a, w, 2);
+}
+// Fermat inverse (0 -> 0)
+template <class C>
+HD Field<C> f_inv(const Field<C>& a) {
+    uint32_t e[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e[i] = C::P(i);
+    e[0] -= 2;  // P[0] >= 2 for both moduli
+    return f_pow<C>(a, e, 8);
+}
+// halo2curves from_u512: (lo + 2^256·hi) mod P in Montgomery form
+template <class C>
+HD Field<C> f_from_u512(const uint32_t* w) {
+    Field<C> d0, d1, r2, r3;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        d0.l[i] = w[i];
+        d1.l[i] = w[8 + i];
+        r2.l[i] = C::R2(i);
+        r3.l[i] = C::R3(i);
+    }
+    return f_add<C>(f_mul<C>(r2, d0), f_mul<C>(r3, d1));
+}
+
+}  // namespace b200zk

@@ -1,0 +1,90 @@
+/* libb200zk — C ABI of the B200-native KZG-BN254 proving backend.
+ *
+ * This is the drop-in boundary for the hot path of halo2_proofs::plonk::{keygen_pk, create_proof} that the
+ * reference reaches through halo2-base `bench_builder` (reference: verifier/src/stark/mod.rs:543 and :593).
+ * The reference has no FFI for this path (it is plain Rust generics in the un-vendored crates halo2-axiom /
+ * halo2curves-axiom); each entry point below names the upstream function whose body a patched halo2_proofs
+ * replaces with this call (INTEGRATION.md shows the Rust `-sys` binding).
+ *
+ * Conventions
+ *   - `fr` / `fq` = uint64_t[4], little-endian limbs, Montgomery form (R = 2^256), canonical: byte-for-byte
+ *     the in-memory layout of halo2curves::bn256::{Fr,Fq}. `g1_affine` = fq x, fq y (64 bytes); identity = (0,0).
+ *   - Every function returns 0 on success and a negative B200ZK_E* code otherwise; nothing unwinds across the
+ *     boundary. `b200zk_last_error(ctx)` returns a human-readable description of the last failure on ctx.
+ *   - Host buffers are borrowed for the duration of the call only. Device memory lives behind the context.
+ *   - Entry points ending in `_dev` take DEVICE pointers (same layouts) and run on the context's stream
+ *     (`b200zk_stream`); they return after enqueueing unless stated otherwise.
+ *   - Any OS thread may call; calls on one context are serialised by an internal mutex.
+ *   - There is no CPU fallback: without a CUDA device `b200zk_create` fails with B200ZK_ENODEV.
+ */
+#ifndef B200ZK_H
+#define B200ZK_H
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define B200ZK_API __attribute__((visibility("default")))
+#else
+#define B200ZK_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200zk_ctx b200zk_ctx;
+typedef struct { uint64_t l[4]; } b200zk_fr;
+typedef struct { uint64_t l[4]; } b200zk_fq;
+typedef struct { b200zk_fq x, y; } b200zk_g1_affine;
+
+enum {
+    B200ZK_OK = 0,
+    B200ZK_ENODEV = -1,   /* no usable CUDA device */
+    B200ZK_EINVAL = -2,   /* bad argument */
+    B200ZK_ECUDA = -3,    /* CUDA runtime failure (see b200zk_last_error) */
+    B200ZK_ESTATE = -4,   /* missing prerequisite (e.g. SRS not loaded) */
+    B200ZK_ESYNTH = -5    /* constraint system failure (halo2 Error::ConstraintSystemFailure) */
+};
+
+/* ---- context ------------------------------------------------------------------------------------------- */
+B200ZK_API int b200zk_create(int device, b200zk_ctx** out);
+B200ZK_API int b200zk_destroy(b200zk_ctx* ctx);
+B200ZK_API const char* b200zk_last_error(b200zk_ctx* ctx);
+/* cudaStream_t of the context, for event timing by the caller */
+B200ZK_API void* b200zk_stream(b200zk_ctx* ctx);
+B200ZK_API int b200zk_sync(b200zk_ctx* ctx);
+/* kernels launched by this library since process start (bench.py "gpu_launches") */
+B200ZK_API unsigned long long b200zk_launch_count(void);
+/* raw device memory helpers for hosts without their own allocator */
+B200ZK_API int b200zk_dev_alloc(b200zk_ctx* ctx, size_t bytes, void** out);
+B200ZK_API int b200zk_dev_free(b200zk_ctx* ctx, void* p);
+B200ZK_API int b200zk_h2d(b200zk_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+B200ZK_API int b200zk_d2h(b200zk_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+
+/* ---- row A: field arithmetic (halo2curves::bn256::{Fr,Fq}) — vector forms, used by the parity tests --------
+ * field: 0 = Fr, 1 = Fq. op: 0 add, 1 sub, 2 mul, 3 inverse (0 -> 0), 4 neg, 5 from Montgomery (to_repr limbs),
+ * 6 to Montgomery. Host buffers of n elements; b is ignored by unary ops. */
+B200ZK_API int b200zk_field_vec_op(b200zk_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
+/* G1: op 0 = a + b (affine in, affine out), 1 = scalar[i]·a[i] (b = n fr scalars), 2 = 2·a */
+B200ZK_API int b200zk_g1_vec_op(b200zk_ctx* ctx, int op, const b200zk_g1_affine* a, const void* b, b200zk_g1_affine* out, size_t n);
+
+/* ---- row C: halo2_proofs::arithmetic::best_fft(a, omega, log_n) — natural order in and out, in place ----- */
+B200ZK_API int b200zk_ntt(b200zk_ctx* ctx, b200zk_fr* a, uint32_t log_n, const b200zk_fr* omega);
+B200ZK_API int b200zk_ntt_dev(b200zk_ctx* ctx, b200zk_fr* a_dev, uint32_t log_n, const b200zk_fr* omega);
+/* `batch` columns of 2^log_n elements, `stride` elements apart (device) */
+B200ZK_API int b200zk_ntt_batch_dev(b200zk_ctx* ctx, b200zk_fr* a_dev, uint32_t log_n, const b200zk_fr* omega, uint32_t batch, size_t stride);
+
+/* ---- row D: EvaluationDomain::new(4, k) and its transforms ------------------------------------------------
+ * lagrange_to_coeff: n -> n in place. coeff_to_extended: n -> 4n. extended_to_coeff: 4n -> 3n. */
+B200ZK_API int b200zk_lagrange_to_coeff(b200zk_ctx* ctx, uint32_t k, b200zk_fr* a);
+B200ZK_API int b200zk_coeff_to_extended(b200zk_ctx* ctx, uint32_t k, const b200zk_fr* in, b200zk_fr* out);
+B200ZK_API int b200zk_extended_to_coeff(b200zk_ctx* ctx, uint32_t k, const b200zk_fr* in, b200zk_fr* out);
+B200ZK_API int b200zk_lagrange_to_coeff_dev(b200zk_ctx* ctx, uint32_t k, b200zk_fr* a_dev, uint32_t batch, size_t stride);
+B200ZK_API int b200zk_coeff_to_extended_dev(b200zk_ctx* ctx, uint32_t k, const b200zk_fr* in_dev, b200zk_fr* out_dev, uint32_t batch,
+                                 size_t stride_in, size_t stride_out);
+B200ZK_API int b200zk_extended_to_coeff_dev(b200zk_ctx* ctx, uint32_t k, const b200zk_fr* in_dev, b200zk_fr* out_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -76,7 +76,9 @@ typedef Field<FqCfg> Fq;
 
 // ------------------------------------------------------------------------------------------------
 // row primitives: device = PTX carry chains, host = the same arithmetic with an explicit carry.
-// Every chain is ONE asm statement, so the carry flag never crosses a statement boundary.
+// Every chain is ONE asm statement, so the carry flag never crosses a statement boundary. Read-write operands
+// are early-clobber ("+&r"): they are written before the last input is read, and without '&' the compiler may
+// place an input that happens to hold the same value (e.g. a zero) in the same register.
 // ------------------------------------------------------------------------------------------------
 #if defined(__CUDA_ARCH__)
 // acc[0..7] += (v0,v2,v4,v6)·x ; top = top_in + carry
@@ -90,7 +92,7 @@ DEV void chain_mad8(uint32_t* acc, uint32_t& top, uint32_t top_in, uint32_t v0, 
         "madc.lo.cc.u32 %6, %13, %14, %6;\n\t"
         "madc.hi.cc.u32 %7, %13, %14, %7;\n\t"
         "addc.u32 %8, %9, 0;"
-        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "=r"(top)
+        : "+&r"(acc[0]), "+&r"(acc[1]), "+&r"(acc[2]), "+&r"(acc[3]), "+&r"(acc[4]), "+&r"(acc[5]), "+&r"(acc[6]), "+&r"(acc[7]), "=r"(top)
         : "r"(top_in), "r"(v0), "r"(v2), "r"(v4), "r"(v6), "r"(x));
 }
 // same without a carry-out limb (caller guarantees no overflow past acc[7])
@@ -103,7 +105,7 @@ DEV void chain_mad8_nocarry(uint32_t* acc, uint32_t v0, uint32_t v2, uint32_t v4
         "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
         "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
         "madc.hi.u32 %7, %11, %12, %7;"
-        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7])
+        : "+&r"(acc[0]), "+&r"(acc[1]), "+&r"(acc[2]), "+&r"(acc[3]), "+&r"(acc[4]), "+&r"(acc[5]), "+&r"(acc[6]), "+&r"(acc[7])
         : "r"(v0), "r"(v2), "r"(v4), "r"(v6), "r"(x));
 }
 // merge + chain: e0 += m1 (carry c); then acc[0..6] += (v1,v3,v5,v7)·x + c with acc[7] = hi(v7·x) + carry (acc[7] was 0)
@@ -117,7 +119,7 @@ DEV void chain_merge_mad8(uint32_t& e0, uint32_t m1, uint32_t* acc, uint32_t v1,
         "madc.hi.cc.u32 %6, %12, %14, %6;\n\t"
         "madc.lo.cc.u32 %7, %13, %14, %7;\n\t"
         "madc.hi.u32 %8, %13, %14, 0;"
-        : "+r"(e0), "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "=r"(acc[7])
+        : "+&r"(e0), "+&r"(acc[0]), "+&r"(acc[1]), "+&r"(acc[2]), "+&r"(acc[3]), "+&r"(acc[4]), "+&r"(acc[5]), "+&r"(acc[6]), "=r"(acc[7])
         : "r"(m1), "r"(v1), "r"(v3), "r"(v5), "r"(v7), "r"(x));
 }
 // r[0..7] = a[0..7] + b[0..7], returns carry. Outputs are tied to the a-operands ("+r") so that no output
@@ -134,7 +136,7 @@ DEV uint32_t add8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
         "addc.cc.u32 %6, %6, %15;\n\t"
         "addc.cc.u32 %7, %7, %16;\n\t"
         "addc.u32 %8, 0, 0;"
-        : "+r"(t0), "+r"(t1), "+r"(t2), "+r"(t3), "+r"(t4), "+r"(t5), "+r"(t6), "+r"(t7), "=r"(c)
+        : "+&r"(t0), "+&r"(t1), "+&r"(t2), "+&r"(t3), "+&r"(t4), "+&r"(t5), "+&r"(t6), "+&r"(t7), "=r"(c)
         : "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
     r[0] = t0; r[1] = t1; r[2] = t2; r[3] = t3; r[4] = t4; r[5] = t5; r[6] = t6; r[7] = t7;
     return c;
@@ -152,7 +154,7 @@ DEV uint32_t sub8(uint32_t* r, const uint32_t* a, const uint32_t* b) {
         "subc.cc.u32 %6, %6, %15;\n\t"
         "subc.cc.u32 %7, %7, %16;\n\t"
         "subc.u32 %8, 0, 0;"
-        : "+r"(t0), "+r"(t1), "+r"(t2), "+r"(t3), "+r"(t4), "+r"(t5), "+r"(t6), "+r"(t7), "=r"(c)
+        : "+&r"(t0), "+&r"(t1), "+&r"(t2), "+&r"(t3), "+&r"(t4), "+&r"(t5), "+&r"(t6), "+&r"(t7), "=r"(c)
         : "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
     r[0] = t0; r[1] = t1; r[2] = t2; r[3] = t3; r[4] = t4; r[5] = t5; r[6] = t6; r[7] = t7;
     return c & 1u;

@@ -169,3 +169,38 @@ class Context:
 
     def extended_to_coeff_dev(self, k, src, dst):
         self._check(lib().b200zk_extended_to_coeff_dev(self._h, ctypes.c_uint32(k), ctypes.c_void_p(src), ctypes.c_void_p(dst)))
+
+    # ---- rows B / K ----
+    def srs_load(self, k, g, g_lagrange):
+        """Copy ParamsKZG's `g` and `g_lagrange` (2^k affine points each) to the device."""
+        g = _c(g).reshape(-1, 8)
+        gl = _c(g_lagrange).reshape(-1, 8)
+        assert len(g) == 1 << k and len(gl) == 1 << k
+        self._check(lib().b200zk_srs_load(self._h, ctypes.c_uint32(k), _p(g), _p(gl)))
+        self.srs_k = k
+
+    def msm(self, scalars, basis=0):
+        """ParamsKZG::commit (basis=0) / commit_lagrange (basis=1) == best_multiexp(scalars, bases); affine result."""
+        scalars = _c(scalars).reshape(-1, 4)
+        out = np.empty(8, dtype=np.uint64)
+        self._check(lib().b200zk_msm(self._h, int(basis), _p(scalars), ctypes.c_size_t(len(scalars)), _p(out)))
+        return out
+
+    def msm_dev(self, scalars_ptr, n, basis=0):
+        out = np.empty(8, dtype=np.uint64)
+        self._check(lib().b200zk_msm_dev(self._h, int(basis), ctypes.c_void_p(scalars_ptr), ctypes.c_size_t(n), _p(out)))
+        return out
+
+    def msm_bases(self, scalars, bases):
+        """halo2curves::msm::best_multiexp(coeffs, bases) with caller-supplied bases."""
+        scalars = _c(scalars).reshape(-1, 4)
+        bases = _c(bases).reshape(-1, 8)
+        assert len(scalars) == len(bases)
+        out = np.empty(8, dtype=np.uint64)
+        self._check(lib().b200zk_msm_bases(self._h, _p(bases), _p(scalars), ctypes.c_size_t(len(scalars)), _p(out)))
+        return out
+
+    def msm_bases_dev(self, bases_ptr, scalars_ptr, n):
+        out = np.empty(8, dtype=np.uint64)
+        self._check(lib().b200zk_msm_bases_dev(self._h, ctypes.c_void_p(bases_ptr), ctypes.c_void_p(scalars_ptr), ctypes.c_size_t(n), _p(out)))
+        return out

@@ -5,6 +5,10 @@
 
 using namespace b200zk;
 
+namespace b200zk {
+G1Affine msm_run(Context& ctx, const G1Affine* bases, const Fr* scalars, size_t n);
+}
+
 struct b200zk_ctx {
     Context c;
 };
@@ -293,6 +297,72 @@ int b200zk_extended_to_coeff(b200zk_ctx* ctx, uint32_t k, const b200zk_fr* in, b
     const size_t n = (size_t)1 << k;
     return staged(ctx, in, 128 * n, out, 96 * n, 128 * n,
                   [](b200zk_ctx* c, void* d, void* o) { return b200zk_extended_to_coeff_dev(c, tl_k, (const b200zk_fr*)d, (b200zk_fr*)o); }, true);
+}
+
+}  // extern "C"
+
+// ---- SRS + MSM ----------------------------------------------------------------------------------------------------
+extern "C" {
+
+int b200zk_srs_load(b200zk_ctx* ctx, uint32_t k, const b200zk_g1_affine* g, const b200zk_g1_affine* g_lagrange) {
+    API_BEGIN(ctx)
+    if (!g || !g_lagrange || k > 26) throw std::invalid_argument("srs_load: bad arguments");
+    Context& c = ctx->c;
+    auto srs = std::make_unique<Srs>();
+    srs->k = k;
+    srs->n = (size_t)1 << k;
+    srs->g.alloc(srs->n, c.stream);
+    srs->g_lagrange.alloc(srs->n, c.stream);
+    CUDA_CHECK(cudaMemcpyAsync(srs->g.get(), g, 64 * srs->n, cudaMemcpyHostToDevice, c.stream));
+    CUDA_CHECK(cudaMemcpyAsync(srs->g_lagrange.get(), g_lagrange, 64 * srs->n, cudaMemcpyHostToDevice, c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    c.srs = std::move(srs);
+    API_END(ctx)
+}
+static const G1Affine* srs_basis(Context& c, int basis, size_t n) {
+    if (!c.srs) throw std::runtime_error("no SRS loaded (call b200zk_srs_load / b200zk_srs_setup first)");
+    if (n > c.srs->n) throw std::invalid_argument("msm: more scalars than SRS points");
+    if (basis != 0 && basis != 1) throw std::invalid_argument("msm: basis must be 0 (g) or 1 (g_lagrange)");
+    return basis == 0 ? c.srs->g.get() : c.srs->g_lagrange.get();
+}
+int b200zk_msm_bases_dev(b200zk_ctx* ctx, const b200zk_g1_affine* bases_dev, const b200zk_fr* scalars_dev, size_t n, b200zk_g1_affine* out) {
+    API_BEGIN(ctx)
+    if (!out || (n && (!bases_dev || !scalars_dev))) throw std::invalid_argument("msm: null argument");
+    G1Affine r = msm_run(ctx->c, (const G1Affine*)bases_dev, (const Fr*)scalars_dev, n);
+    memcpy(out, &r, 64);
+    API_END(ctx)
+}
+int b200zk_msm_dev(b200zk_ctx* ctx, int basis, const b200zk_fr* scalars_dev, size_t n, b200zk_g1_affine* out) {
+    API_BEGIN(ctx)
+    if (!out || (n && !scalars_dev)) throw std::invalid_argument("msm: null argument");
+    G1Affine r = msm_run(ctx->c, srs_basis(ctx->c, basis, n), (const Fr*)scalars_dev, n);
+    memcpy(out, &r, 64);
+    API_END(ctx)
+}
+int b200zk_msm(b200zk_ctx* ctx, int basis, const b200zk_fr* scalars, size_t n, b200zk_g1_affine* out) {
+    API_BEGIN(ctx)
+    if (!out || (n && !scalars)) throw std::invalid_argument("msm: null argument");
+    Context& c = ctx->c;
+    const G1Affine* bases = srs_basis(c, basis, n);
+    DevBuf<Fr> d(n, c.stream);
+    if (n) CUDA_CHECK(cudaMemcpyAsync(d.get(), scalars, 32 * n, cudaMemcpyHostToDevice, c.stream));
+    G1Affine r = msm_run(c, bases, d.get(), n);
+    memcpy(out, &r, 64);
+    API_END(ctx)
+}
+int b200zk_msm_bases(b200zk_ctx* ctx, const b200zk_g1_affine* bases, const b200zk_fr* scalars, size_t n, b200zk_g1_affine* out) {
+    API_BEGIN(ctx)
+    if (!out || (n && (!scalars || !bases))) throw std::invalid_argument("msm: null argument");
+    Context& c = ctx->c;
+    DevBuf<Fr> d(n, c.stream);
+    DevBuf<G1Affine> b(n, c.stream);
+    if (n) {
+        CUDA_CHECK(cudaMemcpyAsync(d.get(), scalars, 32 * n, cudaMemcpyHostToDevice, c.stream));
+        CUDA_CHECK(cudaMemcpyAsync(b.get(), bases, 64 * n, cudaMemcpyHostToDevice, c.stream));
+    }
+    G1Affine r = msm_run(c, b.get(), d.get(), n);
+    memcpy(out, &r, 64);
+    API_END(ctx)
 }
 
 }  // extern "C"

@@ -1,0 +1,360 @@
+// G1 Pippenger MSM for sm_100a (replaces halo2curves::msm::best_multiexp as called by
+// ParamsKZG::{commit, commit_lagrange} from create_proof — reference entry verifier/src/stark/mod.rs:543,593).
+//
+// Only the group element Σ sᵢ·Pᵢ matters (canonical affine at the boundary), so the decomposition is free:
+//   1. digits   : scalars leave Montgomery form; each is cut into W signed c-bit digits dₗ ∈ [-2^(c-1), 2^(c-1)];
+//                 zero digits create no work (advice-like scalars are mostly < 2^84, lookup columns < 2^(k-1)).
+//   2. sort     : counting sort of (window, |digit|) → bucket: histogram with atomics, exclusive scan, scatter.
+//                 Order inside a bucket is irrelevant to the group sum, so the result stays deterministic.
+//   3. accumulate: the sorted entry list is cut into equal chunks of T entries, one thread each (perfect balance
+//                 whatever the bucket histogram: hot buckets simply span many chunks). A thread walks its chunk
+//                 with one XYZZ accumulator and mixed additions (8M+2S); runs that begin inside the chunk are
+//                 stored to their bucket, the run that began earlier goes to a "head" list, which is itself
+//                 segment-summed by the same scheme with chunk T2 until one thread covers it.
+//   4. reduce   : per window Σ b·B_b via running sums over chunks of m buckets plus a small double-and-add for the
+//                 chunk offset, then a block tree sum per window.
+//   5. fold     : Σ 2^(c·w)·S_w over W window sums — 254 dependent doublings, done on the host in 64-bit limbs
+//                 (≈0.1 ms) because a single GPU thread would take longer than the whole MSM.
+// Bound: integer pipe (≈10 Fq products per point·window), not HBM; see DESIGN.md.
+#include "context.cuh"
+
+namespace b200zk {
+
+constexpr uint32_t INVALID_KEY = 0xffffffffu;
+
+struct MsmConfig {
+    uint32_t c, W, B;  // window bits, windows, buckets per window (2^(c-1))
+};
+MsmConfig msm_config(size_t n) {
+    uint32_t lg = 0;
+    while (((size_t)1 << (lg + 1)) <= n) ++lg;
+    uint32_t c = lg > 4 ? lg - 4 : 1;
+    if (c < 4) c = 4;
+    if (c > 16) c = 16;
+    if (lg >= 24) c = 18;
+    if (lg >= 26) c = 20;
+    MsmConfig m;
+    m.c = c;
+    m.W = (255 + c - 1) / c;
+    m.B = 1u << (c - 1);
+    return m;
+}
+
+DEV G1X g1x_load(const G1X* p) {
+    G1X r;
+    r.x = f_load(&p->x);
+    r.y = f_load(&p->y);
+    r.zz = f_load(&p->zz);
+    r.zzz = f_load(&p->zzz);
+    return r;
+}
+DEV void g1x_store(G1X* p, const G1X& v) {
+    f_store(&p->x, v.x);
+    f_store(&p->y, v.y);
+    f_store(&p->zz, v.zz);
+    f_store(&p->zzz, v.zzz);
+}
+DEV G1Affine g1a_load_ro(const G1Affine* p) {
+    G1Affine r;
+    r.x = f_load_ro(&p->x);
+    r.y = f_load_ro(&p->y);
+    return r;
+}
+
+constexpr int MAX_W = 64;
+
+// Signed-digit recoding done on the fly: window w holds bits [w·c, w·c+c) plus the carry of the window below;
+// values above 2^(c-1) become negative digits with a carry into the next window.
+// mode 0: histogram; mode 1: scatter (counters = running offsets)
+__global__ void msm_digits_kernel(const Fr* scalars, size_t n, MsmConfig cfg, uint32_t* counters, uint32_t* entries, int mode) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Fr s = f_from_mont(f_load(scalars + i));
+    const uint32_t c = cfg.c, mask = (1u << c) - 1, halfv = 1u << (c - 1);
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < cfg.W; ++w) {
+        const uint32_t o = w * c, limb = o >> 5, sh = o & 31;
+        uint32_t v = 0;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {  // register-resident limb select
+            if ((uint32_t)t == limb) v = s.l[t] >> sh;
+        }
+        if (sh + c > 32) {
+#pragma unroll
+            for (int t = 1; t < 8; ++t) {
+                if ((uint32_t)t == limb + 1) v |= s.l[t] << (32 - sh);
+            }
+        }
+        v = (v & mask) + carry;
+        const bool neg = v > halfv;
+        const uint32_t mag = neg ? (1u << c) - v : v;
+        carry = neg ? 1u : 0u;
+        if (mag == 0) continue;
+        const uint32_t bucket = w * cfg.B + mag - 1;
+        if (mode == 0) {
+            atomicAdd(counters + bucket, 1u);
+        } else {
+            const uint32_t pos = atomicAdd(counters + bucket, 1u);
+            entries[pos] = (uint32_t)i | (neg ? 0x80000000u : 0u);
+        }
+    }
+}
+
+// ---- u32 exclusive scan (3 phases, 4096 items per block) ----------------------------------------------------
+constexpr int SCAN_THREADS = 1024, SCAN_ITEMS = 4;
+__global__ void scan_block_kernel(const uint32_t* in, uint32_t* out, uint32_t* block_sums, size_t n) {
+    __shared__ uint32_t warp_sums[32];
+    const size_t base = ((size_t)blockIdx.x * SCAN_THREADS + threadIdx.x) * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS], sum = 0;
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = base + k < n ? in[base + k] : 0;
+        sum += v[k];
+    }
+    // inclusive warp scan of thread sums
+    uint32_t x = sum;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= (uint32_t)o) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = warp_sums[lane], ws = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, ws, o);
+            if (lane >= (uint32_t)o) ws += y;
+        }
+        warp_sums[lane] = ws - w;  // exclusive
+        if (lane == 31 && block_sums) block_sums[blockIdx.x] = ws;
+    }
+    __syncthreads();
+    uint32_t run = warp_sums[wid] + x - sum;
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+    }
+}
+__global__ void scan_add_kernel(uint32_t* out, const uint32_t* block_offsets, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] += block_offsets[i / (SCAN_THREADS * SCAN_ITEMS)];
+}
+// out[i] = sum_{j<i} in[j]; out may alias in. Returns nothing; total is out[n-1] + in[n-1] (callers append a 0).
+void exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, cudaStream_t stream) {
+    if (n == 0) return;
+    const size_t per = SCAN_THREADS * SCAN_ITEMS;
+    const size_t nb = (n + per - 1) / per;
+    if (nb == 1) {
+        scan_block_kernel<<<1, SCAN_THREADS, 0, stream>>>(in, out, nullptr, n);
+        ++g_launch_count;
+        return;
+    }
+    DevBuf<uint32_t> sums(nb, stream);
+    scan_block_kernel<<<(unsigned)nb, SCAN_THREADS, 0, stream>>>(in, out, sums.get(), n);
+    exclusive_scan_u32(sums.get(), sums.get(), nb, stream);
+    scan_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(out, sums.get(), n);
+    g_launch_count += 2;
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// ---- accumulate ---------------------------------------------------------------------------------------------
+DEV uint32_t find_bucket(const uint32_t* offsets, uint32_t nb, uint32_t p) {
+    uint32_t lo = 0, hi = nb;  // offsets[lo] <= p < offsets[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(offsets + mid) <= p) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+constexpr int ACC_T = 32;        // entries per thread, level 1
+constexpr int COMB_T = 16;       // partial sums per thread, levels >= 2
+constexpr int ACC_THREADS = 128;
+
+__global__ void __launch_bounds__(ACC_THREADS) msm_accumulate_kernel(const G1Affine* bases, const uint32_t* entries, const uint32_t* offsets,
+                                                                     uint32_t nb, uint32_t total, G1X* bucket_sums, G1X* heads,
+                                                                     uint32_t* head_keys) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t p0l = (uint64_t)t * ACC_T;
+    if (p0l >= total) return;
+    const uint32_t p0 = (uint32_t)p0l;
+    const uint32_t p1 = total - p0 > (uint32_t)ACC_T ? p0 + ACC_T : total;
+    uint32_t cur = find_bucket(offsets, nb, p0);
+    uint32_t end = __ldg(offsets + cur + 1);
+    bool started_before = __ldg(offsets + cur) < p0;
+    head_keys[t] = started_before ? cur : INVALID_KEY;
+    G1X acc = g1x_identity();
+    for (uint32_t p = p0; p < p1; ++p) {
+        if (p == end) {
+            g1x_store(started_before ? heads + t : bucket_sums + cur, acc);
+            acc = g1x_identity();
+            started_before = false;
+            do {
+                ++cur;
+                end = __ldg(offsets + cur + 1);
+            } while (end == p);
+        }
+        const uint32_t e = __ldg(entries + p);
+        G1Affine b = g1a_load_ro(bases + (e & 0x7fffffffu));
+        if (e >> 31) b.y = f_neg(b.y);
+        acc = g1x_add_affine(acc, b);
+    }
+    g1x_store(started_before ? heads + t : bucket_sums + cur, acc);
+}
+
+// segmented sum of a key-sorted list of partial sums (INVALID_KEY entries are holes)
+__global__ void __launch_bounds__(ACC_THREADS) msm_combine_kernel(const G1X* pts, const uint32_t* keys, uint32_t n, G1X* bucket_sums, G1X* heads_out,
+                                                                  uint32_t* keys_out) {
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t p0l = (uint64_t)u * COMB_T;
+    if (p0l >= n) return;
+    const uint32_t p0 = (uint32_t)p0l;
+    const uint32_t p1 = n - p0 > (uint32_t)COMB_T ? p0 + COMB_T : n;
+    bool have = false, started_before = false;
+    uint32_t cur = INVALID_KEY, out_key = INVALID_KEY;
+    G1X acc = g1x_identity();
+    for (uint32_t p = p0; p < p1; ++p) {
+        const uint32_t k = __ldg(keys + p);
+        if (have && k != cur) {
+            if (started_before) g1x_store(heads_out + u, acc);
+            else g1x_store(bucket_sums + cur, g1x_add(g1x_load(bucket_sums + cur), acc));
+            have = false;
+        }
+        if (k == INVALID_KEY) continue;
+        if (!have) {
+            cur = k;
+            have = true;
+            acc = g1x_identity();
+            started_before = p == p0 && p0 > 0 && __ldg(keys + p0 - 1) == k;
+            if (started_before) out_key = k;
+        }
+        acc = g1x_add(acc, g1x_load(pts + p));
+    }
+    if (have) {
+        if (started_before) g1x_store(heads_out + u, acc);
+        else g1x_store(bucket_sums + cur, g1x_add(g1x_load(bucket_sums + cur), acc));
+    }
+    keys_out[u] = out_key;
+}
+
+// ---- bucket reduction: per window sum_b (b+1)·B[b] -----------------------------------------------------------
+constexpr int RED_M = 8;  // buckets per thread
+__global__ void __launch_bounds__(128) msm_reduce_chunks_kernel(const G1X* bucket_sums, uint32_t total_chunks, G1X* chunk_out) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;  // global chunk index (window-major)
+    if (j >= total_chunks) return;
+    const G1X* b = bucket_sums + (size_t)j * RED_M;
+    G1X run = g1x_identity(), tot = g1x_identity();
+    for (int i = RED_M - 1; i >= 0; --i) {
+        run = g1x_add(run, g1x_load(b + i));
+        tot = g1x_add(tot, run);
+    }
+    g1x_store(chunk_out + j, tot);                 // sum (i+1)·B[jm+i]
+    g1x_store(chunk_out + total_chunks + j, run);  // sum B
+}
+// contribution of chunk j inside its window: tot + (j_in_window·m)·run ; then tree-sum per window (one block each)
+__global__ void __launch_bounds__(256) msm_reduce_window_kernel(const G1X* chunk_out, uint32_t total_chunks, uint32_t chunks_per_window, G1X* window_sums) {
+    __shared__ G1X sh[256];
+    const uint32_t w = blockIdx.x;
+    G1X acc = g1x_identity();
+    for (uint32_t j = threadIdx.x; j < chunks_per_window; j += blockDim.x) {
+        const uint32_t g = w * chunks_per_window + j;
+        G1X tot = g1x_load(chunk_out + g), run = g1x_load(chunk_out + total_chunks + g);
+        const uint32_t k = j * RED_M;
+        if (k) {
+            uint32_t bits = 32 - __clz(k);
+            tot = g1x_add(tot, g1x_mul_bits(run, &k, (int)bits));
+        }
+        acc = g1x_add(acc, tot);
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (uint32_t s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sh[threadIdx.x] = g1x_add(sh[threadIdx.x], sh[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) g1x_store(window_sums + w, sh[0]);
+}
+// Σ 2^(c·w)·S_w on the host (64-bit limb path of the shared field code)
+G1X msm_fold_windows(const G1X* window_sums, uint32_t W, uint32_t c) {
+    G1X acc = g1x_identity();
+    for (uint32_t w = W; w-- > 0;) {
+        for (uint32_t i = 0; i < c; ++i) acc = g1x_dbl(acc);
+        acc = g1x_add(acc, window_sums[w]);
+    }
+    return acc;
+}
+
+// Computes the W window sums of Σ scalars[i]·bases[i] into `window_sums_host` (XYZZ). Synchronises the stream.
+void msm_window_sums(Context& ctx, const G1Affine* bases, const Fr* scalars, size_t n, MsmConfig& cfg, std::vector<G1X>& window_sums_host) {
+    cudaStream_t s = ctx.stream;
+    cfg = msm_config(n);
+    if (cfg.W > (uint32_t)MAX_W) throw std::runtime_error("msm: too many windows");
+    if (n >= ((size_t)1 << 31)) throw std::invalid_argument("msm: n must be < 2^31");
+    const uint32_t nb = cfg.W * cfg.B;
+    window_sums_host.assign(cfg.W, g1x_identity());
+    if (n == 0) return;
+    DevBuf<uint32_t> counters(nb + 1, s), offsets(nb + 1, s);
+    CUDA_CHECK(cudaMemsetAsync(counters.get(), 0, (nb + 1) * 4, s));
+    const unsigned dblocks = (unsigned)((n + 127) / 128);
+    msm_digits_kernel<<<dblocks, 128, 0, s>>>(scalars, n, cfg, counters.get(), nullptr, 0);
+    ++g_launch_count;
+    exclusive_scan_u32(counters.get(), offsets.get(), nb + 1, s);
+    uint32_t total = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&total, offsets.get() + nb, 4, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaMemcpyAsync(counters.get(), offsets.get(), (nb + 1) * 4, cudaMemcpyDeviceToDevice, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    if (total == 0) return;
+    DevBuf<uint32_t> entries(total, s);
+    msm_digits_kernel<<<dblocks, 128, 0, s>>>(scalars, n, cfg, counters.get(), entries.get(), 1);
+    ++g_launch_count;
+    DevBuf<G1X> bucket_sums(nb, s);
+    CUDA_CHECK(cudaMemsetAsync(bucket_sums.get(), 0, (size_t)nb * sizeof(G1X), s));
+    // level 1
+    uint32_t nthreads = (uint32_t)(((uint64_t)total + ACC_T - 1) / ACC_T);
+    DevBuf<G1X> heads_a(nthreads, s), heads_b;
+    DevBuf<uint32_t> keys_a(nthreads, s), keys_b;
+    msm_accumulate_kernel<<<(nthreads + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, s>>>(bases, entries.get(), offsets.get(), nb, total,
+                                                                                              bucket_sums.get(), heads_a.get(), keys_a.get());
+    ++g_launch_count;
+    CUDA_CHECK(cudaGetLastError());
+    // levels >= 2: segment-sum the head list until a single thread covers it
+    uint32_t len = nthreads;
+    bool flip = false;
+    while (true) {
+        const uint32_t nt = (len + COMB_T - 1) / COMB_T;
+        DevBuf<G1X>& in_p = flip ? heads_b : heads_a;
+        DevBuf<uint32_t>& in_k = flip ? keys_b : keys_a;
+        DevBuf<G1X>& out_p = flip ? heads_a : heads_b;
+        DevBuf<uint32_t>& out_k = flip ? keys_a : keys_b;
+        out_p.alloc(nt, s);
+        out_k.alloc(nt, s);
+        msm_combine_kernel<<<(nt + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, s>>>(in_p.get(), in_k.get(), len, bucket_sums.get(), out_p.get(),
+                                                                                        out_k.get());
+        ++g_launch_count;
+        CUDA_CHECK(cudaGetLastError());
+        if (nt == 1) break;  // a single thread has no predecessor: nothing can be left in its head slot
+        len = nt;
+        flip = !flip;
+    }
+    // reduce
+    DevBuf<G1X> wsums(cfg.W, s);
+    if (cfg.B % RED_M != 0) throw std::runtime_error("msm: bucket count not a multiple of the reduce chunk");
+    const uint32_t cpw = cfg.B / RED_M, total_chunks = cfg.W * cpw;
+    DevBuf<G1X> chunk_out((size_t)2 * total_chunks, s);
+    msm_reduce_chunks_kernel<<<(total_chunks + 127) / 128, 128, 0, s>>>(bucket_sums.get(), total_chunks, chunk_out.get());
+    msm_reduce_window_kernel<<<cfg.W, 256, 0, s>>>(chunk_out.get(), total_chunks, cpw, wsums.get());
+    g_launch_count += 2;
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(window_sums_host.data(), wsums.get(), cfg.W * sizeof(G1X), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
+G1Affine msm_run(Context& ctx, const G1Affine* bases, const Fr* scalars, size_t n) {
+    MsmConfig cfg;
+    std::vector<G1X> ws;
+    msm_window_sums(ctx, bases, scalars, n, cfg, ws);
+    return g1x_to_affine(msm_fold_windows(ws.data(), cfg.W, cfg.c));
+}
+
+}  // namespace b200zk

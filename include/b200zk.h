@@ -84,6 +84,18 @@ B200ZK_API int b200zk_coeff_to_extended_dev(b200zk_ctx* ctx, uint32_t k, const b
                                  size_t stride_in, size_t stride_out);
 B200ZK_API int b200zk_extended_to_coeff_dev(b200zk_ctx* ctx, uint32_t k, const b200zk_fr* in_dev, b200zk_fr* out_dev);
 
+/* ---- rows B, K: ParamsKZG<Bn256> bases and halo2curves::msm::best_multiexp ------------------------------------
+ * srs_load copies both bases (n = 2^k affine points each) to the device once; `basis` below: 0 = g (monomial,
+ * ParamsKZG::commit), 1 = g_lagrange (ParamsKZG::commit_lagrange). Results are canonical affine points. */
+B200ZK_API int b200zk_srs_load(b200zk_ctx* ctx, uint32_t k, const b200zk_g1_affine* g, const b200zk_g1_affine* g_lagrange);
+B200ZK_API int b200zk_msm(b200zk_ctx* ctx, int basis, const b200zk_fr* scalars, size_t n, b200zk_g1_affine* out);
+B200ZK_API int b200zk_msm_dev(b200zk_ctx* ctx, int basis, const b200zk_fr* scalars_dev, size_t n, b200zk_g1_affine* out);
+/* best_multiexp(coeffs, bases) with caller-supplied bases (host buffers) */
+B200ZK_API int b200zk_msm_bases(b200zk_ctx* ctx, const b200zk_g1_affine* bases, const b200zk_fr* scalars, size_t n, b200zk_g1_affine* out);
+/* device bases + device scalars (bench / multi-GPU shards): point range [0, n) of bases_dev */
+B200ZK_API int b200zk_msm_bases_dev(b200zk_ctx* ctx, const b200zk_g1_affine* bases_dev, const b200zk_fr* scalars_dev, size_t n,
+                                    b200zk_g1_affine* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -238,43 +238,62 @@ __global__ void __launch_bounds__(ACC_THREADS) msm_combine_kernel(const G1X* pts
     keys_out[u] = out_key;
 }
 
-// ---- bucket reduction: per window sum_b (b+1)·B[b] -----------------------------------------------------------
-constexpr int RED_M = 8;  // buckets per thread
-__global__ void __launch_bounds__(128) msm_reduce_chunks_kernel(const G1X* bucket_sums, uint32_t total_chunks, G1X* chunk_out) {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;  // global chunk index (window-major)
+// ---- bucket reduction: per window F(B) = sum_b (b+1)·B[b] ---------------------------------------------------
+// Chunks of m consecutive entries give tot_q = Σ_r (r+1)·X[qm+r] and run_q = Σ_r X[qm+r] with 2 additions per
+// entry; then F(X) = Σ_q tot_q + m·(F(run) − S), S = ΣX, so the same kernel recurses on the `run` list (÷m per
+// level) and the per-level sums T_l = Σ_q tot_q are combined by a short Horner in m: A = S; A = T_l + m·(A − S).
+constexpr int RED_LOG_M = 3;
+// lists are window-major: X[w·len + i]; outputs tot[w·(len/m) + q], run[w·(len/m) + q]
+__global__ void __launch_bounds__(128) msm_reduce_chunks_kernel(const G1X* X, uint32_t total_chunks, uint32_t m, G1X* tot_out, G1X* run_out) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= total_chunks) return;
-    const G1X* b = bucket_sums + (size_t)j * RED_M;
+    const G1X* b = X + (size_t)j * m;
     G1X run = g1x_identity(), tot = g1x_identity();
-    for (int i = RED_M - 1; i >= 0; --i) {
+    for (int i = (int)m - 1; i >= 0; --i) {
         run = g1x_add(run, g1x_load(b + i));
         tot = g1x_add(tot, run);
     }
-    g1x_store(chunk_out + j, tot);                 // sum (i+1)·B[jm+i]
-    g1x_store(chunk_out + total_chunks + j, run);  // sum B
+    g1x_store(tot_out + j, tot);
+    g1x_store(run_out + j, run);
 }
-// contribution of chunk j inside its window: tot + (j_in_window·m)·run ; then tree-sum per window (one block each)
-__global__ void __launch_bounds__(256) msm_reduce_window_kernel(const G1X* chunk_out, uint32_t total_chunks, uint32_t chunks_per_window, G1X* window_sums) {
-    __shared__ G1X sh[256];
-    const uint32_t w = blockIdx.x;
+// one block per (window, level): T[level·W + w] = Σ_q tot_level[w·len + q]
+struct SumLevels {
+    const G1X* tot[16];
+    uint32_t len[16];
+};
+__global__ void __launch_bounds__(128) msm_reduce_sum_kernel(SumLevels lv, uint32_t W, G1X* T) {
+    __shared__ G1X sh[128];
+    const uint32_t w = blockIdx.x, level = blockIdx.y;
+    const uint32_t len = lv.len[level];
+    const G1X* src = lv.tot[level] + (size_t)w * len;
     G1X acc = g1x_identity();
-    for (uint32_t j = threadIdx.x; j < chunks_per_window; j += blockDim.x) {
-        const uint32_t g = w * chunks_per_window + j;
-        G1X tot = g1x_load(chunk_out + g), run = g1x_load(chunk_out + total_chunks + g);
-        const uint32_t k = j * RED_M;
-        if (k) {
-            uint32_t bits = 32 - __clz(k);
-            tot = g1x_add(tot, g1x_mul_bits(run, &k, (int)bits));
-        }
-        acc = g1x_add(acc, tot);
-    }
+    for (uint32_t q = threadIdx.x; q < len; q += blockDim.x) acc = g1x_add(acc, g1x_load(src + q));
     sh[threadIdx.x] = acc;
     __syncthreads();
     for (uint32_t s = blockDim.x / 2; s > 0; s >>= 1) {
-        if (threadIdx.x < s) sh[threadIdx.x] = g1x_add(sh[threadIdx.x], sh[threadIdx.x + s]);
+        if (threadIdx.x < s && threadIdx.x + s < len) sh[threadIdx.x] = g1x_add(sh[threadIdx.x], sh[threadIdx.x + s]);
         __syncthreads();
     }
-    if (threadIdx.x == 0) g1x_store(window_sums + w, sh[0]);
+    if (threadIdx.x == 0) g1x_store(T + (size_t)level * W + w, sh[0]);
 }
+// one thread per window: Horner over the levels. S[w] = the single entry of the last run list.
+struct HornerLevels {
+    uint32_t log_m[16];
+    uint32_t levels;
+};
+__global__ void msm_reduce_horner_kernel(const G1X* T, const G1X* S, HornerLevels hl, uint32_t W, G1X* window_sums) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    const G1X s = g1x_load(S + w), neg_s = g1x_neg(s);
+    G1X a = s;
+    for (int l = (int)hl.levels - 1; l >= 0; --l) {
+        a = g1x_add(a, neg_s);
+        for (uint32_t d = 0; d < hl.log_m[l]; ++d) a = g1x_dbl(a);
+        a = g1x_add(a, g1x_load(T + (size_t)l * W + w));
+    }
+    g1x_store(window_sums + w, a);
+}
+
 // Σ 2^(c·w)·S_w on the host (64-bit limb path of the shared field code)
 G1X msm_fold_windows(const G1X* window_sums, uint32_t W, uint32_t c) {
     G1X acc = g1x_identity();
@@ -337,15 +356,39 @@ void msm_window_sums(Context& ctx, const G1Affine* bases, const Fr* scalars, siz
         len = nt;
         flip = !flip;
     }
-    // reduce
+    // reduce: recursive chunked running sums (see above)
     DevBuf<G1X> wsums(cfg.W, s);
-    if (cfg.B % RED_M != 0) throw std::runtime_error("msm: bucket count not a multiple of the reduce chunk");
-    const uint32_t cpw = cfg.B / RED_M, total_chunks = cfg.W * cpw;
-    DevBuf<G1X> chunk_out((size_t)2 * total_chunks, s);
-    msm_reduce_chunks_kernel<<<(total_chunks + 127) / 128, 128, 0, s>>>(bucket_sums.get(), total_chunks, chunk_out.get());
-    msm_reduce_window_kernel<<<cfg.W, 256, 0, s>>>(chunk_out.get(), total_chunks, cpw, wsums.get());
-    g_launch_count += 2;
-    CUDA_CHECK(cudaGetLastError());
+    {
+        std::vector<DevBuf<G1X>> tots, runs;
+        SumLevels sl{};
+        HornerLevels hl{};
+        const G1X* X = bucket_sums.get();
+        uint32_t len = cfg.B, level = 0;
+        while (len > 1) {
+            const uint32_t lm = len >= (1u << RED_LOG_M) ? RED_LOG_M : (uint32_t)__builtin_ctz(len);
+            const uint32_t m = 1u << lm, out_len = len >> lm, total_chunks = cfg.W * out_len;
+            tots.emplace_back((size_t)total_chunks, s);
+            runs.emplace_back((size_t)total_chunks, s);
+            msm_reduce_chunks_kernel<<<(total_chunks + 127) / 128, 128, 0, s>>>(X, total_chunks, m, tots.back().get(), runs.back().get());
+            ++g_launch_count;
+            sl.tot[level] = tots.back().get();
+            sl.len[level] = out_len;
+            hl.log_m[level] = lm;
+            X = runs.back().get();
+            len = out_len;
+            ++level;
+        }
+        hl.levels = level;
+        if (level == 0) {  // one bucket per window: F(B) = B[0]
+            CUDA_CHECK(cudaMemcpyAsync(wsums.get(), bucket_sums.get(), cfg.W * sizeof(G1X), cudaMemcpyDeviceToDevice, s));
+        } else {
+            DevBuf<G1X> T((size_t)level * cfg.W, s);
+            msm_reduce_sum_kernel<<<dim3(cfg.W, level), 128, 0, s>>>(sl, cfg.W, T.get());
+            msm_reduce_horner_kernel<<<(cfg.W + 31) / 32, 32, 0, s>>>(T.get(), X, hl, cfg.W, wsums.get());
+            g_launch_count += 2;
+        }
+        CUDA_CHECK(cudaGetLastError());
+    }
     CUDA_CHECK(cudaMemcpyAsync(window_sums_host.data(), wsums.get(), cfg.W * sizeof(G1X), cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
 }

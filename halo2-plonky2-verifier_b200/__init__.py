@@ -46,6 +46,8 @@ def lib():
         _lib.b200zk_last_error.restype = ctypes.c_char_p
         _lib.b200zk_stream.restype = ctypes.c_void_p
         _lib.b200zk_launch_count.restype = ctypes.c_ulonglong
+        _lib.b200zk_proof_size.restype = ctypes.c_size_t
+        _lib.b200zk_synth_max_copies.restype = ctypes.c_size_t
     return _lib
 
 
@@ -204,3 +206,86 @@ class Context:
         out = np.empty(8, dtype=np.uint64)
         self._check(lib().b200zk_msm_bases_dev(self._h, ctypes.c_void_p(bases_ptr), ctypes.c_void_p(scalars_ptr), ctypes.c_size_t(n), _p(out)))
         return out
+
+    # ---- rows J, E-I: keygen + create_proof ----
+    def keygen(self, k, A, L, F, fixed, copies):
+        """plonk::keygen_vk + keygen_pk for the halo2-base shape; returns a device-resident ProvingKey."""
+        return ProvingKey(self, k, A, L, F, fixed, copies)
+
+
+TIMING_KEYS = ("upload", "msm", "ntt", "lookup", "products", "quotient", "evals", "shplonk", "other")
+
+
+class ProvingKey:
+    """halo2_proofs::plonk::ProvingKey (device-resident columns, host-side vk commitments)."""
+
+    def __init__(self, ctx, k, A, L, F, fixed, copies):
+        self.ctx, self.shape = ctx, (k, A, L, F)
+        fixed = _c(fixed)
+        copies = np.ascontiguousarray(copies, dtype=np.uint32).reshape(-1, 4)
+        assert fixed.size == (F + 1 + A) * (1 << k) * 4
+        self._h = ctypes.c_void_p()
+        ctx._check(lib().b200zk_keygen(ctx._h, k, A, L, F, _p(fixed), _p(copies), ctypes.c_size_t(len(copies)), ctypes.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) and self.ctx._h:
+            lib().b200zk_pk_free(self.ctx._h, self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def commitments(self):
+        k, A, L, F = self.shape
+        fc = np.empty((F + 1 + A, 8), dtype=np.uint64)
+        pc = np.empty((F + A + L, 8), dtype=np.uint64)
+        self.ctx._check(lib().b200zk_pk_commitments(self.ctx._h, self._h, _p(fc), _p(pc)))
+        return fc, pc
+
+    def transcript_repr(self, set_to=None):
+        out = np.empty(4, dtype=np.uint64)
+        st = _c(set_to) if set_to is not None else None
+        self.ctx._check(lib().b200zk_pk_transcript_repr(self.ctx._h, self._h, _p(out), _p(st)))
+        return out
+
+    def get_column(self, which, idx):
+        n = 1 << self.shape[0]
+        out = np.empty((n if which == 0 else 4 * n, 4), dtype=np.uint64)
+        self.ctx._check(lib().b200zk_pk_get_column(self.ctx._h, self._h, which, idx, _p(out)))
+        return out
+
+    def proof_size(self):
+        return int(lib().b200zk_proof_size(*self.shape))
+
+    def create_proof(self, advice, rng_seed=0, timings=False):
+        """plonk::create_proof with StdRng::seed_from_u64(rng_seed) and a Blake2b transcript; returns the proof bytes."""
+        k, A, L, F = self.shape
+        advice = _c(advice)
+        assert advice.size == (A + L) * (1 << k) * 4
+        buf = np.empty(self.proof_size(), dtype=np.uint8)
+        plen = ctypes.c_size_t(0)
+        tm = np.zeros(9, dtype=np.float64)
+        self.ctx._check(lib().b200zk_create_proof(self.ctx._h, self._h, _p(advice), ctypes.c_uint64(rng_seed), _p(buf), ctypes.byref(plen),
+                                                  _p(tm) if timings else None))
+        proof = buf[: plen.value].tobytes()
+        if timings:
+            return proof, dict(zip(TIMING_KEYS, tm.tolist()))
+        return proof
+
+
+def synth_circuit(k, A, L, F, seed=0):
+    """Host-only generator of a satisfying circuit of the halo2-base shape (see csrc/synth.cu): returns
+    (fixed [F+1+A, n, 4], advice [A+L, n, 4], copies [m, 4])."""
+    n = 1 << k
+    fixed = np.empty((F + 1 + A, n, 4), dtype=np.uint64)
+    advice = np.empty((A + L, n, 4), dtype=np.uint64)
+    maxc = int(lib().b200zk_synth_max_copies(k, A, L, F))
+    copies = np.empty((maxc, 4), dtype=np.uint32)
+    nc = ctypes.c_size_t(0)
+    rc = lib().b200zk_synth_circuit(k, A, L, F, ctypes.c_uint64(seed), _p(fixed), _p(advice), _p(copies), ctypes.byref(nc))
+    if rc != OK:
+        raise B200zkError(rc, "synth_circuit failed")
+    return fixed, advice, copies[: nc.value].copy()

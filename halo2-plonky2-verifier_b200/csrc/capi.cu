@@ -1,7 +1,7 @@
 // extern "C" surface of libb200zk (include/b200zk.h): argument checking, error mapping, host<->device staging.
 #include "../../include/b200zk.h"
 
-#include "context.cuh"
+#include "prover.cuh"
 
 using namespace b200zk;
 
@@ -23,6 +23,10 @@ struct b200zk_ctx {
     catch (const CudaError& e) {            \
         (ctx)->c.last_error = e.what();     \
         return B200ZK_ECUDA;                \
+    }                                       \
+    catch (const SynthesisError& e) {       \
+        (ctx)->c.last_error = e.what();     \
+        return B200ZK_ESYNTH;               \
     }                                       \
     catch (const std::invalid_argument& e) {\
         (ctx)->c.last_error = e.what();     \
@@ -362,6 +366,78 @@ int b200zk_msm_bases(b200zk_ctx* ctx, const b200zk_g1_affine* bases, const b200z
     }
     G1Affine r = msm_run(c, b.get(), d.get(), n);
     memcpy(out, &r, 64);
+    API_END(ctx)
+}
+
+}  // extern "C"
+
+// ---- keygen / create_proof ------------------------------------------------------------------------------------------
+struct b200zk_pk {
+    std::unique_ptr<ProvingKeyDev> pk;
+};
+
+extern "C" {
+
+int b200zk_keygen(b200zk_ctx* ctx, uint32_t k, uint32_t A, uint32_t L, uint32_t F, const b200zk_fr* fixed, const uint32_t* copies, size_t ncopies,
+                  b200zk_pk** out) {
+    API_BEGIN(ctx)
+    if (!fixed || !out || (ncopies && !copies)) throw std::invalid_argument("keygen: null argument");
+    Shape sh{k, A, L, F};
+    auto pk = keygen(ctx->c, sh, (const Fr*)fixed, copies, ncopies);
+    *out = new b200zk_pk{std::move(pk)};
+    API_END(ctx)
+}
+int b200zk_pk_free(b200zk_ctx* ctx, b200zk_pk* pk) {
+    API_BEGIN(ctx)
+    delete pk;
+    API_END(ctx)
+}
+int b200zk_pk_commitments(b200zk_ctx* ctx, const b200zk_pk* pk, b200zk_g1_affine* fixed_out, b200zk_g1_affine* perm_out) {
+    API_BEGIN(ctx)
+    if (!pk) throw std::invalid_argument("null pk");
+    if (fixed_out) memcpy(fixed_out, pk->pk->fixed_commitments.data(), 64 * pk->pk->fixed_commitments.size());
+    if (perm_out) memcpy(perm_out, pk->pk->perm_commitments.data(), 64 * pk->pk->perm_commitments.size());
+    API_END(ctx)
+}
+int b200zk_pk_transcript_repr(b200zk_ctx* ctx, b200zk_pk* pk, b200zk_fr* get_out, const b200zk_fr* set_in) {
+    API_BEGIN(ctx)
+    if (!pk) throw std::invalid_argument("null pk");
+    if (set_in) memcpy(pk->pk->transcript_repr.l, set_in->l, 32);
+    if (get_out) memcpy(get_out->l, pk->pk->transcript_repr.l, 32);
+    API_END(ctx)
+}
+int b200zk_pk_get_column(b200zk_ctx* ctx, const b200zk_pk* pk, int which, uint32_t idx, b200zk_fr* out) {
+    API_BEGIN(ctx)
+    if (!pk || !out) throw std::invalid_argument("null argument");
+    const ProvingKeyDev& p = *pk->pk;
+    const size_t n = p.shape.n(), en = 4 * n;
+    const Fr* src = nullptr;
+    size_t len = 0;
+    switch (which) {
+        case 0: if (idx < p.shape.num_perm()) { src = p.sigma_values.get() + (size_t)idx * n; len = n; } break;
+        case 1: if (idx < p.shape.num_fixed()) { src = p.fixed_cosets.get() + (size_t)idx * en; len = en; } break;
+        case 2: if (idx < p.shape.num_perm()) { src = p.sigma_cosets.get() + (size_t)idx * en; len = en; } break;
+        case 3: if (idx < 3) { src = p.l_polys.get() + (size_t)idx * en; len = en; } break;
+    }
+    if (!src) throw std::invalid_argument("pk_get_column: bad selector");
+    CUDA_CHECK(cudaMemcpyAsync(out, src, len * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->c.stream));
+    API_END(ctx)
+}
+size_t b200zk_proof_size(uint32_t k, uint32_t A, uint32_t L, uint32_t F) { return Shape{k, A, L, F}.proof_size(); }
+int b200zk_create_proof(b200zk_ctx* ctx, const b200zk_pk* pk, const b200zk_fr* advice, uint64_t rng_seed, uint8_t* proof_out, size_t* proof_len,
+                        double* timings) {
+    API_BEGIN(ctx)
+    if (!pk || !advice || !proof_out || !proof_len) throw std::invalid_argument("create_proof: null argument");
+    host::FrRandomStream rng = host::FrRandomStream::std_rng_seed_from_u64(rng_seed);
+    ProofTimings tm;
+    std::vector<uint8_t> proof = create_proof(ctx->c, *pk->pk, (const Fr*)advice, rng, timings ? &tm : nullptr);
+    memcpy(proof_out, proof.data(), proof.size());
+    *proof_len = proof.size();
+    if (timings) {
+        const double t[9] = {tm.upload, tm.msm, tm.ntt, tm.lookup, tm.products, tm.quotient, tm.evals, tm.shplonk, tm.other};
+        memcpy(timings, t, sizeof(t));
+    }
     API_END(ctx)
 }
 

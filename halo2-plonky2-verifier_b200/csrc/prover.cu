@@ -1,0 +1,636 @@
+// Device-resident mirror of halo2_proofs::plonk::{keygen_vk, keygen_pk, create_proof} with the KZG / SHPLONK
+// backend for the ConstraintSystem of halo2-base's BaseConfig (SURVEY.md §3.2, Appendix B, D.3–D.12). This is the
+// path the reference drives through `base_test().k(k).bench_builder(..)` at verifier/src/stark/mod.rs:543 and :593.
+//
+// Every column stays in HBM between steps; only commitments (64 B), evaluations (32 B) and challenges cross the
+// PCIe bus after the witness upload. The transcript and the Fr::random stream are host-side (row L), exactly as in
+// the reference; everything else is a launch of the kernels in ntt.cu / msm.cu / poly.cu / quotient.cu.
+#include "prover.cuh"
+
+#include <algorithm>
+#include <chrono>
+
+namespace b200zk {
+
+G1Affine msm_run(Context& ctx, const G1Affine* bases, const Fr* scalars, size_t n);
+
+static const Srs& need_srs(Context& ctx, uint32_t k) {
+    if (!ctx.srs) throw std::runtime_error("no SRS loaded");
+    if (ctx.srs->k != k) throw std::runtime_error("SRS size does not match the circuit (k)");
+    return *ctx.srs;
+}
+static G1Affine commit_lagrange(Context& ctx, const Fr* evals, size_t n) { return msm_run(ctx, ctx.srs->g_lagrange.get(), evals, n); }
+static G1Affine commit_coeff(Context& ctx, const Fr* coeffs, size_t n) { return msm_run(ctx, ctx.srs->g.get(), coeffs, n); }
+
+// ---- permutation::keygen::Assembly (host, serial — as upstream) ------------------------------------------------------
+struct Assembly {
+    size_t n;
+    uint32_t p;
+    std::vector<uint32_t> map_col, map_row, aux_col, aux_row, sizes;  // [p][n] flattened
+    Assembly(size_t n_, uint32_t p_) : n(n_), p(p_), map_col(n_ * p_), map_row(n_ * p_), aux_col(n_ * p_), aux_row(n_ * p_), sizes(n_ * p_, 1) {
+        for (uint32_t c = 0; c < p; ++c)
+            for (size_t r = 0; r < n; ++r) {
+                map_col[c * n + r] = aux_col[c * n + r] = c;
+                map_row[c * n + r] = aux_row[c * n + r] = (uint32_t)r;
+            }
+    }
+    void copy(uint32_t lc, uint32_t lr, uint32_t rc, uint32_t rr) {
+        if (lc >= p || rc >= p || lr >= n || rr >= n) throw std::invalid_argument("copy constraint out of range");
+        size_t li = lc * n + lr, ri = rc * n + rr;
+        uint32_t lcc = aux_col[li], lcr = aux_row[li], rcc = aux_col[ri], rcr = aux_row[ri];
+        if (lcc == rcc && lcr == rcr) return;
+        if (sizes[lcc * n + lcr] < sizes[rcc * n + rcr]) {
+            std::swap(lcc, rcc);
+            std::swap(lcr, rcr);
+        }
+        sizes[lcc * n + lcr] += sizes[rcc * n + rcr];
+        uint32_t ic = rcc, ir = rcr;
+        for (;;) {
+            size_t ii = ic * n + ir;
+            aux_col[ii] = lcc;
+            aux_row[ii] = lcr;
+            uint32_t nc = map_col[ii], nr = map_row[ii];
+            ic = nc;
+            ir = nr;
+            if (ic == rcc && ir == rcr) break;
+        }
+        std::swap(map_col[li], map_col[ri]);
+        std::swap(map_row[li], map_row[ri]);
+    }
+};
+
+// [UNVERIFIED-5 of SURVEY §8c] stand-in for upstream's Debug-string hash; same bytes as the oracle's rendering.
+static Fr default_transcript_repr(const ProvingKeyDev& pk) {
+    host::Blake2b512 h("Halo2-Verify-Key");
+    const Shape& sh = pk.shape;
+    std::string s = "b200zk-vk k=" + std::to_string(sh.k) + " A=" + std::to_string(sh.A) + " L=" + std::to_string(sh.L) + " F=" + std::to_string(sh.F);
+    uint64_t len = s.size() + 64 * (pk.fixed_commitments.size() + pk.perm_commitments.size());
+    h.absorb(&len, 8);
+    h.absorb(s.data(), s.size());
+    auto absorb = [&](const G1Affine& p) {
+        uint8_t b[64];
+        host::field_to_bytes(p.x, b);
+        host::field_to_bytes(p.y, b + 32);
+        h.absorb(b, 64);
+    };
+    for (auto& p : pk.fixed_commitments) absorb(p);
+    for (auto& p : pk.perm_commitments) absorb(p);
+    uint8_t d[64];
+    h.peek(d);
+    uint32_t w[16];
+    memcpy(w, d, 64);
+    return f_from_u512<FrCfg>(w);
+}
+
+std::unique_ptr<ProvingKeyDev> keygen(Context& ctx, const Shape& sh, const Fr* fixed_host, const uint32_t* copies, size_t ncopies) {
+    if (sh.k < 4 || sh.k + 2 > FrConsts::S || sh.A == 0) throw std::invalid_argument("keygen: unsupported shape");
+    if (sh.num_advice() > Q_MAX_ADVICE || sh.num_fixed() > Q_MAX_FIXED || sh.num_perm() > Q_MAX_PERM || sh.num_sets() > Q_MAX_SETS)
+        throw std::invalid_argument("keygen: too many columns for the h(X) kernel argument block");
+    need_srs(ctx, sh.k);
+    cudaStream_t s = ctx.stream;
+    const size_t n = sh.n(), en = 4 * n;
+    const Domain& dom = ctx.domain(sh.k);
+    const TwiddleTable& tw = ctx.std_table(sh.k + 2);
+    auto pk = std::make_unique<ProvingKeyDev>();
+    pk->shape = sh;
+    const uint32_t NF = sh.num_fixed(), P = sh.num_perm();
+    // fixed columns
+    pk->fixed_values.alloc((size_t)NF * n, s);
+    CUDA_CHECK(cudaMemcpyAsync(pk->fixed_values.get(), fixed_host, (size_t)NF * n * sizeof(Fr), cudaMemcpyHostToDevice, s));
+    // sigma columns from the copy-constraint cycles
+    pk->sigma_values.alloc((size_t)P * n, s);
+    {
+        Assembly as(n, P);
+        for (size_t i = 0; i < ncopies; ++i) as.copy(copies[4 * i], copies[4 * i + 1], copies[4 * i + 2], copies[4 * i + 3]);
+        DevBuf<uint32_t> mc((size_t)P * n, s), mr((size_t)P * n, s);
+        CUDA_CHECK(cudaMemcpyAsync(mc.get(), as.map_col.data(), (size_t)P * n * 4, cudaMemcpyHostToDevice, s));
+        CUDA_CHECK(cudaMemcpyAsync(mr.get(), as.map_row.data(), (size_t)P * n * 4, cudaMemcpyHostToDevice, s));
+        std::vector<Fr> dp(P);
+        dp[0] = f_one<FrCfg>();
+        for (uint32_t j = 1; j < P; ++j) dp[j] = f_mul(dp[j - 1], FrConsts::delta());
+        DevBuf<Fr> dpd(P, s);
+        CUDA_CHECK(cudaMemcpyAsync(dpd.get(), dp.data(), P * sizeof(Fr), cudaMemcpyHostToDevice, s));
+        for (uint32_t j = 0; j < P; ++j)
+            sigma_from_mapping(pk->sigma_values.get() + (size_t)j * n, mc.get() + (size_t)j * n, mr.get() + (size_t)j * n, dpd.get(), tw.t.get(),
+                               tw.log_n, sh.k, s);
+        CUDA_CHECK(cudaStreamSynchronize(s));  // host staging vectors go out of scope
+    }
+    // keygen_vk: commitments (Lagrange basis, no blinding)
+    for (uint32_t i = 0; i < NF; ++i) pk->fixed_commitments.push_back(commit_lagrange(ctx, pk->fixed_values.get() + (size_t)i * n, n));
+    for (uint32_t j = 0; j < P; ++j) pk->perm_commitments.push_back(commit_lagrange(ctx, pk->sigma_values.get() + (size_t)j * n, n));
+    pk->transcript_repr = default_transcript_repr(*pk);
+    // keygen_pk: coefficient forms and extended cosets
+    pk->fixed_polys.alloc((size_t)NF * n, s);
+    pk->sigma_polys.alloc((size_t)P * n, s);
+    CUDA_CHECK(cudaMemcpyAsync(pk->fixed_polys.get(), pk->fixed_values.get(), (size_t)NF * n * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
+    CUDA_CHECK(cudaMemcpyAsync(pk->sigma_polys.get(), pk->sigma_values.get(), (size_t)P * n * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
+    for (uint32_t i = 0; i < NF; ++i) dev_lagrange_to_coeff(ctx, sh.k, pk->fixed_polys.get() + (size_t)i * n);
+    for (uint32_t j = 0; j < P; ++j) dev_lagrange_to_coeff(ctx, sh.k, pk->sigma_polys.get() + (size_t)j * n);
+    pk->fixed_cosets.alloc((size_t)NF * en, s);
+    pk->sigma_cosets.alloc((size_t)P * en, s);
+    for (uint32_t i = 0; i < NF; ++i) dev_coeff_to_extended(ctx, sh.k, pk->fixed_polys.get() + (size_t)i * n, pk->fixed_cosets.get() + (size_t)i * en);
+    for (uint32_t j = 0; j < P; ++j) dev_coeff_to_extended(ctx, sh.k, pk->sigma_polys.get() + (size_t)j * n, pk->sigma_cosets.get() + (size_t)j * en);
+    // l0, l_last, l_active_row = 1 - l_last - l_blind on the extended domain
+    {
+        pk->l_polys.alloc(3 * en, s);
+        DevBuf<Fr> tmp(3 * n, s);
+        CUDA_CHECK(cudaMemsetAsync(tmp.get(), 0, 3 * n * sizeof(Fr), s));
+        const Fr one = f_one<FrCfg>();
+        const uint32_t bf = Shape::blinding_factors;
+        fr_fill(tmp.get(), one, 1, s);                              // l0: row 0
+        fr_fill(tmp.get() + n + (n - bf - 1), one, 1, s);           // l_last: row n-bf-1
+        fr_fill(tmp.get() + 2 * n + (n - bf), one, bf, s);          // l_blind: rows n-bf..n-1
+        for (int j = 0; j < 3; ++j) {
+            dev_lagrange_to_coeff(ctx, sh.k, tmp.get() + (size_t)j * n);
+            dev_coeff_to_extended(ctx, sh.k, tmp.get() + (size_t)j * n, pk->l_polys.get() + (size_t)j * en);
+        }
+        // l_active = 1 - l_last - l_blind, written over the l_blind slot
+        std::vector<const Fr*> ps = {pk->l_polys.get() + en, pk->l_polys.get() + 2 * en};
+        const Fr minus_one = f_neg(one);
+        DevBuf<Fr> act(en, s);
+        fr_fill(act.get(), one, en, s);
+        fr_lincomb(act.get(), ps, {minus_one, minus_one}, en, true, s);
+        CUDA_CHECK(cudaMemcpyAsync(pk->l_polys.get() + 2 * en, act.get(), en * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    (void)dom;
+    return pk;
+}
+
+// ---- SHPLONK bookkeeping (host) -----------------------------------------------------------------------------------------
+struct Query {
+    size_t poly;
+    Fr point, eval;
+};
+static int fr_cmp(const Fr& a, const Fr& b) {  // numeric order of the canonical integers
+    const Fr x = f_from_mont(a), y = f_from_mont(b);
+    for (int i = 7; i >= 0; --i)
+        if (x.l[i] != y.l[i]) return x.l[i] < y.l[i] ? -1 : 1;
+    return 0;
+}
+struct RotationSet {
+    std::vector<Fr> points;
+    std::vector<size_t> polys;
+    std::vector<std::vector<Fr>> evals;
+};
+static void sorted_insert(std::vector<Fr>& v, const Fr& x) {
+    size_t i = 0;
+    for (; i < v.size(); ++i) {
+        int c = fr_cmp(x, v[i]);
+        if (c == 0) return;
+        if (c < 0) break;
+    }
+    v.insert(v.begin() + i, x);
+}
+static bool same_points(const std::vector<Fr>& a, const std::vector<Fr>& b) {
+    if (a.size() != b.size()) return false;
+    for (size_t i = 0; i < a.size(); ++i)
+        if (!f_eq(a[i], b[i])) return false;
+    return true;
+}
+static void construct_intermediate_sets(const std::vector<Query>& queries, std::vector<RotationSet>& sets, std::vector<Fr>& super) {
+    std::vector<std::pair<size_t, std::vector<Fr>>> by_poly;
+    for (auto& q : queries) {
+        sorted_insert(super, q.point);
+        bool found = false;
+        for (auto& e : by_poly)
+            if (e.first == q.poly) {
+                sorted_insert(e.second, q.point);
+                found = true;
+                break;
+            }
+        if (!found) by_poly.push_back({q.poly, {q.point}});
+    }
+    for (auto& e : by_poly) {
+        bool found = false;
+        for (auto& rs : sets)
+            if (same_points(rs.points, e.second)) {
+                rs.polys.push_back(e.first);
+                found = true;
+                break;
+            }
+        if (!found) {
+            RotationSet rs;
+            rs.points = e.second;
+            rs.polys.push_back(e.first);
+            sets.push_back(rs);
+        }
+    }
+    for (auto& rs : sets)
+        for (size_t id : rs.polys) {
+            std::vector<Fr> ev;
+            for (auto& pt : rs.points) {
+                bool ok = false;
+                for (auto& q : queries)
+                    if (q.poly == id && f_eq(q.point, pt)) {
+                        ev.push_back(q.eval);
+                        ok = true;
+                        break;
+                    }
+                if (!ok) throw std::runtime_error("shplonk: missing evaluation");
+            }
+            rs.evals.push_back(ev);
+        }
+}
+static std::vector<Fr> lagrange_interpolate(const std::vector<Fr>& pts, const std::vector<Fr>& evals) {
+    const size_t m = pts.size();
+    std::vector<Fr> res(m, f_zero<FrCfg>());
+    for (size_t j = 0; j < m; ++j) {
+        std::vector<Fr> num(1, f_one<FrCfg>());
+        Fr denom = f_one<FrCfg>();
+        for (size_t i = 0; i < m; ++i) {
+            if (i == j) continue;
+            std::vector<Fr> nx(num.size() + 1, f_zero<FrCfg>());
+            for (size_t t = 0; t < num.size(); ++t) {
+                nx[t + 1] = f_add(nx[t + 1], num[t]);
+                nx[t] = f_sub(nx[t], f_mul(num[t], pts[i]));
+            }
+            num = nx;
+            denom = f_mul(denom, f_sub(pts[j], pts[i]));
+        }
+        const Fr sc = f_mul(evals[j], f_inv(denom));
+        for (size_t t = 0; t < num.size(); ++t) res[t] = f_add(res[t], f_mul(num[t], sc));
+    }
+    return res;
+}
+static Fr eval_small(const std::vector<Fr>& p, const Fr& x) {
+    Fr acc = f_zero<FrCfg>();
+    for (size_t i = p.size(); i-- > 0;) acc = f_add(f_mul(acc, x), p[i]);
+    return acc;
+}
+static Fr vanishing_eval(const std::vector<Fr>& roots, const Fr& z) {
+    Fr r = f_one<FrCfg>();
+    for (auto& x : roots) r = f_mul(r, f_sub(z, x));
+    return r;
+}
+
+// ---- create_proof ---------------------------------------------------------------------------------------------------------
+std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const Fr* advice_host, host::FrRandomStream& rng, ProofTimings* tm) {
+    const Shape& sh = pk.shape;
+    need_srs(ctx, sh.k);
+    cudaStream_t s = ctx.stream;
+    const size_t n = sh.n(), en = 4 * n, u = sh.usable_rows();
+    const uint32_t bf = Shape::blinding_factors, NA = sh.num_advice(), A = sh.A, L = sh.L, F = sh.F, P = sh.num_perm(), NS = sh.num_sets();
+    const Domain& dom = ctx.domain(sh.k);
+    const TwiddleTable& tw = ctx.std_table(sh.k + 2);
+    host::Transcript tr;
+    auto clock_now = [&]() {
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        return std::chrono::steady_clock::now();
+    };
+    auto t_start = clock_now();
+    auto lap = [&](double* slot) {
+        if (!tm) return;
+        auto t = clock_now();
+        *slot += std::chrono::duration<double>(t - t_start).count();
+        t_start = t;
+    };
+    const Fr one = f_one<FrCfg>();
+
+    // step 0
+    tr.common_scalar(pk.transcript_repr);
+    // step 1: upload, blind, commit advice (D.3)
+    DevBuf<Fr> advice((size_t)NA * n, s);
+    CUDA_CHECK(cudaMemcpyAsync(advice.get(), advice_host, (size_t)NA * n * sizeof(Fr), cudaMemcpyHostToDevice, s));
+    {
+        std::vector<Fr> blind((size_t)NA * (bf + 1));
+        for (auto& b : blind) b = rng.next();
+        for (uint32_t c = 0; c < NA; ++c)
+            CUDA_CHECK(cudaMemcpyAsync(advice.get() + (size_t)c * n + u, blind.data() + (size_t)c * (bf + 1), (bf + 1) * sizeof(Fr),
+                                       cudaMemcpyHostToDevice, s));
+        rng.skip(NA);  // Blind(..) per column: drawn upstream, unused by KZG commitments
+        CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+    lap(tm ? &tm->upload : nullptr);
+    for (uint32_t c = 0; c < NA; ++c) tr.write_point(commit_lagrange(ctx, advice.get() + (size_t)c * n, n));
+    lap(tm ? &tm->msm : nullptr);
+    const Fr theta = tr.squeeze_challenge();
+    (void)theta;  // single-expression lookups: theta-compression is the identity
+    // step 3: lookups, permuted columns (D.4)
+    const Fr* table_values = pk.fixed_values.get() + (size_t)sh.table_col() * n;
+    DevBuf<Fr> perm_in((size_t)L * n, s), perm_tab((size_t)L * n, s), perm_in_poly((size_t)L * n, s), perm_tab_poly((size_t)L * n, s);
+    for (uint32_t l = 0; l < L; ++l) {
+        Fr* a_out = perm_in.get() + (size_t)l * n;
+        Fr* s_out = perm_tab.get() + (size_t)l * n;
+        if (!lookup_permute(ctx, advice.get() + (size_t)(A + l) * n, table_values, a_out, s_out, n, u))
+            throw SynthesisError("ConstraintSystemFailure: lookup input not in table");
+        std::vector<Fr> blind(2 * (bf + 1));
+        for (auto& b : blind) b = rng.next();
+        CUDA_CHECK(cudaMemcpyAsync(a_out + u, blind.data(), (bf + 1) * sizeof(Fr), cudaMemcpyHostToDevice, s));
+        CUDA_CHECK(cudaMemcpyAsync(s_out + u, blind.data() + bf + 1, (bf + 1) * sizeof(Fr), cudaMemcpyHostToDevice, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        lap(tm ? &tm->lookup : nullptr);
+        rng.skip(1);
+        const G1Affine ca = commit_lagrange(ctx, a_out, n);
+        rng.skip(1);
+        const G1Affine cs = commit_lagrange(ctx, s_out, n);
+        lap(tm ? &tm->msm : nullptr);
+        CUDA_CHECK(cudaMemcpyAsync(perm_in_poly.get() + (size_t)l * n, a_out, n * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
+        CUDA_CHECK(cudaMemcpyAsync(perm_tab_poly.get() + (size_t)l * n, s_out, n * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
+        dev_lagrange_to_coeff(ctx, sh.k, perm_in_poly.get() + (size_t)l * n);
+        dev_lagrange_to_coeff(ctx, sh.k, perm_tab_poly.get() + (size_t)l * n);
+        lap(tm ? &tm->ntt : nullptr);
+        tr.write_point(ca);
+        tr.write_point(cs);
+    }
+    const Fr beta = tr.squeeze_challenge();
+    const Fr gamma = tr.squeeze_challenge();
+    // step 5: permutation grand products (D.5)
+    auto perm_values = [&](uint32_t j) -> const Fr* {
+        return sh.perm_is_fixed(j) ? pk.fixed_values.get() + (size_t)sh.perm_col_index(j) * n : advice.get() + (size_t)sh.perm_col_index(j) * n;
+    };
+    DevBuf<Fr> z_polys((size_t)NS * n, s), z_cosets((size_t)NS * en, s);
+    {
+        DevBuf<Fr> m(n, s), z(n, s);
+        Fr delta_pow = one, last_z = one;
+        for (uint32_t set = 0; set < NS; ++set) {
+            const uint32_t j0 = set * Shape::chunk_len, j1 = std::min(P, j0 + Shape::chunk_len);
+            for (uint32_t j = j0; j < j1; ++j) perm_denominator(m.get(), perm_values(j), pk.sigma_values.get() + (size_t)j * n, beta, gamma, n, j == j0, s);
+            fr_batch_invert(m.get(), n, s);
+            for (uint32_t j = j0; j < j1; ++j) {
+                perm_numerator(m.get(), perm_values(j), f_mul(delta_pow, beta), gamma, tw.t.get(), tw.log_n, sh.k, s);
+                delta_pow = f_mul(delta_pow, FrConsts::delta());
+            }
+            fr_prefix_product(z.get(), m.get(), last_z, n, s);
+            std::vector<Fr> blind(bf);
+            for (auto& b : blind) b = rng.next();
+            CUDA_CHECK(cudaMemcpyAsync(z.get() + (n - bf), blind.data(), bf * sizeof(Fr), cudaMemcpyHostToDevice, s));
+            CUDA_CHECK(cudaMemcpyAsync(&last_z, z.get() + (n - bf - 1), sizeof(Fr), cudaMemcpyDeviceToHost, s));
+            CUDA_CHECK(cudaStreamSynchronize(s));
+            rng.skip(1);
+            lap(tm ? &tm->products : nullptr);
+            const G1Affine cm = commit_lagrange(ctx, z.get(), n);
+            lap(tm ? &tm->msm : nullptr);
+            Fr* zp = z_polys.get() + (size_t)set * n;
+            CUDA_CHECK(cudaMemcpyAsync(zp, z.get(), n * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
+            dev_lagrange_to_coeff(ctx, sh.k, zp);
+            dev_coeff_to_extended(ctx, sh.k, zp, z_cosets.get() + (size_t)set * en);
+            lap(tm ? &tm->ntt : nullptr);
+            tr.write_point(cm);
+        }
+    }
+    // step 6: lookup grand products (D.6)
+    DevBuf<Fr> lk_z_poly((size_t)L * n, s);
+    {
+        DevBuf<Fr> p(n, s);
+        for (uint32_t l = 0; l < L; ++l) {
+            Fr* z = lk_z_poly.get() + (size_t)l * n;
+            lookup_denominator(p.get(), perm_in.get() + (size_t)l * n, perm_tab.get() + (size_t)l * n, beta, gamma, n, s);
+            fr_batch_invert(p.get(), n, s);
+            lookup_numerator(p.get(), advice.get() + (size_t)(A + l) * n, table_values, beta, gamma, n, s);
+            fr_prefix_product(z, p.get(), one, n, s);
+            std::vector<Fr> blind(bf);
+            for (auto& b : blind) b = rng.next();
+            CUDA_CHECK(cudaMemcpyAsync(z + (n - bf), blind.data(), bf * sizeof(Fr), cudaMemcpyHostToDevice, s));
+            CUDA_CHECK(cudaStreamSynchronize(s));
+            rng.skip(1);
+            lap(tm ? &tm->products : nullptr);
+            const G1Affine cm = commit_lagrange(ctx, z, n);
+            lap(tm ? &tm->msm : nullptr);
+            dev_lagrange_to_coeff(ctx, sh.k, z);
+            lap(tm ? &tm->ntt : nullptr);
+            tr.write_point(cm);
+        }
+    }
+    // step 7: vanishing::commit (D.7): n sequential Fr::random draws = n consecutive ChaCha blocks, generated in place
+    DevBuf<Fr> random_poly(n, s);
+    fr_random_stream(random_poly.get(), n, rng.key, rng.draws, rng.rounds, s);
+    rng.skip(n);
+    rng.skip(1);
+    lap(tm ? &tm->other : nullptr);
+    tr.write_point(commit_coeff(ctx, random_poly.get(), n));
+    lap(tm ? &tm->msm : nullptr);
+    const Fr y = tr.squeeze_challenge();
+    // step 8/9: advice polys + cosets, h(X) (D.8)
+    DevBuf<Fr> advice_polys((size_t)NA * n, s), advice_cosets((size_t)NA * en, s);
+    CUDA_CHECK(cudaMemcpyAsync(advice_polys.get(), advice.get(), (size_t)NA * n * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
+    for (uint32_t c = 0; c < NA; ++c) {
+        dev_lagrange_to_coeff(ctx, sh.k, advice_polys.get() + (size_t)c * n);
+        dev_coeff_to_extended(ctx, sh.k, advice_polys.get() + (size_t)c * n, advice_cosets.get() + (size_t)c * en);
+    }
+    lap(tm ? &tm->ntt : nullptr);
+    DevBuf<Fr> h(en, s);
+    {
+        QuotientArgs Q{};
+        Q.k = sh.k; Q.A = A; Q.L = L; Q.F = F; Q.P = P; Q.num_sets = NS; Q.blinding_factors = bf;
+        Q.table = tw.t.get();
+        Q.table_log = tw.log_n;
+        Q.t_inv = dom.t_inv_dev();
+        for (uint32_t c = 0; c < NA; ++c) Q.advice[c] = advice_cosets.get() + (size_t)c * en;
+        for (uint32_t i = 0; i < sh.num_fixed(); ++i) Q.fixed[i] = pk.fixed_cosets.get() + (size_t)i * en;
+        for (uint32_t j = 0; j < P; ++j) {
+            Q.perm_cols[j] = sh.perm_is_fixed(j) ? Q.fixed[sh.perm_col_index(j)] : Q.advice[sh.perm_col_index(j)];
+            Q.sigma[j] = pk.sigma_cosets.get() + (size_t)j * en;
+        }
+        for (uint32_t set = 0; set < NS; ++set) Q.z[set] = z_cosets.get() + (size_t)set * en;
+        Q.l0 = pk.l_polys.get();
+        Q.l_last = pk.l_polys.get() + en;
+        Q.l_active = pk.l_polys.get() + 2 * en;
+        Q.y = y; Q.beta = beta; Q.gamma = gamma; Q.delta = FrConsts::delta();
+        Q.beta_zeta = f_mul(beta, FrConsts::zeta());
+        h_gates(Q, h.get(), s);
+        h_permutation(Q, h.get(), L == 0, s);
+        lap(tm ? &tm->quotient : nullptr);
+        DevBuf<Fr> lc(3 * en, s);
+        for (uint32_t l = 0; l < L; ++l) {
+            dev_coeff_to_extended(ctx, sh.k, lk_z_poly.get() + (size_t)l * n, lc.get());
+            dev_coeff_to_extended(ctx, sh.k, perm_in_poly.get() + (size_t)l * n, lc.get() + en);
+            dev_coeff_to_extended(ctx, sh.k, perm_tab_poly.get() + (size_t)l * n, lc.get() + 2 * en);
+            lap(tm ? &tm->ntt : nullptr);
+            LookupCosets Lk{lc.get(), lc.get() + en, lc.get() + 2 * en, Q.advice[A + l], Q.fixed[sh.table_col()]};
+            h_lookup(Q, Lk, h.get(), l + 1 == L, s);
+            lap(tm ? &tm->quotient : nullptr);
+        }
+    }
+    // step 10: vanishing::construct (D.9) — t_inv scaling already applied by the last h kernel
+    DevBuf<Fr> h_coeff(3 * n, s);
+    dev_extended_to_coeff(ctx, sh.k, h.get(), h_coeff.get());
+    h.release();
+    lap(tm ? &tm->ntt : nullptr);
+    rng.skip(3);
+    for (uint32_t j = 0; j < 3; ++j) tr.write_point(commit_coeff(ctx, h_coeff.get() + (size_t)j * n, n));
+    lap(tm ? &tm->msm : nullptr);
+    const Fr x = tr.squeeze_challenge();
+    const Fr xn = f_pow_u64(x, n);
+    // step 11: evaluations (D.10)
+    const Fr x_next = dom.rotate_omega(x, 1), x_prev = dom.rotate_omega(x, -1), x_last = dom.rotate_omega(x, -(int)(bf + 1));
+    const Fr x_rot2 = dom.rotate_omega(x, 2), x_rot3 = dom.rotate_omega(x, 3);
+    // h_poly = sum_j xn^j h_j
+    DevBuf<Fr> h_poly(n, s);
+    fr_lincomb(h_poly.get(), {h_coeff.get(), h_coeff.get() + n, h_coeff.get() + 2 * n}, {one, xn, f_sqr(xn)}, n, false, s);
+    // poly table for SHPLONK
+    std::vector<const Fr*> polys;
+    auto add_poly = [&](const Fr* p) {
+        polys.push_back(p);
+        return polys.size() - 1;
+    };
+    std::vector<size_t> id_adv(NA), id_fixed(sh.num_fixed()), id_sigma(P), id_z(NS), id_lz(L), id_la(L), id_ls(L);
+    for (uint32_t c = 0; c < NA; ++c) id_adv[c] = add_poly(advice_polys.get() + (size_t)c * n);
+    for (uint32_t i = 0; i < sh.num_fixed(); ++i) id_fixed[i] = add_poly(pk.fixed_polys.get() + (size_t)i * n);
+    const size_t id_h = add_poly(h_poly.get()), id_rand = add_poly(random_poly.get());
+    for (uint32_t j = 0; j < P; ++j) id_sigma[j] = add_poly(pk.sigma_polys.get() + (size_t)j * n);
+    for (uint32_t set = 0; set < NS; ++set) id_z[set] = add_poly(z_polys.get() + (size_t)set * n);
+    for (uint32_t l = 0; l < L; ++l) {
+        id_lz[l] = add_poly(lk_z_poly.get() + (size_t)l * n);
+        id_la[l] = add_poly(perm_in_poly.get() + (size_t)l * n);
+        id_ls[l] = add_poly(perm_tab_poly.get() + (size_t)l * n);
+    }
+    // evaluate everything grouped by point
+    std::vector<Fr> ev_x(polys.size()), ev_next(polys.size()), ev_r2(A), ev_r3(A), ev_prev(L), ev_last(NS);
+    {
+        fr_eval_many(ctx, polys, n, x, ev_x.data());
+        std::vector<const Fr*> list;
+        std::vector<Fr> out;
+        // x_next: gate advice columns, permutation z, lookup z
+        for (uint32_t c = 0; c < A; ++c) list.push_back(polys[id_adv[c]]);
+        for (uint32_t set = 0; set < NS; ++set) list.push_back(polys[id_z[set]]);
+        for (uint32_t l = 0; l < L; ++l) list.push_back(polys[id_lz[l]]);
+        out.resize(list.size());
+        fr_eval_many(ctx, list, n, x_next, out.data());
+        for (uint32_t c = 0; c < A; ++c) ev_next[id_adv[c]] = out[c];
+        for (uint32_t set = 0; set < NS; ++set) ev_next[id_z[set]] = out[A + set];
+        for (uint32_t l = 0; l < L; ++l) ev_next[id_lz[l]] = out[A + NS + l];
+        list.clear();
+        for (uint32_t c = 0; c < A; ++c) list.push_back(polys[id_adv[c]]);
+        fr_eval_many(ctx, list, n, x_rot2, ev_r2.data());
+        fr_eval_many(ctx, list, n, x_rot3, ev_r3.data());
+        list.clear();
+        for (uint32_t l = 0; l < L; ++l) list.push_back(polys[id_la[l]]);
+        fr_eval_many(ctx, list, n, x_prev, ev_prev.data());
+        list.clear();
+        for (uint32_t set = 0; set + 1 < NS; ++set) list.push_back(polys[id_z[set]]);
+        fr_eval_many(ctx, list, n, x_last, ev_last.data());
+    }
+    std::vector<Query> q_advice, q_perm, q_lookup, q_fixed, q_sigma, q_vanish, queries;
+    for (uint32_t c = 0; c < NA; ++c) {
+        const size_t id = id_adv[c];
+        tr.write_scalar(ev_x[id]);
+        q_advice.push_back({id, x, ev_x[id]});
+        if (c < A) {
+            tr.write_scalar(ev_next[id]);
+            tr.write_scalar(ev_r2[c]);
+            tr.write_scalar(ev_r3[c]);
+            q_advice.push_back({id, x_next, ev_next[id]});
+            q_advice.push_back({id, x_rot2, ev_r2[c]});
+            q_advice.push_back({id, x_rot3, ev_r3[c]});
+        }
+    }
+    for (uint32_t i = 0; i < sh.num_fixed(); ++i) {
+        tr.write_scalar(ev_x[id_fixed[i]]);
+        q_fixed.push_back({id_fixed[i], x, ev_x[id_fixed[i]]});
+    }
+    tr.write_scalar(ev_x[id_rand]);
+    q_vanish.push_back({id_h, x, ev_x[id_h]});
+    q_vanish.push_back({id_rand, x, ev_x[id_rand]});
+    for (uint32_t j = 0; j < P; ++j) {
+        tr.write_scalar(ev_x[id_sigma[j]]);
+        q_sigma.push_back({id_sigma[j], x, ev_x[id_sigma[j]]});
+    }
+    {
+        std::vector<Query> lastq;
+        for (uint32_t set = 0; set < NS; ++set) {
+            const size_t id = id_z[set];
+            tr.write_scalar(ev_x[id]);
+            tr.write_scalar(ev_next[id]);
+            q_perm.push_back({id, x, ev_x[id]});
+            q_perm.push_back({id, x_next, ev_next[id]});
+            if (set + 1 != NS) {
+                tr.write_scalar(ev_last[set]);
+                lastq.push_back({id, x_last, ev_last[set]});
+            }
+        }
+        for (size_t i = lastq.size(); i-- > 0;) q_perm.push_back(lastq[i]);
+    }
+    for (uint32_t l = 0; l < L; ++l) {
+        tr.write_scalar(ev_x[id_lz[l]]);
+        tr.write_scalar(ev_next[id_lz[l]]);
+        tr.write_scalar(ev_x[id_la[l]]);
+        tr.write_scalar(ev_prev[l]);
+        tr.write_scalar(ev_x[id_ls[l]]);
+        q_lookup.push_back({id_lz[l], x, ev_x[id_lz[l]]});
+        q_lookup.push_back({id_la[l], x, ev_x[id_la[l]]});
+        q_lookup.push_back({id_ls[l], x, ev_x[id_ls[l]]});
+        q_lookup.push_back({id_la[l], x_prev, ev_prev[l]});
+        q_lookup.push_back({id_lz[l], x_next, ev_next[id_lz[l]]});
+    }
+    for (auto* v : {&q_advice, &q_perm, &q_lookup, &q_fixed, &q_sigma, &q_vanish}) queries.insert(queries.end(), v->begin(), v->end());
+    lap(tm ? &tm->evals : nullptr);
+    // step 12: SHPLONK (D.11)
+    const Fr ych = tr.squeeze_challenge();
+    std::vector<RotationSet> sets;
+    std::vector<Fr> super;
+    construct_intermediate_sets(queries, sets, super);
+    const Fr vch = tr.squeeze_challenge();
+    DevBuf<Fr> h_x(n, s), buf_a(n, s), buf_b(n, s);
+    CUDA_CHECK(cudaMemsetAsync(h_x.get(), 0, n * sizeof(Fr), s));
+    std::vector<std::vector<std::vector<Fr>>> low(sets.size());
+    {
+        Fr vp = one;
+        for (size_t i = 0; i < sets.size(); ++i) {
+            const RotationSet& rs = sets[i];
+            std::vector<const Fr*> ps;
+            std::vector<Fr> cs;
+            std::vector<Fr> r_comb(rs.points.size(), f_zero<FrCfg>());
+            Fr yp = one;
+            for (size_t j = 0; j < rs.polys.size(); ++j) {
+                low[i].push_back(lagrange_interpolate(rs.points, rs.evals[j]));
+                ps.push_back(polys[rs.polys[j]]);
+                cs.push_back(yp);
+                for (size_t t = 0; t < low[i][j].size(); ++t) r_comb[t] = f_add(r_comb[t], f_mul(low[i][j][t], yp));
+                yp = f_mul(yp, ych);
+            }
+            fr_lincomb(buf_a.get(), ps, cs, n, false, s);
+            fr_sub_low(buf_a.get(), r_comb.data(), (uint32_t)r_comb.size(), s);
+            Fr *src = buf_a.get(), *dst = buf_b.get();
+            for (auto& pt : rs.points) {
+                fr_kate_division(ctx, src, dst, n, pt);
+                std::swap(src, dst);
+            }
+            fr_lincomb(h_x.get(), {src}, {vp}, n, true, s);
+            vp = f_mul(vp, vch);
+        }
+    }
+    lap(tm ? &tm->shplonk : nullptr);
+    tr.write_point(commit_coeff(ctx, h_x.get(), n));
+    lap(tm ? &tm->msm : nullptr);
+    const Fr uch = tr.squeeze_challenge();
+    {
+        std::vector<const Fr*> ps;
+        std::vector<Fr> cs;
+        std::vector<Fr> z_diffs;
+        Fr const_term = f_zero<FrCfg>(), vp = one;
+        for (size_t i = 0; i < sets.size(); ++i) {
+            const RotationSet& rs = sets[i];
+            std::vector<Fr> diffs;
+            for (auto& pnt : super) {
+                bool in_set = false;
+                for (auto& q : rs.points) in_set |= f_eq(pnt, q);
+                if (!in_set) diffs.push_back(pnt);
+            }
+            const Fr z_i = vanishing_eval(diffs, uch);
+            z_diffs.push_back(z_i);
+            const Fr sc = f_mul(z_i, vp);
+            Fr yp = one;
+            for (size_t j = 0; j < rs.polys.size(); ++j) {
+                ps.push_back(polys[rs.polys[j]]);
+                cs.push_back(f_mul(sc, yp));
+                const_term = f_add(const_term, f_mul(f_mul(sc, yp), eval_small(low[i][j], uch)));
+                yp = f_mul(yp, ych);
+            }
+            vp = f_mul(vp, vch);
+        }
+        const Fr zt_eval = vanishing_eval(super, uch);
+        ps.push_back(h_x.get());
+        cs.push_back(f_neg(zt_eval));
+        fr_lincomb(buf_a.get(), ps, cs, n, false, s);
+        fr_sub_low(buf_a.get(), &const_term, 1, s);
+        fr_kate_division(ctx, buf_a.get(), buf_b.get(), n, uch);
+        fr_scale(buf_b.get(), f_inv(z_diffs[0]), n, s);
+    }
+    lap(tm ? &tm->shplonk : nullptr);
+    tr.write_point(commit_coeff(ctx, buf_b.get(), n));
+    lap(tm ? &tm->msm : nullptr);
+    return tr.proof;
+}
+
+}  // namespace b200zk

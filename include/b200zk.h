@@ -96,6 +96,35 @@ B200ZK_API int b200zk_msm_bases(b200zk_ctx* ctx, const b200zk_g1_affine* bases, 
 B200ZK_API int b200zk_msm_bases_dev(b200zk_ctx* ctx, const b200zk_g1_affine* bases_dev, const b200zk_fr* scalars_dev, size_t n,
                                     b200zk_g1_affine* out);
 
+/* ---- rows J, E–I: plonk::{keygen_vk, keygen_pk, create_proof} for the halo2-base ConstraintSystem -----------------
+ * Shape: A gate advice columns (one `q·(a + b·c − d)` gate each, rotations 0..3), L lookup
+ * advice columns against one table column, F constant columns. Fixed column order: F constants, table, A selectors.
+ * Permutation column order (indices used by `copies`): F constants, A gate columns, L lookup columns.
+ * `fixed`: num_fixed × 2^k elements, column-major; `copies`: ncopies × {col_a,row_a,col_b,row_b}.
+ * Requires an SRS of the same k on the context. The key lives on the device until b200zk_pk_free. */
+typedef struct b200zk_pk b200zk_pk;
+B200ZK_API int b200zk_keygen(b200zk_ctx* ctx, uint32_t k, uint32_t A, uint32_t L, uint32_t F, const b200zk_fr* fixed, const uint32_t* copies,
+                             size_t ncopies, b200zk_pk** out);
+B200ZK_API int b200zk_pk_free(b200zk_ctx* ctx, b200zk_pk* pk);
+/* vk.fixed_commitments (num_fixed points) and vk.permutation.commitments (num_perm points); either may be NULL */
+B200ZK_API int b200zk_pk_commitments(b200zk_ctx* ctx, const b200zk_pk* pk, b200zk_g1_affine* fixed_out, b200zk_g1_affine* perm_out);
+/* vk.transcript_repr: read, or override with the value the Rust side computed (opaque 32-byte scalar) */
+B200ZK_API int b200zk_pk_transcript_repr(b200zk_ctx* ctx, b200zk_pk* pk, b200zk_fr* get_out, const b200zk_fr* set_in);
+/* test access to key columns: which 0 = sigma values j (n), 1 = fixed coset i (4n), 2 = sigma coset j (4n),
+ * 3 = l0 / l_last / l_active_row (idx 0..2, 4n) */
+B200ZK_API int b200zk_pk_get_column(b200zk_ctx* ctx, const b200zk_pk* pk, int which, uint32_t idx, b200zk_fr* out);
+B200ZK_API size_t b200zk_proof_size(uint32_t k, uint32_t A, uint32_t L, uint32_t F);
+/* create_proof::<KZGCommitmentScheme<Bn256>, ProverSHPLONK, Challenge255, StdRng, Blake2bWrite> for ONE circuit without
+ * instances. `advice`: (A+L) × 2^k witness values, column-major (rows >= 2^k − 7 are overwritten by blinding).
+ * rng = StdRng::seed_from_u64(rng_seed). `proof_out` must hold b200zk_proof_size bytes. `timings` (optional, 9 doubles):
+ * seconds spent in upload, msm, ntt, lookup, products, quotient, evals, shplonk, other. */
+B200ZK_API int b200zk_create_proof(b200zk_ctx* ctx, const b200zk_pk* pk, const b200zk_fr* advice, uint64_t rng_seed, uint8_t* proof_out,
+                                   size_t* proof_len, double* timings);
+/* ---- synthetic circuits of that shape (host only; stands in for the reference's FRI-verifier witness) */
+B200ZK_API size_t b200zk_synth_max_copies(uint32_t k, uint32_t A, uint32_t L, uint32_t F);
+B200ZK_API int b200zk_synth_circuit(uint32_t k, uint32_t A, uint32_t L, uint32_t F, uint64_t seed, b200zk_fr* fixed, b200zk_fr* advice,
+                                    uint32_t* copies, size_t* ncopies);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py — the headline benchmark of BASELINE.json: `create_proof` seconds for the FRI-verifier-shaped circuit at
+k=20 (shape S20-bn: 14 gate + 3 lookup + 1 constant columns, 41 MSMs of 2^20, 35 iNTTs, 35 coset NTTs),
+KZG-BN254 / SHPLONK / Blake2b transcript, plus the MSM Mpts/s and NTT GB/s lines the metric names.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--k 20]
+
+One JSON line on stdout (rank 0). A "step" = one create_proof over one synthetic witness.
+  value  : seconds per proof with the witness already resident in HBM (b200zk_create_proof_dev), CUDA events on the
+           library's stream, max over ranks.
+  e2e    : the same through the reference-facing call with HOST buffers (b200zk_create_proof): pinned host witness ->
+           device inside the timed region, proof bytes back on the host.
+  --impl reference : the CPU restatement of halo2's prover (oracle/, all host threads) on a bounded sample of the same
+           workload (same shape at k=17 = 1/8 of the rows), scaled linearly to k=20 — the real Rust prover cannot be built
+           here (no Rust toolchain, un-vendored dependencies).
+N > 1 (torchrun): every rank proves the same circuit independently on its own GPU (replicas, weak scaling, no data-path
+collective) — the sharded single-proof path is ROADMAP.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SHAPE = dict(A=14, L=3, F=1)  # S20-bn / its k-scaled versions
+IMAD_PEAK_TOPS = 18.0  # measured by tools/microbench.cu on this pool's B200 (profiles/microbench_r01.json)
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200")
+    p.add_argument("--k", type=int, default=20)
+    p.add_argument("--sample-k", type=int, default=17, help="k of the bounded CPU sample")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-extras", action="store_true", help="skip the MSM / NTT side lines")
+    return p.parse_args()
+
+
+def workload_name(k):
+    A, L, F = SHAPE["A"], SHAPE["L"], SHAPE["F"]
+    return (f"S{k}-bn: halo2-base-shaped FRI-verifier stand-in, k={k}, {A} gate + {L} lookup + {F} constant columns, "
+            f"create_proof KZG-BN254 SHPLONK Blake2b, {A + L + 2 * L + (A + L + F + 1) // 2 + L + 6} MSMs of 2^{k}")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_sample(k, threads=None):
+    """Oracle (restated halo2 CPU prover, std::thread on all host cores) on the same shape at k: returns seconds."""
+    import numpy as np  # noqa: F401
+
+    import b200zk
+    import oracle_lib as O
+
+    if threads:
+        O.lib().oracle_set_threads(threads)
+    fixed, advice, copies = b200zk.synth_circuit(k, SHAPE["A"], SHAPE["L"], SHAPE["F"], seed=0)
+    params = O.Params.setup(k)
+    pk = O.ProvingKey(params, k, SHAPE["A"], SHAPE["L"], SHAPE["F"], fixed, copies)
+
+    def step():
+        proof = pk.create_proof(advice, 0)
+        return pk.last_seconds, proof
+
+    return step, O.lib().oracle_get_threads(), pk
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the path (oracle port) on the box's host cores."""
+    if rank != 0:
+        return
+    step, cores, pk = cpu_sample(args.sample_k)
+    for _ in range(args.warmup):
+        step()
+    t = []
+    for _ in range(args.steps):
+        s, proof = step()
+        t.append(s)
+    assert pk.verify(proof)[0]
+    scale = float(1 << (args.k - args.sample_k))
+    sample_s = sum(t) / len(t)
+    value = sample_s * scale
+    line = {
+        "impl": "reference", "metric": "create_proof_s", "value": value, "unit": "s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": value * 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (254-bit Montgomery)",
+        "data": "synthetic", "config": {"workload": workload_name(args.k)},
+        "cpu_baseline": {"value": value, "unit": "s", "cores": cores, "kind": "port",
+                         "sample": f"same shape at k={args.sample_k} ({sample_s:.3f} s per create_proof, mean of {args.steps}), scaled x{int(scale)} "
+                                   f"(rows) to k={args.k}; restated halo2 CPU algorithms (C++ oracle), not the rayon binary"},
+        "e2e": {"value": value, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    import numpy as np
+    import torch
+
+    import b200zk
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — libb200zk has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    k, A, L, F = args.k, SHAPE["A"], SHAPE["L"], SHAPE["F"]
+    n = 1 << k
+    ctx = b200zk.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+    # ---- untimed setup: SRS on the device, synthetic circuit, keygen ----
+    t0 = time.time()
+    ctx.srs_setup(k)  # ParamsKZG::setup(k, ChaCha20Rng::from_seed([0;32])) like halo2-base gen_srs
+    t_srs = time.time() - t0
+    fixed, advice, copies = b200zk.synth_circuit(k, A, L, F, seed=0)
+    t0 = time.time()
+    pk = ctx.keygen(k, A, L, F, fixed, copies)
+    t_keygen = time.time() - t0
+    del fixed, copies
+    pinned = torch.from_numpy(advice.view(np.int64).reshape(-1)).pin_memory()
+    host_advice = pinned.numpy().view(np.uint64)
+    dev_advice = torch.empty(pinned.numel(), dtype=torch.int64, device="cuda")
+    dev_advice.copy_(pinned)
+    torch.cuda.synchronize()
+    advice_bytes = pinned.numel() * 8
+    launches0 = b200zk.launch_count()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        w0 = time.time()
+        e0.record(stream)
+        for _ in range(steps):
+            out = fn()
+        e1.record(stream)
+        ctx.sync()
+        barrier()
+        wall = time.time() - w0
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms, wall * 1e3], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = t[0].item(), t[1].item() / 1e3
+        return ms / steps, wall / steps, out
+
+    step_dev = lambda: pk.create_proof(None, 0, device_ptr=dev_advice.data_ptr())  # noqa: E731
+    step_host = lambda: pk.create_proof(host_advice, 0)  # noqa: E731
+    for _ in range(max(args.warmup, 0)):
+        step_dev()
+    l_before = b200zk.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_dev, wall_dev, proof = timed(step_dev, args.steps)
+    launches = (b200zk.launch_count() - l_before) // max(args.steps, 1)
+    for _ in range(min(args.warmup, 2)):
+        step_host()
+    ms_host, wall_host, proof_h = timed(step_host, args.steps)
+    clocks = sampler.stop()
+    assert proof == proof_h and len(proof) == pk.proof_size()
+    # ---- one profiled step: per-stage split + dominant-kernel durations by CUDA events on the launching stream ----
+    ctx.profile_enable(True)
+    _, stages = pk.create_proof(None, 0, timings=True, device_ptr=dev_advice.data_ptr())
+    acc_ms, acc_n = ctx.profile_get("msm_accumulate")
+    ntt_ms, ntt_n = ctx.profile_get("ntt_pass")
+    q_ms, q_n = ctx.profile_get("quotient")
+    ctx.profile_enable(False)
+    n_msm = acc_n
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    # dominant kernel = msm_accumulate_kernel: algorithmic bytes per launch = 96·n (32 B scalar + 64 B base per point)
+    acc_avg_ms = acc_ms / max(acc_n, 1)
+    alg_bytes = 96.0 * n
+    achieved = alg_bytes / (acc_avg_ms * 1e-3) / 1e9 if acc_avg_ms > 0 else 0.0
+    roofline = {"kernel": "msm_accumulate_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": None, "peak_source": peak_src, "launches": acc_n, "avg_launch_ms": acc_avg_ms, "share_of_step": acc_ms / (ms_dev if ms_dev else 1),
+                "note": "integer-pipe bound by design (north_star: no tensor cores, IMAD carry chains); the HBM fraction is reported because the "
+                        "contract asks for it — see int_pipe for the binding roof"}
+    line = {
+        "metric": "create_proof_s", "value": ms_dev / 1e3, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
+        "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (254-bit Montgomery integers)", "data": "synthetic",
+        "config": {"workload": workload_name(k), "l2": "inputs larger than L2 (witness 0.57 GB, ~12 GB of device-resident columns per proof)",
+                   "parallelism": "1 proof per GPU" + (f", {world} replicas" if world > 1 else ""), "rng": "StdRng::seed_from_u64(0)",
+                   "srs": "ParamsKZG::setup(k, ChaCha20Rng::from_seed([0;32])) generated on device"},
+        "clocks": clocks,
+        "e2e": {"value": ms_host / 1e3, "unit": "s", "h2d_bytes_per_step": advice_bytes, "d2h_bytes_per_step": len(proof) + n_msm * 16 * 128,
+                "wall_s": wall_host, "api": "b200zk_create_proof (host witness in pinned memory -> proof bytes on host)"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "stages_ms": {k_: round(v * 1e3, 2) for k_, v in stages.items()},
+        "setup_s": {"srs_device": round(t_srs, 2), "keygen_pk": round(t_keygen, 2)},
+        "proof_bytes": len(proof),
+    }
+    if world > 1:
+        line["value"] = ms_dev / 1e3 / world
+        line["e2e"]["value"] = ms_host / 1e3 / world
+        line["config"]["aggregate"] = f"{world} independent proofs per step; value = step time / {world}"
+    if rank == 0 and not args.no_extras:
+        line.update(side_lines(ctx, stream, torch, np, k, acc_ms, acc_n, ntt_ms, ntt_n, q_ms, q_n))
+    if rank == 0 and not args.no_cpu_baseline:
+        step, cores, opk = cpu_sample(args.sample_k)
+        t0 = time.time()
+        secs, oproof = step()
+        scale = float(1 << (k - args.sample_k))
+        line["cpu_baseline"] = {"value": secs * scale, "unit": "s", "cores": cores, "kind": "port",
+                                "sample": f"oracle create_proof on the same shape at k={args.sample_k}: {secs:.3f} s, scaled x{int(scale)} (rows) to k={k}; "
+                                          "restated halo2 CPU algorithms (C++ oracle, std::thread), not the rayon binary"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    os._exit(0)
+
+
+def side_lines(ctx, stream, torch, np, k, acc_ms, acc_n, ntt_ms, ntt_n, q_ms, q_n):
+    """MSM Mpts/s and NTT GB/s (the other two parts of BASELINE.json's metric) at the workload's size, device-resident."""
+    n = 1 << k
+    rng = np.random.default_rng(0)
+    host = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
+    host[:, 3] &= np.uint64((1 << 60) - 1)  # 252-bit limbs: canonical (< r) whatever the other limbs are
+    buf = torch.empty(4 * n * 4, dtype=torch.int64, device="cuda")
+    for b in range(4):
+        ctx.h2d(buf.data_ptr() + 32 * n * b, host)
+
+    def ev(fn, iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(3):
+            fn()
+        ctx.sync()
+        e0.record(stream)
+        for _ in range(iters):
+            fn()
+        e1.record(stream)
+        ctx.sync()
+        return e0.elapsed_time(e1) / iters
+
+    msm_ms = ev(lambda: ctx.msm_dev(buf.data_ptr(), n, 0), 5)
+    # NTT: 4 columns of 2^k (forward, standard root) and one coset NTT n -> 4n
+    omega = np.empty(4, dtype=np.uint64)
+    # the domain generator = ROOT_OF_UNITY^(2^(28-k)); computed with the library's own field kernels
+    root = np.array([[0xd34f1ed960c37c9c, 0x3215cf6dd39329c8, 0x98865ea93dd31f74, 0x03ddb9f5166d18b7]], dtype=np.uint64)
+    w = ctx.field_vec_op(0, 6, root)  # to Montgomery form
+    for _ in range(28 - k):
+        w = ctx.field_vec_op(0, 2, w, w)
+    omega[:] = w[0]
+    ntt_batch_ms = ev(lambda: ctx.ntt_dev(buf.data_ptr(), k, omega, 4, n), 5)
+    ext = torch.empty(4 * n * 4, dtype=torch.int64, device="cuda")
+    coset_ms = ev(lambda: ctx.coeff_to_extended_dev(k, buf.data_ptr(), ext.data_ptr()), 5)
+    return {
+        "msm": {"n": n, "scalars": "uniform Fr", "ms": msm_ms, "Mpts_s": n / msm_ms / 1e3},
+        "ntt": {"n": n, "batch": 4, "ms": ntt_batch_ms, "GBps_64nB": 64.0 * n * 4 / (ntt_batch_ms * 1e-3) / 1e9,
+                "Gbutterfly_s": 4 * (n // 2) * k / (ntt_batch_ms * 1e-3) / 1e9},
+        "coset_ntt": {"n": n, "ms": coset_ms, "GBps_160n": 160.0 * n / (coset_ms * 1e-3) / 1e9},
+        "int_pipe": {"peak_Tops": IMAD_PEAK_TOPS, "peak_source": "tools/microbench.cu IMAD issue rate on this pool's B200 (profiles/microbench_r01.json)",
+                     "kernel_ms_in_profiled_step": {"msm_accumulate": acc_ms, "ntt_pass": ntt_ms, "quotient": q_ms},
+                     "launches": {"msm_accumulate": acc_n, "ntt_pass": ntt_n, "quotient": q_n}},
+    }
+
+
+if __name__ == "__main__":
+    main()

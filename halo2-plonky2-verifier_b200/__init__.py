@@ -95,6 +95,18 @@ class Context:
     def sync(self):
         self._check(lib().b200zk_sync(self._h))
 
+    # ---- per-kernel-family event timing (bench.py roofline section) ----
+    PROF_IDS = {"msm_accumulate": 0, "ntt_pass": 2, "quotient": 3}
+
+    def profile_enable(self, on=True):
+        self._check(lib().b200zk_profile_enable(self._h, int(bool(on))))
+
+    def profile_get(self, name):
+        ms = ctypes.c_double(0)
+        cnt = ctypes.c_ulonglong(0)
+        self._check(lib().b200zk_profile_get(self._h, self.PROF_IDS[name], ctypes.byref(ms), ctypes.byref(cnt)))
+        return ms.value, int(cnt.value)
+
     # ---- raw device memory ----
     def dev_alloc(self, nbytes):
         p = ctypes.c_void_p()
@@ -181,6 +193,26 @@ class Context:
         self._check(lib().b200zk_srs_load(self._h, ctypes.c_uint32(k), _p(g), _p(gl)))
         self.srs_k = k
 
+    def srs_setup(self, k, seed=bytes(32), trapdoor=None):
+        """ParamsKZG::<Bn256>::setup(k, ChaCha20Rng::from_seed(seed)) generated on the device (halo2-base gen_srs uses
+        seed [0;32]); returns the trapdoor s (tests use it to check openings without a pairing)."""
+        out = np.empty(4, dtype=np.uint64)
+        if trapdoor is not None:
+            t = _c(trapdoor)
+            self._check(lib().b200zk_srs_setup_trapdoor(self._h, ctypes.c_uint32(k), _p(t)))
+            out[:] = t
+        else:
+            self._check(lib().b200zk_srs_setup(self._h, ctypes.c_uint32(k), bytes(seed), _p(out)))
+        self.srs_k = k
+        return out
+
+    def srs_download(self):
+        n = 1 << self.srs_k
+        g = np.empty((n, 8), dtype=np.uint64)
+        gl = np.empty((n, 8), dtype=np.uint64)
+        self._check(lib().b200zk_srs_download(self._h, _p(g), _p(gl)))
+        return g, gl
+
     def msm(self, scalars, basis=0):
         """ParamsKZG::commit (basis=0) / commit_lagrange (basis=1) == best_multiexp(scalars, bases); affine result."""
         scalars = _c(scalars).reshape(-1, 4)
@@ -260,16 +292,22 @@ class ProvingKey:
     def proof_size(self):
         return int(lib().b200zk_proof_size(*self.shape))
 
-    def create_proof(self, advice, rng_seed=0, timings=False):
-        """plonk::create_proof with StdRng::seed_from_u64(rng_seed) and a Blake2b transcript; returns the proof bytes."""
+    def create_proof(self, advice, rng_seed=0, timings=False, device_ptr=None):
+        """plonk::create_proof with StdRng::seed_from_u64(rng_seed) and a Blake2b transcript; returns the proof bytes.
+        `advice`: host array ((A+L) × 2^k × 4 uint64), or pass `device_ptr` for columns already resident in HBM."""
         k, A, L, F = self.shape
-        advice = _c(advice)
-        assert advice.size == (A + L) * (1 << k) * 4
         buf = np.empty(self.proof_size(), dtype=np.uint8)
         plen = ctypes.c_size_t(0)
         tm = np.zeros(9, dtype=np.float64)
-        self.ctx._check(lib().b200zk_create_proof(self.ctx._h, self._h, _p(advice), ctypes.c_uint64(rng_seed), _p(buf), ctypes.byref(plen),
-                                                  _p(tm) if timings else None))
+        if device_ptr is not None:
+            self.ctx._check(lib().b200zk_create_proof_dev(self.ctx._h, self._h, ctypes.c_void_p(device_ptr), ctypes.c_uint64(rng_seed), _p(buf),
+                                                          ctypes.byref(plen), _p(tm) if timings else None))
+        else:
+            if not (isinstance(advice, np.ndarray) and advice.dtype == np.uint64 and advice.flags["C_CONTIGUOUS"]):
+                advice = _c(advice)
+            assert advice.size == (A + L) * (1 << k) * 4
+            self.ctx._check(lib().b200zk_create_proof(self.ctx._h, self._h, _p(advice), ctypes.c_uint64(rng_seed), _p(buf), ctypes.byref(plen),
+                                                      _p(tm) if timings else None))
         proof = buf[: plen.value].tobytes()
         if timings:
             return proof, dict(zip(TIMING_KEYS, tm.tolist()))

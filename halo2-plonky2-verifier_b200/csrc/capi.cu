@@ -7,6 +7,7 @@ using namespace b200zk;
 
 namespace b200zk {
 G1Affine msm_run(Context& ctx, const G1Affine* bases, const Fr* scalars, size_t n);
+void srs_setup(Context& ctx, uint32_t k, const Fr& s_trapdoor);
 }
 
 struct b200zk_ctx {
@@ -78,6 +79,34 @@ int b200zk_sync(b200zk_ctx* ctx) {
     API_END(ctx)
 }
 unsigned long long b200zk_launch_count(void) { return g_launch_count; }
+int b200zk_profile_enable(b200zk_ctx* ctx, int on) {
+    API_BEGIN(ctx)
+    CUDA_CHECK(cudaStreamSynchronize(ctx->c.stream));
+    for (auto& sp : g_prof_spans) {
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+    }
+    g_prof_spans.clear();
+    g_prof_enabled = on != 0;
+    API_END(ctx)
+}
+int b200zk_profile_get(b200zk_ctx* ctx, int id, double* total_ms, unsigned long long* launches) {
+    API_BEGIN(ctx)
+    if (!total_ms || !launches) throw std::invalid_argument("profile_get: null argument");
+    CUDA_CHECK(cudaStreamSynchronize(ctx->c.stream));
+    double tot = 0;
+    unsigned long long cnt = 0;
+    for (auto& sp : g_prof_spans) {
+        if (sp.id != id) continue;
+        float ms = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, sp.a, sp.b));
+        tot += ms;
+        ++cnt;
+    }
+    *total_ms = tot;
+    *launches = cnt;
+    API_END(ctx)
+}
 int b200zk_dev_alloc(b200zk_ctx* ctx, size_t bytes, void** out) {
     API_BEGIN(ctx)
     if (!out) throw std::invalid_argument("null out");
@@ -424,14 +453,38 @@ int b200zk_pk_get_column(b200zk_ctx* ctx, const b200zk_pk* pk, int which, uint32
     CUDA_CHECK(cudaStreamSynchronize(ctx->c.stream));
     API_END(ctx)
 }
+int b200zk_srs_setup_trapdoor(b200zk_ctx* ctx, uint32_t k, const b200zk_fr* s) {
+    API_BEGIN(ctx)
+    if (!s) throw std::invalid_argument("srs_setup: null trapdoor");
+    srs_setup(ctx->c, k, load_fr(s));
+    API_END(ctx)
+}
+int b200zk_srs_setup(b200zk_ctx* ctx, uint32_t k, const uint8_t seed[32], b200zk_fr* trapdoor_out) {
+    API_BEGIN(ctx)
+    if (!seed) throw std::invalid_argument("srs_setup: null seed");
+    host::FrRandomStream rng = host::FrRandomStream::chacha20_from_seed(seed);
+    const Fr s = rng.next();
+    if (trapdoor_out) memcpy(trapdoor_out->l, s.l, 32);
+    srs_setup(ctx->c, k, s);
+    API_END(ctx)
+}
+int b200zk_srs_download(b200zk_ctx* ctx, b200zk_g1_affine* g, b200zk_g1_affine* g_lagrange) {
+    API_BEGIN(ctx)
+    Context& c = ctx->c;
+    if (!c.srs) throw std::runtime_error("no SRS loaded");
+    if (g) CUDA_CHECK(cudaMemcpyAsync(g, c.srs->g.get(), 64 * c.srs->n, cudaMemcpyDeviceToHost, c.stream));
+    if (g_lagrange) CUDA_CHECK(cudaMemcpyAsync(g_lagrange, c.srs->g_lagrange.get(), 64 * c.srs->n, cudaMemcpyDeviceToHost, c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    API_END(ctx)
+}
 size_t b200zk_proof_size(uint32_t k, uint32_t A, uint32_t L, uint32_t F) { return Shape{k, A, L, F}.proof_size(); }
-int b200zk_create_proof(b200zk_ctx* ctx, const b200zk_pk* pk, const b200zk_fr* advice, uint64_t rng_seed, uint8_t* proof_out, size_t* proof_len,
-                        double* timings) {
+static int create_proof_impl(b200zk_ctx* ctx, const b200zk_pk* pk, const b200zk_fr* advice, bool on_device, uint64_t rng_seed, uint8_t* proof_out,
+                             size_t* proof_len, double* timings) {
     API_BEGIN(ctx)
     if (!pk || !advice || !proof_out || !proof_len) throw std::invalid_argument("create_proof: null argument");
     host::FrRandomStream rng = host::FrRandomStream::std_rng_seed_from_u64(rng_seed);
     ProofTimings tm;
-    std::vector<uint8_t> proof = create_proof(ctx->c, *pk->pk, (const Fr*)advice, rng, timings ? &tm : nullptr);
+    std::vector<uint8_t> proof = create_proof(ctx->c, *pk->pk, (const Fr*)advice, on_device, rng, timings ? &tm : nullptr);
     memcpy(proof_out, proof.data(), proof.size());
     *proof_len = proof.size();
     if (timings) {
@@ -439,6 +492,14 @@ int b200zk_create_proof(b200zk_ctx* ctx, const b200zk_pk* pk, const b200zk_fr* a
         memcpy(timings, t, sizeof(t));
     }
     API_END(ctx)
+}
+int b200zk_create_proof(b200zk_ctx* ctx, const b200zk_pk* pk, const b200zk_fr* advice, uint64_t rng_seed, uint8_t* proof_out, size_t* proof_len,
+                        double* timings) {
+    return create_proof_impl(ctx, pk, advice, false, rng_seed, proof_out, proof_len, timings);
+}
+int b200zk_create_proof_dev(b200zk_ctx* ctx, const b200zk_pk* pk, const b200zk_fr* advice_dev, uint64_t rng_seed, uint8_t* proof_out,
+                            size_t* proof_len, double* timings) {
+    return create_proof_impl(ctx, pk, advice_dev, true, rng_seed, proof_out, proof_len, timings);
 }
 
 }  // extern "C"

@@ -108,4 +108,27 @@ void build_twiddle_table(Fr* table, const Fr& omega, uint32_t log_n, cudaStream_
 int ntt_num_passes(uint32_t log_n);
 extern unsigned long long g_launch_count;  // kernels launched by this library (bench "gpu_launches")
 
+// Optional per-kernel-family timing with CUDA events on the launching stream (bench.py roofline section).
+// Disabled by default: when off, prof_begin/prof_end are a branch on a global flag.
+enum ProfId { PROF_MSM_ACCUMULATE = 0, PROF_MSM_OTHER, PROF_NTT_PASS, PROF_QUOTIENT, PROF_COUNT };
+struct ProfSpan {
+    int id;
+    cudaEvent_t a, b;
+};
+extern bool g_prof_enabled;
+extern std::vector<ProfSpan> g_prof_spans;
+inline void prof_begin(int id, cudaStream_t s) {
+    if (!g_prof_enabled) return;
+    ProfSpan sp;
+    sp.id = id;
+    cudaEventCreate(&sp.a);
+    cudaEventCreate(&sp.b);
+    cudaEventRecord(sp.a, s);
+    g_prof_spans.push_back(sp);
+}
+inline void prof_end(cudaStream_t s) {
+    if (!g_prof_enabled) return;
+    cudaEventRecord(g_prof_spans.back().b, s);
+}
+
 }  // namespace b200zk

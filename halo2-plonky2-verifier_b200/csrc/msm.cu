@@ -333,8 +333,10 @@ void msm_window_sums(Context& ctx, const G1Affine* bases, const Fr* scalars, siz
     uint32_t nthreads = (uint32_t)(((uint64_t)total + ACC_T - 1) / ACC_T);
     DevBuf<G1X> heads_a(nthreads, s), heads_b;
     DevBuf<uint32_t> keys_a(nthreads, s), keys_b;
+    prof_begin(PROF_MSM_ACCUMULATE, s);
     msm_accumulate_kernel<<<(nthreads + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, s>>>(bases, entries.get(), offsets.get(), nb, total,
                                                                                               bucket_sums.get(), heads_a.get(), keys_a.get());
+    prof_end(s);
     ++g_launch_count;
     CUDA_CHECK(cudaGetLastError());
     // levels >= 2: segment-sum the head list until a single thread covers it

@@ -21,6 +21,8 @@
 namespace b200zk {
 
 unsigned long long g_launch_count = 0;
+bool g_prof_enabled = false;
+std::vector<ProfSpan> g_prof_spans;
 
 struct PassParams {
     const Fr* in;
@@ -189,7 +191,9 @@ void ntt_run_batch(const NttPlan& plan, const Fr* in, Fr* out, Fr* scratch, uint
         const uint32_t T = 1u << (r + P.logC);
         const size_t smem = (size_t)2 * T * 16 + SMEM_PAD * 16;
         dim3 grid(1u << (L - r - P.logC), batch);
+        prof_begin(PROF_NTT_PASS, stream);
         ntt_pass_kernel<<<grid, NTT_THREADS, smem, stream>>>(P);
+        prof_end(stream);
         ++g_launch_count;
         CUDA_CHECK(cudaGetLastError());
         s0 += r;

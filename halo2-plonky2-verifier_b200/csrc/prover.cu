@@ -265,7 +265,8 @@ static Fr vanishing_eval(const std::vector<Fr>& roots, const Fr& z) {
 }
 
 // ---- create_proof ---------------------------------------------------------------------------------------------------------
-std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const Fr* advice_host, host::FrRandomStream& rng, ProofTimings* tm) {
+std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const Fr* advice_in, bool advice_on_device, host::FrRandomStream& rng,
+                                  ProofTimings* tm) {
     const Shape& sh = pk.shape;
     need_srs(ctx, sh.k);
     cudaStream_t s = ctx.stream;
@@ -291,7 +292,7 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
     tr.common_scalar(pk.transcript_repr);
     // step 1: upload, blind, commit advice (D.3)
     DevBuf<Fr> advice((size_t)NA * n, s);
-    CUDA_CHECK(cudaMemcpyAsync(advice.get(), advice_host, (size_t)NA * n * sizeof(Fr), cudaMemcpyHostToDevice, s));
+    CUDA_CHECK(cudaMemcpyAsync(advice.get(), advice_in, (size_t)NA * n * sizeof(Fr), advice_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
     {
         std::vector<Fr> blind((size_t)NA * (bf + 1));
         for (auto& b : blind) b = rng.next();

@@ -48,6 +48,7 @@ struct ProofTimings {
 };
 
 std::unique_ptr<ProvingKeyDev> keygen(Context& ctx, const Shape& sh, const Fr* fixed_host, const uint32_t* copies, size_t ncopies);
-std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const Fr* advice_host, host::FrRandomStream& rng, ProofTimings* tm);
+std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const Fr* advice_in, bool advice_on_device, host::FrRandomStream& rng,
+                                  ProofTimings* tm);
 
 }  // namespace b200zk

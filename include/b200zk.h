@@ -55,6 +55,10 @@ B200ZK_API void* b200zk_stream(b200zk_ctx* ctx);
 B200ZK_API int b200zk_sync(b200zk_ctx* ctx);
 /* kernels launched by this library since process start (bench.py "gpu_launches") */
 B200ZK_API unsigned long long b200zk_launch_count(void);
+/* per-kernel-family CUDA-event timing (off by default). ids: 0 msm_accumulate, 1 (reserved), 2 ntt_pass, 3 quotient.
+ * profile_get synchronises, sums the spans recorded since the last reset and clears them. */
+B200ZK_API int b200zk_profile_enable(b200zk_ctx* ctx, int on);
+B200ZK_API int b200zk_profile_get(b200zk_ctx* ctx, int id, double* total_ms, unsigned long long* launches);
 /* raw device memory helpers for hosts without their own allocator */
 B200ZK_API int b200zk_dev_alloc(b200zk_ctx* ctx, size_t bytes, void** out);
 B200ZK_API int b200zk_dev_free(b200zk_ctx* ctx, void* p);
@@ -88,6 +92,13 @@ B200ZK_API int b200zk_extended_to_coeff_dev(b200zk_ctx* ctx, uint32_t k, const b
  * srs_load copies both bases (n = 2^k affine points each) to the device once; `basis` below: 0 = g (monomial,
  * ParamsKZG::commit), 1 = g_lagrange (ParamsKZG::commit_lagrange). Results are canonical affine points. */
 B200ZK_API int b200zk_srs_load(b200zk_ctx* ctx, uint32_t k, const b200zk_g1_affine* g, const b200zk_g1_affine* g_lagrange);
+/* ParamsKZG::setup(k, rng) with s = Fr::random(rng) drawn from ChaCha20Rng::from_seed(seed) (halo2-base gen_srs uses
+ * seed = [0;32]), or from an explicit trapdoor; both bases are generated on the device. For tests and benches only —
+ * a production SRS comes from a ceremony through b200zk_srs_load. `trapdoor_out` (optional) receives s. */
+B200ZK_API int b200zk_srs_setup(b200zk_ctx* ctx, uint32_t k, const uint8_t seed[32], b200zk_fr* trapdoor_out);
+B200ZK_API int b200zk_srs_setup_trapdoor(b200zk_ctx* ctx, uint32_t k, const b200zk_fr* s);
+/* copy the bases back (either may be NULL) */
+B200ZK_API int b200zk_srs_download(b200zk_ctx* ctx, b200zk_g1_affine* g, b200zk_g1_affine* g_lagrange);
 B200ZK_API int b200zk_msm(b200zk_ctx* ctx, int basis, const b200zk_fr* scalars, size_t n, b200zk_g1_affine* out);
 B200ZK_API int b200zk_msm_dev(b200zk_ctx* ctx, int basis, const b200zk_fr* scalars_dev, size_t n, b200zk_g1_affine* out);
 /* best_multiexp(coeffs, bases) with caller-supplied bases (host buffers) */
@@ -120,6 +131,9 @@ B200ZK_API size_t b200zk_proof_size(uint32_t k, uint32_t A, uint32_t L, uint32_t
  * seconds spent in upload, msm, ntt, lookup, products, quotient, evals, shplonk, other. */
 B200ZK_API int b200zk_create_proof(b200zk_ctx* ctx, const b200zk_pk* pk, const b200zk_fr* advice, uint64_t rng_seed, uint8_t* proof_out,
                                    size_t* proof_len, double* timings);
+/* same with the advice columns already resident in device memory (the witness upload excluded) */
+B200ZK_API int b200zk_create_proof_dev(b200zk_ctx* ctx, const b200zk_pk* pk, const b200zk_fr* advice_dev, uint64_t rng_seed, uint8_t* proof_out,
+                                       size_t* proof_len, double* timings);
 /* ---- synthetic circuits of that shape (host only; stands in for the reference's FRI-verifier witness) */
 B200ZK_API size_t b200zk_synth_max_copies(uint32_t k, uint32_t A, uint32_t L, uint32_t F);
 B200ZK_API int b200zk_synth_circuit(uint32_t k, uint32_t A, uint32_t L, uint32_t F, uint64_t seed, b200zk_fr* fixed, b200zk_fr* advice,

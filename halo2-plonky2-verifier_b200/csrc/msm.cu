@@ -190,10 +190,10 @@ __global__ void __launch_bounds__(ACC_THREADS) msm_accumulate_kernel(const G1Aff
             g1x_store(started_before ? heads + t : bucket_sums + cur, acc);
             acc = g1x_identity();
             started_before = false;
-            do {
-                ++cur;
-                end = __ldg(offsets + cur + 1);
-            } while (end == p);
+            // next non-empty bucket: binary search, not a linear walk — small-scalar columns leave tens of thousands of
+            // consecutive empty buckets (a serial skip cost 19 ms per lookup-column MSM, profiles/launches_r01_before_fix.csv)
+            cur = find_bucket(offsets, nb, p);
+            end = __ldg(offsets + cur + 1);
         }
         const uint32_t e = __ldg(entries + p);
         G1Affine b = g1a_load_ro(bases + (e & 0x7fffffffu));

@@ -503,3 +503,70 @@ int b200zk_create_proof_dev(b200zk_ctx* ctx, const b200zk_pk* pk, const b200zk_f
 }
 
 }  // extern "C"
+
+// ---- host-only helpers ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int b200zk_g1_sum_host(const b200zk_g1_affine* points, size_t n, b200zk_g1_affine* out) {
+    if (!out || (n && !points)) return B200ZK_EINVAL;
+    G1X acc = g1x_identity();
+    for (size_t i = 0; i < n; ++i) {
+        G1Affine p;
+        memcpy(&p, points + i, 64);
+        acc = g1x_add_affine(acc, p);
+    }
+    const G1Affine r = g1x_to_affine(acc);
+    memcpy(out, &r, 64);
+    return B200ZK_OK;
+}
+
+int b200zk_host_selftest(uint64_t seed, size_t iters) {
+    uint64_t st = seed * 0x9e3779b97f4a7c15ull + 1;
+    auto next = [&]() {
+        st ^= st << 13;
+        st ^= st >> 7;
+        st ^= st << 17;
+        return st;
+    };
+    auto rnd = [&]() {
+        uint32_t w[16];
+        for (int i = 0; i < 8; ++i) {
+            uint64_t v = next();
+            w[2 * i] = (uint32_t)v;
+            w[2 * i + 1] = (uint32_t)(v >> 32);
+        }
+        return w[0] & 1 ? f_from_u512<FrCfg>(w) : f_from_u512<FrCfg>(w);
+    };
+    for (size_t it = 0; it < iters; ++it) {
+        const Fr a = rnd(), b = rnd(), c = rnd();
+        if (!f_eq(f_mul_chains(a, b), f_mul_host64(a, b))) return -10;                       // both multipliers agree
+        if (!f_eq(f_mul(a, f_add(b, c)), f_add(f_mul(a, b), f_mul(a, c)))) return -11;       // distributivity
+        if (!f_eq(f_sub(f_add(a, b), b), a)) return -12;
+        if (!f_is_zero(a) && !f_eq(f_mul(a, f_inv(a)), f_one<FrCfg>())) return -13;
+        if (!f_eq(f_to_mont(f_from_mont(a)), a)) return -14;
+        Fq x, y;
+        memcpy(x.l, a.l, 32);
+        memcpy(y.l, b.l, 32);
+        x.l[7] &= 0x0fffffffu;
+        y.l[7] &= 0x0fffffffu;
+        if (!f_eq(f_mul_chains(x, y), f_mul_host64(x, y))) return -15;
+    }
+    // group laws on the generator: (2G + G) + G == 2·(2G), 5G - 5G == 0, mixed add == full add
+    G1Affine gen;
+    gen.x = f_to_mont(Fq{{1, 0, 0, 0, 0, 0, 0, 0}});
+    gen.y = f_to_mont(Fq{{2, 0, 0, 0, 0, 0, 0, 0}});
+    const G1X g = g1x_from_affine(gen), g2 = g1x_dbl(g), g3 = g1x_add_affine(g2, gen), g4a = g1x_add(g3, g), g4b = g1x_dbl(g2);
+    const G1Affine a4 = g1x_to_affine(g4a), b4 = g1x_to_affine(g4b);
+    if (!f_eq(a4.x, b4.x) || !f_eq(a4.y, b4.y)) return -20;
+    if (!g1_is_identity(g1x_add(g4a, g1x_neg(g4b)))) return -21;
+    if (!g1_is_identity(g1x_add_affine(g1x_neg(g), gen))) return -22;
+    const uint32_t five = 5;
+    const G1Affine m5 = g1x_to_affine(g1x_mul_bits(g, &five, 3)), s5 = g1x_to_affine(g1x_add_affine(g4a, gen));
+    if (!f_eq(m5.x, s5.x) || !f_eq(m5.y, s5.y)) return -23;
+    // on-curve: y^2 = x^3 + 3
+    const Fq three = f_to_mont(Fq{{3, 0, 0, 0, 0, 0, 0, 0}});
+    if (!f_eq(f_sqr(m5.y), f_add(f_mul(f_sqr(m5.x), m5.x), three))) return -24;
+    return 0;
+}
+
+}  // extern "C"

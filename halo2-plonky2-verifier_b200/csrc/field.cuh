@@ -325,8 +325,7 @@ HD Field<C> f_mul_chains(const Field<C>& a, const Field<C>& b) {
     uint32_t c = add8(t.l, E + 1, O);
     return f_reduce_once<C>(t, c);
 }
-#if !defined(__CUDA_ARCH__)
-// host fast path: 4×64-bit limbs, same value as f_mul_chains (checked in tests/test_host_lib.py)
+// host fast path: 4×64-bit limbs, same value as f_mul_chains (checked by b200zk_host_selftest)
 template <class C>
 inline Field<C> f_mul_host64(const Field<C>& a, const Field<C>& b) {
     typedef unsigned __int128 u128;
@@ -368,7 +367,6 @@ inline Field<C> f_mul_host64(const Field<C>& a, const Field<C>& b) {
     }
     return f_reduce_once<C>(r, (uint32_t)t[4]);
 }
-#endif
 template <class C>
 HD Field<C> f_mul(const Field<C>& a, const Field<C>& b) {
 #if defined(__CUDA_ARCH__)

@@ -134,6 +134,12 @@ B200ZK_API int b200zk_create_proof(b200zk_ctx* ctx, const b200zk_pk* pk, const b
 /* same with the advice columns already resident in device memory (the witness upload excluded) */
 B200ZK_API int b200zk_create_proof_dev(b200zk_ctx* ctx, const b200zk_pk* pk, const b200zk_fr* advice_dev, uint64_t rng_seed, uint8_t* proof_out,
                                        size_t* proof_len, double* timings);
+/* ---- host-only helpers (no CUDA device needed) -------------------------------------------------------------------
+ * Sum of n affine G1 points (canonical affine out): combines per-GPU partial MSM results. */
+B200ZK_API int b200zk_g1_sum_host(const b200zk_g1_affine* points, size_t n, b200zk_g1_affine* out);
+/* Cross-checks the host paths of the shared field/curve code (carry-chain emulation vs 64-bit limbs, group laws) on
+ * `iters` pseudo-random inputs; returns 0 when every identity holds. */
+B200ZK_API int b200zk_host_selftest(uint64_t seed, size_t iters);
 /* ---- synthetic circuits of that shape (host only; stands in for the reference's FRI-verifier witness) */
 B200ZK_API size_t b200zk_synth_max_copies(uint32_t k, uint32_t A, uint32_t L, uint32_t F);
 B200ZK_API int b200zk_synth_circuit(uint32_t k, uint32_t A, uint32_t L, uint32_t F, uint64_t seed, b200zk_fr* fixed, b200zk_fr* advice,

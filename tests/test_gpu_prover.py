@@ -101,3 +101,21 @@ def test_unsatisfied_witness_proof_is_rejected(ctx):
     got = gpk.create_proof(bad, 0)
     assert got == opk.create_proof(bad, 0)
     assert not opk.verify(got)[0]
+
+
+def test_gpu_reproduces_golden_proofs(ctx):
+    """Committed fixtures (tests/golden/oracle_vectors.json): the GPU path must emit the same proof bytes without any
+    oracle code running in this test."""
+    import hashlib
+    import json
+    import os
+
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_vectors.json")))
+    for case in g["proofs"]:
+        k, A, L, F = case["shape"]
+        fixed, advice, copies = make_circuit(k, A, L, F, seed=case["circuit_seed"])
+        ctx.srs_setup(k)
+        dg, dgl = ctx.srs_download()
+        assert hashlib.sha256(dg.tobytes() + dgl.tobytes()).hexdigest() == case["srs_sha256"]
+        pk = ctx.keygen(k, A, L, F, fixed, copies)
+        assert pk.create_proof(advice, case["rng_seed"]).hex() == case["proof_hex"]

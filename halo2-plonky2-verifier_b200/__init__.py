@@ -63,6 +63,26 @@ def launch_count():
     return int(lib().b200zk_launch_count())
 
 
+ALLGATHER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p)
+
+
+def torch_allgather(dist, device=None):
+    """All-gather of a small byte string over torch.distributed (NCCL when `device` is a CUDA device, gloo otherwise)."""
+    import torch
+
+    world = dist.get_world_size()
+
+    def fn(data):
+        t = torch.frombuffer(bytearray(data), dtype=torch.uint8)
+        if device is not None:
+            t = t.to(device)
+        out = torch.empty(world * len(data), dtype=torch.uint8, device=t.device)
+        dist.all_gather_into_tensor(out, t)
+        return out.cpu().numpy().tobytes()
+
+    return fn
+
+
 class Context:
     """One CUDA device + stream (b200zk_create). Mirrors the reference-side objects that own prover state."""
 
@@ -94,6 +114,32 @@ class Context:
 
     def sync(self):
         self._check(lib().b200zk_sync(self._h))
+
+    # ---- multi-GPU: MSM point-range shards + all-gather of the partial sums ----
+    def set_allgather(self, rank, world, fn):
+        """`fn(send: bytes) -> bytes` must return the concatenation of every rank's `send` in rank order (see
+        `torch_allgather`). All ranks must then call the same MSM / create_proof sequence."""
+        if world <= 1:
+            self._check(lib().b200zk_set_allgather(self._h, 0, 1, None, None))
+            self._ag = None
+            return
+
+        def trampoline(user, send, nbytes, recv):
+            try:
+                data = ctypes.string_at(send, nbytes)
+                out = fn(data)
+                if len(out) != nbytes * world:
+                    return -1
+                ctypes.memmove(recv, out, len(out))
+                return 0
+            except Exception:  # never unwind into C
+                return -2
+
+        self._ag = ALLGATHER_FN(trampoline)
+        self._check(lib().b200zk_set_allgather(self._h, int(rank), int(world), self._ag, None))
+
+    def set_msm_tables(self, on=True):
+        self._check(lib().b200zk_set_msm_tables(self._h, int(bool(on))))
 
     # ---- per-kernel-family event timing (bench.py roofline section) ----
     PROF_IDS = {"msm_accumulate": 0, "ntt_pass": 2, "quotient": 3}

@@ -7,7 +7,9 @@ using namespace b200zk;
 
 namespace b200zk {
 G1Affine msm_run(Context& ctx, const G1Affine* bases, const Fr* scalars, size_t n);
+G1Affine msm_run_srs(Context& ctx, int basis, const Fr* scalars, size_t n);
 void srs_setup(Context& ctx, uint32_t k, const Fr& s_trapdoor);
+void srs_build_tables(Context& ctx);
 }
 
 struct b200zk_ctx {
@@ -105,6 +107,29 @@ int b200zk_profile_get(b200zk_ctx* ctx, int id, double* total_ms, unsigned long 
     }
     *total_ms = tot;
     *launches = cnt;
+    API_END(ctx)
+}
+int b200zk_set_allgather(b200zk_ctx* ctx, int rank, int world, b200zk_allgather_fn fn, void* user) {
+    API_BEGIN(ctx)
+    if (world < 1 || rank < 0 || rank >= world || (world > 1 && !fn)) throw std::invalid_argument("set_allgather: bad arguments");
+    ctx->c.rank = rank;
+    ctx->c.world = world;
+    ctx->c.allgather = fn;
+    ctx->c.allgather_user = user;
+    API_END(ctx)
+}
+int b200zk_set_msm_tables(b200zk_ctx* ctx, int on) {
+    API_BEGIN(ctx)
+    ctx->c.msm_tables_enabled = on != 0;
+    if (ctx->c.srs) {
+        if (on) {
+            srs_build_tables(ctx->c);
+        } else {
+            CUDA_CHECK(cudaStreamSynchronize(ctx->c.stream));
+            ctx->c.srs->g_tab.release();
+            ctx->c.srs->gl_tab.release();
+        }
+    }
     API_END(ctx)
 }
 int b200zk_dev_alloc(b200zk_ctx* ctx, size_t bytes, void** out) {
@@ -350,6 +375,7 @@ int b200zk_srs_load(b200zk_ctx* ctx, uint32_t k, const b200zk_g1_affine* g, cons
     CUDA_CHECK(cudaMemcpyAsync(srs->g_lagrange.get(), g_lagrange, 64 * srs->n, cudaMemcpyHostToDevice, c.stream));
     CUDA_CHECK(cudaStreamSynchronize(c.stream));
     c.srs = std::move(srs);
+    srs_build_tables(c);
     API_END(ctx)
 }
 static const G1Affine* srs_basis(Context& c, int basis, size_t n) {
@@ -368,7 +394,8 @@ int b200zk_msm_bases_dev(b200zk_ctx* ctx, const b200zk_g1_affine* bases_dev, con
 int b200zk_msm_dev(b200zk_ctx* ctx, int basis, const b200zk_fr* scalars_dev, size_t n, b200zk_g1_affine* out) {
     API_BEGIN(ctx)
     if (!out || (n && !scalars_dev)) throw std::invalid_argument("msm: null argument");
-    G1Affine r = msm_run(ctx->c, srs_basis(ctx->c, basis, n), (const Fr*)scalars_dev, n);
+    srs_basis(ctx->c, basis, n);
+    G1Affine r = msm_run_srs(ctx->c, basis, (const Fr*)scalars_dev, n);
     memcpy(out, &r, 64);
     API_END(ctx)
 }
@@ -376,10 +403,10 @@ int b200zk_msm(b200zk_ctx* ctx, int basis, const b200zk_fr* scalars, size_t n, b
     API_BEGIN(ctx)
     if (!out || (n && !scalars)) throw std::invalid_argument("msm: null argument");
     Context& c = ctx->c;
-    const G1Affine* bases = srs_basis(c, basis, n);
+    srs_basis(c, basis, n);
     DevBuf<Fr> d(n, c.stream);
     if (n) CUDA_CHECK(cudaMemcpyAsync(d.get(), scalars, 32 * n, cudaMemcpyHostToDevice, c.stream));
-    G1Affine r = msm_run(c, bases, d.get(), n);
+    G1Affine r = msm_run_srs(c, basis, d.get(), n);
     memcpy(out, &r, 64);
     API_END(ctx)
 }

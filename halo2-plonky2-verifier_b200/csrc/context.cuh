@@ -67,10 +67,13 @@ struct Srs {
     uint32_t k = 0;
     size_t n = 0;
     DevBuf<G1Affine> g, g_lagrange;
+    // precomputed window tables T[w][i] = 2^(tab_c·w)·P_i (msm.cu, merged-bucket mode); empty when disabled
+    DevBuf<G1Affine> g_tab, gl_tab;
+    uint32_t tab_c = 0;
 };
+// all-gather of `bytes` from every rank into recv[world][bytes]; returns 0 on success (host buffers)
+typedef int (*AllGatherFn)(void* user, const void* send, size_t bytes, void* recv);
 
-struct MsmWorkspace;  // msm.cu
-struct ProvingKeyDev; // prover
 
 struct Context {
     int device = 0;
@@ -82,7 +85,12 @@ struct Context {
     std::map<uint32_t, std::unique_ptr<Domain>> domains;
     DevBuf<Fr> scratch;
     std::unique_ptr<Srs> srs;
-    std::shared_ptr<MsmWorkspace> msm_ws;
+    // multi-GPU: one process per GPU; MSMs are sharded by point range and partial window sums are exchanged through
+    // this callback (the host binds it to an NCCL all-gather) — SURVEY.md §8e
+    int rank = 0, world = 1;
+    AllGatherFn allgather = nullptr;
+    void* allgather_user = nullptr;
+    bool msm_tables_enabled = true;
 
     // table of the standard 2^t-th root with t >= log_n
     const TwiddleTable& std_table(uint32_t log_n) {

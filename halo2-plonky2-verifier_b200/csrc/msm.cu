@@ -23,7 +23,10 @@ namespace b200zk {
 constexpr uint32_t INVALID_KEY = 0xffffffffu;
 
 struct MsmConfig {
-    uint32_t c, W, B;  // window bits, windows, buckets per window (2^(c-1))
+    uint32_t c, W, B;   // window bits, windows, buckets per window (2^(c-1))
+    uint32_t merged;    // 1: bases are the precomputed table T[w][i] = 2^(c·w)·P_i — one bucket set for all windows
+    uint32_t groups;    // bucket sets that get reduced: W (generic) or 1 (merged)
+    unsigned long long table_n;  // row length of the precomputed table
 };
 MsmConfig msm_config(size_t n) {
     uint32_t lg = 0;
@@ -37,8 +40,22 @@ MsmConfig msm_config(size_t n) {
     m.c = c;
     m.W = (255 + c - 1) / c;
     m.B = 1u << (c - 1);
+    m.merged = 0;
+    m.groups = m.W;
+    m.table_n = 0;
     return m;
 }
+MsmConfig msm_config_merged(uint32_t c, size_t table_n) {
+    MsmConfig m;
+    m.c = c;
+    m.W = (255 + c - 1) / c;
+    m.B = 1u << (c - 1);
+    m.merged = 1;
+    m.groups = 1;
+    m.table_n = table_n;
+    return m;
+}
+uint32_t msm_table_window_bits(uint32_t k) { return k < 8 ? 8 : (k > 20 ? 20 : k); }
 
 DEV G1X g1x_load(const G1X* p) {
     G1X r;
@@ -90,12 +107,13 @@ __global__ void msm_digits_kernel(const Fr* scalars, size_t n, MsmConfig cfg, ui
         const uint32_t mag = neg ? (1u << c) - v : v;
         carry = neg ? 1u : 0u;
         if (mag == 0) continue;
-        const uint32_t bucket = w * cfg.B + mag - 1;
+        const uint32_t bucket = cfg.merged ? mag - 1 : w * cfg.B + mag - 1;
         if (mode == 0) {
             atomicAdd(counters + bucket, 1u);
         } else {
             const uint32_t pos = atomicAdd(counters + bucket, 1u);
-            entries[pos] = (uint32_t)i | (neg ? 0x80000000u : 0u);
+            const uint32_t base_index = cfg.merged ? (uint32_t)(w * cfg.table_n + i) : (uint32_t)i;
+            entries[pos] = base_index | (neg ? 0x80000000u : 0u);
         }
     }
 }
@@ -305,13 +323,12 @@ G1X msm_fold_windows(const G1X* window_sums, uint32_t W, uint32_t c) {
 }
 
 // Computes the W window sums of Σ scalars[i]·bases[i] into `window_sums_host` (XYZZ). Synchronises the stream.
-void msm_window_sums(Context& ctx, const G1Affine* bases, const Fr* scalars, size_t n, MsmConfig& cfg, std::vector<G1X>& window_sums_host) {
+void msm_window_sums(Context& ctx, const G1Affine* bases, const Fr* scalars, size_t n, const MsmConfig& cfg, std::vector<G1X>& window_sums_host) {
     cudaStream_t s = ctx.stream;
-    cfg = msm_config(n);
     if (cfg.W > (uint32_t)MAX_W) throw std::runtime_error("msm: too many windows");
-    if (n >= ((size_t)1 << 31)) throw std::invalid_argument("msm: n must be < 2^31");
-    const uint32_t nb = cfg.W * cfg.B;
-    window_sums_host.assign(cfg.W, g1x_identity());
+    if (n >= ((size_t)1 << 31) || (cfg.merged && cfg.table_n * cfg.W >= ((size_t)1 << 31))) throw std::invalid_argument("msm: index space must be < 2^31");
+    const uint32_t nb = cfg.groups * cfg.B;
+    window_sums_host.assign(cfg.groups, g1x_identity());
     if (n == 0) return;
     DevBuf<uint32_t> counters(nb + 1, s), offsets(nb + 1, s);
     CUDA_CHECK(cudaMemsetAsync(counters.get(), 0, (nb + 1) * 4, s));
@@ -359,7 +376,8 @@ void msm_window_sums(Context& ctx, const G1Affine* bases, const Fr* scalars, siz
         flip = !flip;
     }
     // reduce: recursive chunked running sums (see above)
-    DevBuf<G1X> wsums(cfg.W, s);
+    const uint32_t G = cfg.groups;
+    DevBuf<G1X> wsums(G, s);
     {
         std::vector<DevBuf<G1X>> tots, runs;
         SumLevels sl{};
@@ -368,7 +386,7 @@ void msm_window_sums(Context& ctx, const G1Affine* bases, const Fr* scalars, siz
         uint32_t len = cfg.B, level = 0;
         while (len > 1) {
             const uint32_t lm = len >= (1u << RED_LOG_M) ? RED_LOG_M : (uint32_t)__builtin_ctz(len);
-            const uint32_t m = 1u << lm, out_len = len >> lm, total_chunks = cfg.W * out_len;
+            const uint32_t m = 1u << lm, out_len = len >> lm, total_chunks = G * out_len;
             tots.emplace_back((size_t)total_chunks, s);
             runs.emplace_back((size_t)total_chunks, s);
             msm_reduce_chunks_kernel<<<(total_chunks + 127) / 128, 128, 0, s>>>(X, total_chunks, m, tots.back().get(), runs.back().get());
@@ -382,24 +400,90 @@ void msm_window_sums(Context& ctx, const G1Affine* bases, const Fr* scalars, siz
         }
         hl.levels = level;
         if (level == 0) {  // one bucket per window: F(B) = B[0]
-            CUDA_CHECK(cudaMemcpyAsync(wsums.get(), bucket_sums.get(), cfg.W * sizeof(G1X), cudaMemcpyDeviceToDevice, s));
+            CUDA_CHECK(cudaMemcpyAsync(wsums.get(), bucket_sums.get(), G * sizeof(G1X), cudaMemcpyDeviceToDevice, s));
         } else {
-            DevBuf<G1X> T((size_t)level * cfg.W, s);
-            msm_reduce_sum_kernel<<<dim3(cfg.W, level), 128, 0, s>>>(sl, cfg.W, T.get());
-            msm_reduce_horner_kernel<<<(cfg.W + 31) / 32, 32, 0, s>>>(T.get(), X, hl, cfg.W, wsums.get());
+            DevBuf<G1X> T((size_t)level * G, s);
+            msm_reduce_sum_kernel<<<dim3(G, level), 128, 0, s>>>(sl, G, T.get());
+            msm_reduce_horner_kernel<<<(G + 31) / 32, 32, 0, s>>>(T.get(), X, hl, G, wsums.get());
             g_launch_count += 2;
         }
         CUDA_CHECK(cudaGetLastError());
     }
-    CUDA_CHECK(cudaMemcpyAsync(window_sums_host.data(), wsums.get(), cfg.W * sizeof(G1X), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaMemcpyAsync(window_sums_host.data(), wsums.get(), G * sizeof(G1X), cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
 }
 
+// optional cross-rank combine of partial window sums (set through b200zk_set_allgather)
+static void combine_across_ranks(Context& ctx, std::vector<G1X>& ws) {
+    if (ctx.world <= 1 || !ctx.allgather) return;
+    const size_t bytes = ws.size() * sizeof(G1X);
+    std::vector<G1X> all(ws.size() * ctx.world);
+    if (ctx.allgather(ctx.allgather_user, ws.data(), bytes, all.data()) != 0) throw std::runtime_error("msm: all-gather callback failed");
+    for (size_t w = 0; w < ws.size(); ++w) {
+        G1X acc = g1x_identity();
+        for (int r = 0; r < ctx.world; ++r) acc = g1x_add(acc, all[(size_t)r * ws.size() + w]);
+        ws[w] = acc;
+    }
+}
+// point range of this rank for an n-point MSM (contiguous shards; the last rank takes the remainder)
+static void shard_range(const Context& ctx, size_t n, size_t& lo, size_t& len) {
+    if (ctx.world <= 1 || !ctx.allgather) {
+        lo = 0;
+        len = n;
+        return;
+    }
+    const size_t per = n / ctx.world;
+    lo = per * ctx.rank;
+    len = ctx.rank == ctx.world - 1 ? n - lo : per;
+}
+
+// arbitrary bases (best_multiexp): windows kept separate, folded on the host
 G1Affine msm_run(Context& ctx, const G1Affine* bases, const Fr* scalars, size_t n) {
-    MsmConfig cfg;
+    const MsmConfig cfg = msm_config(n);
+    size_t lo, len;
+    shard_range(ctx, n, lo, len);
     std::vector<G1X> ws;
-    msm_window_sums(ctx, bases, scalars, n, cfg, ws);
+    msm_window_sums(ctx, bases + lo, scalars + lo, len, cfg, ws);
+    combine_across_ranks(ctx, ws);
     return g1x_to_affine(msm_fold_windows(ws.data(), cfg.W, cfg.c));
+}
+
+// SRS bases: uses the precomputed window table when it exists (one bucket set, no fold)
+G1Affine msm_run_srs(Context& ctx, int basis, const Fr* scalars, size_t n) {
+    const Srs& srs = *ctx.srs;
+    const DevBuf<G1Affine>& tab = basis == 0 ? srs.g_tab : srs.gl_tab;
+    if (tab.size() == 0 || n * 8 < srs.n) return msm_run(ctx, basis == 0 ? srs.g.get() : srs.g_lagrange.get(), scalars, n);
+    const MsmConfig cfg = msm_config_merged(srs.tab_c, srs.n);
+    size_t lo, len;
+    shard_range(ctx, n, lo, len);
+    std::vector<G1X> ws;
+    msm_window_sums(ctx, tab.get() + lo, scalars + lo, len, cfg, ws);
+    combine_across_ranks(ctx, ws);
+    return g1x_to_affine(ws[0]);
+}
+
+// T[w][i] = 2^(c·w)·P_i as affine points, w < W: built once per SRS
+__global__ void __launch_bounds__(128) msm_table_step_kernel(const G1Affine* prev, G1Affine* next, size_t n, uint32_t c) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1Affine p;
+    p.x = f_load(&prev[i].x);
+    p.y = f_load(&prev[i].y);
+    G1X a = g1x_from_affine(p);
+    for (uint32_t d = 0; d < c; ++d) a = g1x_dbl(a);
+    const G1Affine r = g1x_to_affine(a);
+    f_store(&next[i].x, r.x);
+    f_store(&next[i].y, r.y);
+}
+void msm_build_table(Context& ctx, const G1Affine* bases, size_t n, uint32_t c, DevBuf<G1Affine>& table) {
+    const uint32_t W = (255 + c - 1) / c;
+    table.alloc((size_t)W * n, ctx.stream);
+    CUDA_CHECK(cudaMemcpyAsync(table.get(), bases, n * sizeof(G1Affine), cudaMemcpyDeviceToDevice, ctx.stream));
+    for (uint32_t w = 1; w < W; ++w) {
+        msm_table_step_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx.stream>>>(table.get() + (size_t)(w - 1) * n, table.get() + (size_t)w * n, n, c);
+        ++g_launch_count;
+    }
+    CUDA_CHECK(cudaGetLastError());
 }
 
 }  // namespace b200zk

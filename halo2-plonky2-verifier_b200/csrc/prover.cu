@@ -12,15 +12,15 @@
 
 namespace b200zk {
 
-G1Affine msm_run(Context& ctx, const G1Affine* bases, const Fr* scalars, size_t n);
+G1Affine msm_run_srs(Context& ctx, int basis, const Fr* scalars, size_t n);
 
 static const Srs& need_srs(Context& ctx, uint32_t k) {
     if (!ctx.srs) throw std::runtime_error("no SRS loaded");
     if (ctx.srs->k != k) throw std::runtime_error("SRS size does not match the circuit (k)");
     return *ctx.srs;
 }
-static G1Affine commit_lagrange(Context& ctx, const Fr* evals, size_t n) { return msm_run(ctx, ctx.srs->g_lagrange.get(), evals, n); }
-static G1Affine commit_coeff(Context& ctx, const Fr* coeffs, size_t n) { return msm_run(ctx, ctx.srs->g.get(), coeffs, n); }
+static G1Affine commit_lagrange(Context& ctx, const Fr* evals, size_t n) { return msm_run_srs(ctx, 1, evals, n); }
+static G1Affine commit_coeff(Context& ctx, const Fr* coeffs, size_t n) { return msm_run_srs(ctx, 0, coeffs, n); }
 
 // ---- permutation::keygen::Assembly (host, serial — as upstream) ------------------------------------------------------
 struct Assembly {

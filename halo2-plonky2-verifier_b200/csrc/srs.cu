@@ -39,6 +39,21 @@ __global__ void __launch_bounds__(128) fixed_base_kernel(const Fr* scalars, size
     f_store(&out[i].y, r.y);
 }
 
+void msm_build_table(Context& ctx, const G1Affine* bases, size_t n, uint32_t c, DevBuf<G1Affine>& table);
+uint32_t msm_table_window_bits(uint32_t k);
+
+// window tables for both bases of the loaded SRS (msm.cu merged-bucket mode)
+void srs_build_tables(Context& ctx) {
+    if (!ctx.srs || !ctx.msm_tables_enabled) return;
+    Srs& srs = *ctx.srs;
+    srs.tab_c = msm_table_window_bits(srs.k);
+    const uint32_t W = (255 + srs.tab_c - 1) / srs.tab_c;
+    if ((size_t)W * srs.n >= ((size_t)1 << 31)) return;  // entry indices are 31-bit: fall back to the generic path
+    msm_build_table(ctx, srs.g.get(), srs.n, srs.tab_c, srs.g_tab);
+    msm_build_table(ctx, srs.g_lagrange.get(), srs.n, srs.tab_c, srs.gl_tab);
+    CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+}
+
 static std::vector<G1Affine> build_generator_table() {
     std::vector<G1Affine> t(32 * 255);
     G1Affine gen;
@@ -86,6 +101,7 @@ void srs_setup(Context& ctx, uint32_t k, const Fr& s_trapdoor) {
     LAUNCHED(2);
     CUDA_CHECK(cudaStreamSynchronize(st));
     ctx.srs = std::move(srs);
+    srs_build_tables(ctx);
 }
 
 }  // namespace b200zk

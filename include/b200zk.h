@@ -55,6 +55,15 @@ B200ZK_API void* b200zk_stream(b200zk_ctx* ctx);
 B200ZK_API int b200zk_sync(b200zk_ctx* ctx);
 /* kernels launched by this library since process start (bench.py "gpu_launches") */
 B200ZK_API unsigned long long b200zk_launch_count(void);
+/* Multi-GPU (one process per GPU): every MSM is sharded by contiguous point range — this rank handles
+ * range `rank` of `world` — and the per-rank partial sums (one XYZZ point per bucket set, 128 B each) are exchanged through
+ * `fn`, which must all-gather `bytes` bytes from every rank into recv[world][bytes] (host buffers; bind it to an NCCL or
+ * MPI all-gather) and return 0. All ranks must issue the same MSM calls in the same order. world = 1 disables it. */
+typedef int (*b200zk_allgather_fn)(void* user, const void* send, size_t bytes, void* recv);
+B200ZK_API int b200zk_set_allgather(b200zk_ctx* ctx, int rank, int world, b200zk_allgather_fn fn, void* user);
+/* Precomputed window tables 2^(c·w)·P_i for the SRS bases (one bucket set per MSM, no host fold; costs W× SRS memory).
+ * On by default; switch off before loading a large SRS to save memory. */
+B200ZK_API int b200zk_set_msm_tables(b200zk_ctx* ctx, int on);
 /* per-kernel-family CUDA-event timing (off by default). ids: 0 msm_accumulate, 1 (reserved), 2 ntt_pass, 3 quotient.
  * profile_get synchronises, sums the spans recorded since the last reset and clears them. */
 B200ZK_API int b200zk_profile_enable(b200zk_ctx* ctx, int on);

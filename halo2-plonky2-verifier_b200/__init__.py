@@ -271,6 +271,13 @@ class Context:
         self._check(lib().b200zk_msm_dev(self._h, int(basis), ctypes.c_void_p(scalars_ptr), ctypes.c_size_t(n), _p(out)))
         return out
 
+    def msm_batch_dev(self, col_ptrs, n, basis=0):
+        """Commit several device-resident columns over one basis (one bucket reduction for the batch)."""
+        arr = (ctypes.c_void_p * len(col_ptrs))(*col_ptrs)
+        out = np.empty((len(col_ptrs), 8), dtype=np.uint64)
+        self._check(lib().b200zk_msm_batch_dev(self._h, int(basis), arr, ctypes.c_size_t(len(col_ptrs)), ctypes.c_size_t(n), _p(out)))
+        return out
+
     def msm_bases(self, scalars, bases):
         """halo2curves::msm::best_multiexp(coeffs, bases) with caller-supplied bases."""
         scalars = _c(scalars).reshape(-1, 4)

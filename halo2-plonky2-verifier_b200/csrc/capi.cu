@@ -8,6 +8,7 @@ using namespace b200zk;
 namespace b200zk {
 G1Affine msm_run(Context& ctx, const G1Affine* bases, const Fr* scalars, size_t n);
 G1Affine msm_run_srs(Context& ctx, int basis, const Fr* scalars, size_t n);
+void msm_batch_srs(Context& ctx, int basis, const Fr* const* cols, size_t ncols, size_t n, G1Affine* out);
 void srs_setup(Context& ctx, uint32_t k, const Fr& s_trapdoor);
 void srs_build_tables(Context& ctx);
 }
@@ -397,6 +398,15 @@ int b200zk_msm_dev(b200zk_ctx* ctx, int basis, const b200zk_fr* scalars_dev, siz
     srs_basis(ctx->c, basis, n);
     G1Affine r = msm_run_srs(ctx->c, basis, (const Fr*)scalars_dev, n);
     memcpy(out, &r, 64);
+    API_END(ctx)
+}
+int b200zk_msm_batch_dev(b200zk_ctx* ctx, int basis, const b200zk_fr* const* cols_dev, size_t ncols, size_t n, b200zk_g1_affine* out) {
+    API_BEGIN(ctx)
+    if (!out || (ncols && !cols_dev)) throw std::invalid_argument("msm_batch: null argument");
+    srs_basis(ctx->c, basis, n);
+    std::vector<G1Affine> r(ncols);
+    if (ncols) msm_batch_srs(ctx->c, basis, (const Fr* const*)cols_dev, ncols, n, r.data());
+    memcpy(out, r.data(), 64 * ncols);
     API_END(ctx)
 }
 int b200zk_msm(b200zk_ctx* ctx, int basis, const b200zk_fr* scalars, size_t n, b200zk_g1_affine* out) {

@@ -16,6 +16,8 @@
 //   5. fold     : Σ 2^(c·w)·S_w over W window sums — 254 dependent doublings, done on the host in 64-bit limbs
 //                 (≈0.1 ms) because a single GPU thread would take longer than the whole MSM.
 // Bound: integer pipe (≈10 Fq products per point·window), not HBM; see DESIGN.md.
+#include <algorithm>
+
 #include "context.cuh"
 
 namespace b200zk {
@@ -274,25 +276,28 @@ __global__ void __launch_bounds__(128) msm_reduce_chunks_kernel(const G1X* X, ui
     g1x_store(tot_out + j, tot);
     g1x_store(run_out + j, run);
 }
-// one block per (window, level): T[level·W + w] = Σ_q tot_level[w·len + q]
+// Σ over lists: block (w, level, slice) sums entries [slice·SUM_SLICE, (slice+1)·SUM_SLICE) of tot_level[w·len ..]
+// into out[(level·W + w)·slices + slice]. Called twice: lists -> per-slice partials -> T[level·W + w].
+constexpr uint32_t SUM_SLICE = 1024;
 struct SumLevels {
     const G1X* tot[16];
     uint32_t len[16];
 };
-__global__ void __launch_bounds__(128) msm_reduce_sum_kernel(SumLevels lv, uint32_t W, G1X* T) {
+__global__ void __launch_bounds__(128) msm_reduce_sum_kernel(SumLevels lv, uint32_t W, uint32_t slices, G1X* out) {
     __shared__ G1X sh[128];
-    const uint32_t w = blockIdx.x, level = blockIdx.y;
+    const uint32_t w = blockIdx.x, level = blockIdx.y, slice = blockIdx.z;
     const uint32_t len = lv.len[level];
     const G1X* src = lv.tot[level] + (size_t)w * len;
+    const uint32_t lo = slice * SUM_SLICE, hi = lo + SUM_SLICE < len ? lo + SUM_SLICE : len;
     G1X acc = g1x_identity();
-    for (uint32_t q = threadIdx.x; q < len; q += blockDim.x) acc = g1x_add(acc, g1x_load(src + q));
+    for (uint32_t q = lo + threadIdx.x; q < hi; q += blockDim.x) acc = g1x_add(acc, g1x_load(src + q));
     sh[threadIdx.x] = acc;
     __syncthreads();
     for (uint32_t s = blockDim.x / 2; s > 0; s >>= 1) {
-        if (threadIdx.x < s && threadIdx.x + s < len) sh[threadIdx.x] = g1x_add(sh[threadIdx.x], sh[threadIdx.x + s]);
+        if (threadIdx.x < s) sh[threadIdx.x] = g1x_add(sh[threadIdx.x], sh[threadIdx.x + s]);
         __syncthreads();
     }
-    if (threadIdx.x == 0) g1x_store(T + (size_t)level * W + w, sh[0]);
+    if (threadIdx.x == 0) g1x_store(out + ((size_t)level * W + w) * slices + slice, sh[0]);
 }
 // one thread per window: Horner over the levels. S[w] = the single entry of the last run list.
 struct HornerLevels {
@@ -322,13 +327,11 @@ G1X msm_fold_windows(const G1X* window_sums, uint32_t W, uint32_t c) {
     return acc;
 }
 
-// Computes the W window sums of Σ scalars[i]·bases[i] into `window_sums_host` (XYZZ). Synchronises the stream.
-void msm_window_sums(Context& ctx, const G1Affine* bases, const Fr* scalars, size_t n, const MsmConfig& cfg, std::vector<G1X>& window_sums_host) {
+// Phase A of one MSM: digits -> counting sort -> chunked accumulation -> head combine. Leaves the bucket sums of this
+// column in bucket_sums[0 .. groups·B) (zero-initialised by the caller). Synchronises once (entry count).
+static void msm_bucket_sums(Context& ctx, const G1Affine* bases, const Fr* scalars, size_t n, const MsmConfig& cfg, G1X* bucket_sums) {
     cudaStream_t s = ctx.stream;
-    if (cfg.W > (uint32_t)MAX_W) throw std::runtime_error("msm: too many windows");
-    if (n >= ((size_t)1 << 31) || (cfg.merged && cfg.table_n * cfg.W >= ((size_t)1 << 31))) throw std::invalid_argument("msm: index space must be < 2^31");
     const uint32_t nb = cfg.groups * cfg.B;
-    window_sums_host.assign(cfg.groups, g1x_identity());
     if (n == 0) return;
     DevBuf<uint32_t> counters(nb + 1, s), offsets(nb + 1, s);
     CUDA_CHECK(cudaMemsetAsync(counters.get(), 0, (nb + 1) * 4, s));
@@ -344,15 +347,13 @@ void msm_window_sums(Context& ctx, const G1Affine* bases, const Fr* scalars, siz
     DevBuf<uint32_t> entries(total, s);
     msm_digits_kernel<<<dblocks, 128, 0, s>>>(scalars, n, cfg, counters.get(), entries.get(), 1);
     ++g_launch_count;
-    DevBuf<G1X> bucket_sums(nb, s);
-    CUDA_CHECK(cudaMemsetAsync(bucket_sums.get(), 0, (size_t)nb * sizeof(G1X), s));
     // level 1
     uint32_t nthreads = (uint32_t)(((uint64_t)total + ACC_T - 1) / ACC_T);
     DevBuf<G1X> heads_a(nthreads, s), heads_b;
     DevBuf<uint32_t> keys_a(nthreads, s), keys_b;
     prof_begin(PROF_MSM_ACCUMULATE, s);
-    msm_accumulate_kernel<<<(nthreads + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, s>>>(bases, entries.get(), offsets.get(), nb, total,
-                                                                                              bucket_sums.get(), heads_a.get(), keys_a.get());
+    msm_accumulate_kernel<<<(nthreads + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, s>>>(bases, entries.get(), offsets.get(), nb, total, bucket_sums,
+                                                                                              heads_a.get(), keys_a.get());
     prof_end(s);
     ++g_launch_count;
     CUDA_CHECK(cudaGetLastError());
@@ -367,23 +368,28 @@ void msm_window_sums(Context& ctx, const G1Affine* bases, const Fr* scalars, siz
         DevBuf<uint32_t>& out_k = flip ? keys_a : keys_b;
         out_p.alloc(nt, s);
         out_k.alloc(nt, s);
-        msm_combine_kernel<<<(nt + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, s>>>(in_p.get(), in_k.get(), len, bucket_sums.get(), out_p.get(),
-                                                                                        out_k.get());
+        msm_combine_kernel<<<(nt + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, s>>>(in_p.get(), in_k.get(), len, bucket_sums, out_p.get(), out_k.get());
         ++g_launch_count;
         CUDA_CHECK(cudaGetLastError());
         if (nt == 1) break;  // a single thread has no predecessor: nothing can be left in its head slot
         len = nt;
         flip = !flip;
     }
-    // reduce: recursive chunked running sums (see above)
-    const uint32_t G = cfg.groups;
+}
+
+// Phase B for `G` bucket sets of B buckets each (window-major): F(set) = Σ_b (b+1)·bucket[b] -> sums_host[G] (XYZZ).
+// One reduction serves every column of a batch: the deep levels are latency bound (≈0.12 ms each whatever G is).
+static void msm_reduce_groups(Context& ctx, const G1X* bucket_sums, uint32_t G, uint32_t B, std::vector<G1X>& sums_host) {
+    cudaStream_t s = ctx.stream;
+    sums_host.assign(G, g1x_identity());
+    if (G == 0) return;
     DevBuf<G1X> wsums(G, s);
     {
         std::vector<DevBuf<G1X>> tots, runs;
         SumLevels sl{};
         HornerLevels hl{};
-        const G1X* X = bucket_sums.get();
-        uint32_t len = cfg.B, level = 0;
+        const G1X* X = bucket_sums;
+        uint32_t len = B, level = 0;
         while (len > 1) {
             const uint32_t lm = len >= (1u << RED_LOG_M) ? RED_LOG_M : (uint32_t)__builtin_ctz(len);
             const uint32_t m = 1u << lm, out_len = len >> lm, total_chunks = G * out_len;
@@ -399,17 +405,33 @@ void msm_window_sums(Context& ctx, const G1Affine* bases, const Fr* scalars, siz
             ++level;
         }
         hl.levels = level;
-        if (level == 0) {  // one bucket per window: F(B) = B[0]
-            CUDA_CHECK(cudaMemcpyAsync(wsums.get(), bucket_sums.get(), G * sizeof(G1X), cudaMemcpyDeviceToDevice, s));
+        if (level == 0) {  // one bucket per set: F = bucket[0]
+            CUDA_CHECK(cudaMemcpyAsync(wsums.get(), bucket_sums, G * sizeof(G1X), cudaMemcpyDeviceToDevice, s));
         } else {
             DevBuf<G1X> T((size_t)level * G, s);
-            msm_reduce_sum_kernel<<<dim3(G, level), 128, 0, s>>>(sl, G, T.get());
+            uint32_t max_len = 0;
+            for (uint32_t l = 0; l < level; ++l) max_len = std::max(max_len, sl.len[l]);
+            const uint32_t slices = (max_len + SUM_SLICE - 1) / SUM_SLICE;
+            if (slices <= 1) {
+                msm_reduce_sum_kernel<<<dim3(G, level, 1), 128, 0, s>>>(sl, G, 1, T.get());
+                ++g_launch_count;
+            } else {
+                DevBuf<G1X> part((size_t)level * G * slices, s);  // slices beyond a short list sum to the identity
+                msm_reduce_sum_kernel<<<dim3(G, level, slices), 128, 0, s>>>(sl, G, slices, part.get());
+                SumLevels sl2{};
+                for (uint32_t l = 0; l < level; ++l) {
+                    sl2.tot[l] = part.get() + (size_t)l * G * slices;
+                    sl2.len[l] = slices;
+                }
+                msm_reduce_sum_kernel<<<dim3(G, level, 1), 128, 0, s>>>(sl2, G, 1, T.get());
+                g_launch_count += 2;
+            }
             msm_reduce_horner_kernel<<<(G + 31) / 32, 32, 0, s>>>(T.get(), X, hl, G, wsums.get());
-            g_launch_count += 2;
+            ++g_launch_count;
         }
         CUDA_CHECK(cudaGetLastError());
     }
-    CUDA_CHECK(cudaMemcpyAsync(window_sums_host.data(), wsums.get(), G * sizeof(G1X), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaMemcpyAsync(sums_host.data(), wsums.get(), G * sizeof(G1X), cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
 }
 
@@ -437,29 +459,52 @@ static void shard_range(const Context& ctx, size_t n, size_t& lo, size_t& len) {
     len = ctx.rank == ctx.world - 1 ? n - lo : per;
 }
 
-// arbitrary bases (best_multiexp): windows kept separate, folded on the host
-G1Affine msm_run(Context& ctx, const G1Affine* bases, const Fr* scalars, size_t n) {
-    const MsmConfig cfg = msm_config(n);
+static void check_cfg(const MsmConfig& cfg, size_t n) {
+    if (cfg.W > (uint32_t)MAX_W) throw std::runtime_error("msm: too many windows");
+    if (n >= ((size_t)1 << 31) || (cfg.merged && cfg.table_n * cfg.W >= ((size_t)1 << 31))) throw std::invalid_argument("msm: index space must be < 2^31");
+}
+// `ncols` MSMs over the same bases: per-column bucket accumulation, ONE reduction for all columns, one exchange across ranks.
+static void msm_batch_core(Context& ctx, const G1Affine* bases, const Fr* const* cols, size_t ncols, size_t n, const MsmConfig& cfg, G1Affine* out) {
+    check_cfg(cfg, n);
+    cudaStream_t s = ctx.stream;
     size_t lo, len;
     shard_range(ctx, n, lo, len);
-    std::vector<G1X> ws;
-    msm_window_sums(ctx, bases + lo, scalars + lo, len, cfg, ws);
-    combine_across_ranks(ctx, ws);
-    return g1x_to_affine(msm_fold_windows(ws.data(), cfg.W, cfg.c));
+    const uint32_t nb = cfg.groups * cfg.B;
+    // bound the scratch: at most 16 columns (≈1 GiB of bucket sums at c = 20) per reduction round
+    const size_t round = 16;
+    for (size_t c0 = 0; c0 < ncols; c0 += round) {
+        const size_t nc = std::min(round, ncols - c0);
+        DevBuf<G1X> bucket_sums((size_t)nc * nb, s);
+        CUDA_CHECK(cudaMemsetAsync(bucket_sums.get(), 0, (size_t)nc * nb * sizeof(G1X), s));
+        for (size_t j = 0; j < nc; ++j) msm_bucket_sums(ctx, bases + lo, cols[c0 + j] + lo, len, cfg, bucket_sums.get() + j * nb);
+        std::vector<G1X> ws;
+        msm_reduce_groups(ctx, bucket_sums.get(), (uint32_t)(nc * cfg.groups), cfg.B, ws);
+        combine_across_ranks(ctx, ws);
+        for (size_t j = 0; j < nc; ++j)
+            out[c0 + j] = cfg.merged ? g1x_to_affine(ws[j]) : g1x_to_affine(msm_fold_windows(ws.data() + j * cfg.W, cfg.W, cfg.c));
+    }
+}
+
+// arbitrary bases (best_multiexp): windows kept separate, folded on the host
+G1Affine msm_run(Context& ctx, const G1Affine* bases, const Fr* scalars, size_t n) {
+    G1Affine r;
+    msm_batch_core(ctx, bases, &scalars, 1, n, msm_config(n), &r);
+    return r;
 }
 
 // SRS bases: uses the precomputed window table when it exists (one bucket set, no fold)
-G1Affine msm_run_srs(Context& ctx, int basis, const Fr* scalars, size_t n) {
+void msm_batch_srs(Context& ctx, int basis, const Fr* const* cols, size_t ncols, size_t n, G1Affine* out) {
     const Srs& srs = *ctx.srs;
     const DevBuf<G1Affine>& tab = basis == 0 ? srs.g_tab : srs.gl_tab;
-    if (tab.size() == 0 || n * 8 < srs.n) return msm_run(ctx, basis == 0 ? srs.g.get() : srs.g_lagrange.get(), scalars, n);
-    const MsmConfig cfg = msm_config_merged(srs.tab_c, srs.n);
-    size_t lo, len;
-    shard_range(ctx, n, lo, len);
-    std::vector<G1X> ws;
-    msm_window_sums(ctx, tab.get() + lo, scalars + lo, len, cfg, ws);
-    combine_across_ranks(ctx, ws);
-    return g1x_to_affine(ws[0]);
+    if (tab.size() == 0 || n * 8 < srs.n)
+        msm_batch_core(ctx, basis == 0 ? srs.g.get() : srs.g_lagrange.get(), cols, ncols, n, msm_config(n), out);
+    else
+        msm_batch_core(ctx, tab.get(), cols, ncols, n, msm_config_merged(srs.tab_c, srs.n), out);
+}
+G1Affine msm_run_srs(Context& ctx, int basis, const Fr* scalars, size_t n) {
+    G1Affine r;
+    msm_batch_srs(ctx, basis, &scalars, 1, n, &r);
+    return r;
 }
 
 // T[w][i] = 2^(c·w)·P_i as affine points, w < W: built once per SRS

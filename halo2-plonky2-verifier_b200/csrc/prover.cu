@@ -13,14 +13,22 @@
 namespace b200zk {
 
 G1Affine msm_run_srs(Context& ctx, int basis, const Fr* scalars, size_t n);
+void msm_batch_srs(Context& ctx, int basis, const Fr* const* cols, size_t ncols, size_t n, G1Affine* out);
 
 static const Srs& need_srs(Context& ctx, uint32_t k) {
     if (!ctx.srs) throw std::runtime_error("no SRS loaded");
     if (ctx.srs->k != k) throw std::runtime_error("SRS size does not match the circuit (k)");
     return *ctx.srs;
 }
-static G1Affine commit_lagrange(Context& ctx, const Fr* evals, size_t n) { return msm_run_srs(ctx, 1, evals, n); }
 static G1Affine commit_coeff(Context& ctx, const Fr* coeffs, size_t n) { return msm_run_srs(ctx, 0, coeffs, n); }
+// commitments of `count` columns `stride` apart: bucket accumulation per column, one bucket reduction for the batch
+static std::vector<G1Affine> commit_batch(Context& ctx, int basis, const Fr* first, size_t stride, size_t count, size_t n) {
+    std::vector<const Fr*> cols(count);
+    for (size_t i = 0; i < count; ++i) cols[i] = first + i * stride;
+    std::vector<G1Affine> out(count);
+    if (count) msm_batch_srs(ctx, basis, cols.data(), count, n, out.data());
+    return out;
+}
 
 // ---- permutation::keygen::Assembly (host, serial — as upstream) ------------------------------------------------------
 struct Assembly {
@@ -116,8 +124,8 @@ std::unique_ptr<ProvingKeyDev> keygen(Context& ctx, const Shape& sh, const Fr* f
         CUDA_CHECK(cudaStreamSynchronize(s));  // host staging vectors go out of scope
     }
     // keygen_vk: commitments (Lagrange basis, no blinding)
-    for (uint32_t i = 0; i < NF; ++i) pk->fixed_commitments.push_back(commit_lagrange(ctx, pk->fixed_values.get() + (size_t)i * n, n));
-    for (uint32_t j = 0; j < P; ++j) pk->perm_commitments.push_back(commit_lagrange(ctx, pk->sigma_values.get() + (size_t)j * n, n));
+    pk->fixed_commitments = commit_batch(ctx, 1, pk->fixed_values.get(), n, NF, n);
+    pk->perm_commitments = commit_batch(ctx, 1, pk->sigma_values.get(), n, P, n);
     pk->transcript_repr = default_transcript_repr(*pk);
     // keygen_pk: coefficient forms and extended cosets
     pk->fixed_polys.alloc((size_t)NF * n, s);
@@ -303,16 +311,18 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
         CUDA_CHECK(cudaStreamSynchronize(s));
     }
     lap(tm ? &tm->upload : nullptr);
-    for (uint32_t c = 0; c < NA; ++c) tr.write_point(commit_lagrange(ctx, advice.get() + (size_t)c * n, n));
+    for (const G1Affine& cm : commit_batch(ctx, 1, advice.get(), n, NA, n)) tr.write_point(cm);
     lap(tm ? &tm->msm : nullptr);
     const Fr theta = tr.squeeze_challenge();
     (void)theta;  // single-expression lookups: theta-compression is the identity
     // step 3: lookups, permuted columns (D.4)
     const Fr* table_values = pk.fixed_values.get() + (size_t)sh.table_col() * n;
     DevBuf<Fr> perm_in((size_t)L * n, s), perm_tab((size_t)L * n, s), perm_in_poly((size_t)L * n, s), perm_tab_poly((size_t)L * n, s);
+    // perm_cols holds a'_0, s'_0, a'_1, s'_1, ... so that one batch commits them in transcript order
+    DevBuf<Fr> perm_cols((size_t)2 * L * n, s);
     for (uint32_t l = 0; l < L; ++l) {
-        Fr* a_out = perm_in.get() + (size_t)l * n;
-        Fr* s_out = perm_tab.get() + (size_t)l * n;
+        Fr* a_out = perm_cols.get() + (size_t)(2 * l) * n;
+        Fr* s_out = perm_cols.get() + (size_t)(2 * l + 1) * n;
         if (!lookup_permute(ctx, advice.get() + (size_t)(A + l) * n, table_values, a_out, s_out, n, u))
             throw SynthesisError("ConstraintSystemFailure: lookup input not in table");
         std::vector<Fr> blind(2 * (bf + 1));
@@ -320,19 +330,24 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
         CUDA_CHECK(cudaMemcpyAsync(a_out + u, blind.data(), (bf + 1) * sizeof(Fr), cudaMemcpyHostToDevice, s));
         CUDA_CHECK(cudaMemcpyAsync(s_out + u, blind.data() + bf + 1, (bf + 1) * sizeof(Fr), cudaMemcpyHostToDevice, s));
         CUDA_CHECK(cudaStreamSynchronize(s));
-        lap(tm ? &tm->lookup : nullptr);
-        rng.skip(1);
-        const G1Affine ca = commit_lagrange(ctx, a_out, n);
-        rng.skip(1);
-        const G1Affine cs = commit_lagrange(ctx, s_out, n);
+        rng.skip(2);  // the two Blind(..) draws of commit_values
+    }
+    lap(tm ? &tm->lookup : nullptr);
+    {
+        const std::vector<G1Affine> cms = commit_batch(ctx, 1, perm_cols.get(), n, 2 * L, n);
         lap(tm ? &tm->msm : nullptr);
-        CUDA_CHECK(cudaMemcpyAsync(perm_in_poly.get() + (size_t)l * n, a_out, n * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
-        CUDA_CHECK(cudaMemcpyAsync(perm_tab_poly.get() + (size_t)l * n, s_out, n * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
-        dev_lagrange_to_coeff(ctx, sh.k, perm_in_poly.get() + (size_t)l * n);
-        dev_lagrange_to_coeff(ctx, sh.k, perm_tab_poly.get() + (size_t)l * n);
+        for (uint32_t l = 0; l < L; ++l) {
+            CUDA_CHECK(cudaMemcpyAsync(perm_in.get() + (size_t)l * n, perm_cols.get() + (size_t)(2 * l) * n, n * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
+            CUDA_CHECK(cudaMemcpyAsync(perm_tab.get() + (size_t)l * n, perm_cols.get() + (size_t)(2 * l + 1) * n, n * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
+        }
+        CUDA_CHECK(cudaMemcpyAsync(perm_in_poly.get(), perm_in.get(), (size_t)L * n * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
+        CUDA_CHECK(cudaMemcpyAsync(perm_tab_poly.get(), perm_tab.get(), (size_t)L * n * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
+        if (L) {
+            dev_lagrange_to_coeff(ctx, sh.k, perm_in_poly.get(), L, n);
+            dev_lagrange_to_coeff(ctx, sh.k, perm_tab_poly.get(), L, n);
+        }
         lap(tm ? &tm->ntt : nullptr);
-        tr.write_point(ca);
-        tr.write_point(cs);
+        for (const G1Affine& cm : cms) tr.write_point(cm);
     }
     const Fr beta = tr.squeeze_challenge();
     const Fr gamma = tr.squeeze_challenge();
@@ -342,9 +357,10 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
     };
     DevBuf<Fr> z_polys((size_t)NS * n, s), z_cosets((size_t)NS * en, s);
     {
-        DevBuf<Fr> m(n, s), z(n, s);
+        DevBuf<Fr> m(n, s);
         Fr delta_pow = one, last_z = one;
         for (uint32_t set = 0; set < NS; ++set) {
+            Fr* z = z_polys.get() + (size_t)set * n;  // Lagrange values first, converted in place after the commit
             const uint32_t j0 = set * Shape::chunk_len, j1 = std::min(P, j0 + Shape::chunk_len);
             for (uint32_t j = j0; j < j1; ++j) perm_denominator(m.get(), perm_values(j), pk.sigma_values.get() + (size_t)j * n, beta, gamma, n, j == j0, s);
             fr_batch_invert(m.get(), n, s);
@@ -352,23 +368,21 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
                 perm_numerator(m.get(), perm_values(j), f_mul(delta_pow, beta), gamma, tw.t.get(), tw.log_n, sh.k, s);
                 delta_pow = f_mul(delta_pow, FrConsts::delta());
             }
-            fr_prefix_product(z.get(), m.get(), last_z, n, s);
+            fr_prefix_product(z, m.get(), last_z, n, s);
             std::vector<Fr> blind(bf);
             for (auto& b : blind) b = rng.next();
-            CUDA_CHECK(cudaMemcpyAsync(z.get() + (n - bf), blind.data(), bf * sizeof(Fr), cudaMemcpyHostToDevice, s));
-            CUDA_CHECK(cudaMemcpyAsync(&last_z, z.get() + (n - bf - 1), sizeof(Fr), cudaMemcpyDeviceToHost, s));
+            CUDA_CHECK(cudaMemcpyAsync(z + (n - bf), blind.data(), bf * sizeof(Fr), cudaMemcpyHostToDevice, s));
+            CUDA_CHECK(cudaMemcpyAsync(&last_z, z + (n - bf - 1), sizeof(Fr), cudaMemcpyDeviceToHost, s));
             CUDA_CHECK(cudaStreamSynchronize(s));
             rng.skip(1);
-            lap(tm ? &tm->products : nullptr);
-            const G1Affine cm = commit_lagrange(ctx, z.get(), n);
-            lap(tm ? &tm->msm : nullptr);
-            Fr* zp = z_polys.get() + (size_t)set * n;
-            CUDA_CHECK(cudaMemcpyAsync(zp, z.get(), n * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
-            dev_lagrange_to_coeff(ctx, sh.k, zp);
-            dev_coeff_to_extended(ctx, sh.k, zp, z_cosets.get() + (size_t)set * en);
-            lap(tm ? &tm->ntt : nullptr);
-            tr.write_point(cm);
         }
+        lap(tm ? &tm->products : nullptr);
+        const std::vector<G1Affine> cms = commit_batch(ctx, 1, z_polys.get(), n, NS, n);
+        lap(tm ? &tm->msm : nullptr);
+        dev_lagrange_to_coeff(ctx, sh.k, z_polys.get(), NS, n);
+        for (uint32_t set = 0; set < NS; ++set) dev_coeff_to_extended(ctx, sh.k, z_polys.get() + (size_t)set * n, z_cosets.get() + (size_t)set * en);
+        lap(tm ? &tm->ntt : nullptr);
+        for (const G1Affine& cm : cms) tr.write_point(cm);
     }
     // step 6: lookup grand products (D.6)
     DevBuf<Fr> lk_z_poly((size_t)L * n, s);
@@ -385,13 +399,13 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
             CUDA_CHECK(cudaMemcpyAsync(z + (n - bf), blind.data(), bf * sizeof(Fr), cudaMemcpyHostToDevice, s));
             CUDA_CHECK(cudaStreamSynchronize(s));
             rng.skip(1);
-            lap(tm ? &tm->products : nullptr);
-            const G1Affine cm = commit_lagrange(ctx, z, n);
-            lap(tm ? &tm->msm : nullptr);
-            dev_lagrange_to_coeff(ctx, sh.k, z);
-            lap(tm ? &tm->ntt : nullptr);
-            tr.write_point(cm);
         }
+        lap(tm ? &tm->products : nullptr);
+        const std::vector<G1Affine> cms = commit_batch(ctx, 1, lk_z_poly.get(), n, L, n);
+        lap(tm ? &tm->msm : nullptr);
+        if (L) dev_lagrange_to_coeff(ctx, sh.k, lk_z_poly.get(), L, n);
+        lap(tm ? &tm->ntt : nullptr);
+        for (const G1Affine& cm : cms) tr.write_point(cm);
     }
     // step 7: vanishing::commit (D.7): n sequential Fr::random draws = n consecutive ChaCha blocks, generated in place
     DevBuf<Fr> random_poly(n, s);
@@ -405,10 +419,8 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
     // step 8/9: advice polys + cosets, h(X) (D.8)
     DevBuf<Fr> advice_polys((size_t)NA * n, s), advice_cosets((size_t)NA * en, s);
     CUDA_CHECK(cudaMemcpyAsync(advice_polys.get(), advice.get(), (size_t)NA * n * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
-    for (uint32_t c = 0; c < NA; ++c) {
-        dev_lagrange_to_coeff(ctx, sh.k, advice_polys.get() + (size_t)c * n);
-        dev_coeff_to_extended(ctx, sh.k, advice_polys.get() + (size_t)c * n, advice_cosets.get() + (size_t)c * en);
-    }
+    dev_lagrange_to_coeff(ctx, sh.k, advice_polys.get(), NA, n);
+    for (uint32_t c = 0; c < NA; ++c) dev_coeff_to_extended(ctx, sh.k, advice_polys.get() + (size_t)c * n, advice_cosets.get() + (size_t)c * en);
     lap(tm ? &tm->ntt : nullptr);
     DevBuf<Fr> h(en, s);
     {
@@ -449,7 +461,7 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
     h.release();
     lap(tm ? &tm->ntt : nullptr);
     rng.skip(3);
-    for (uint32_t j = 0; j < 3; ++j) tr.write_point(commit_coeff(ctx, h_coeff.get() + (size_t)j * n, n));
+    for (const G1Affine& cm : commit_batch(ctx, 0, h_coeff.get(), n, 3, n)) tr.write_point(cm);
     lap(tm ? &tm->msm : nullptr);
     const Fr x = tr.squeeze_challenge();
     const Fr xn = f_pow_u64(x, n);

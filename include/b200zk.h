@@ -110,6 +110,9 @@ B200ZK_API int b200zk_srs_setup_trapdoor(b200zk_ctx* ctx, uint32_t k, const b200
 B200ZK_API int b200zk_srs_download(b200zk_ctx* ctx, b200zk_g1_affine* g, b200zk_g1_affine* g_lagrange);
 B200ZK_API int b200zk_msm(b200zk_ctx* ctx, int basis, const b200zk_fr* scalars, size_t n, b200zk_g1_affine* out);
 B200ZK_API int b200zk_msm_dev(b200zk_ctx* ctx, int basis, const b200zk_fr* scalars_dev, size_t n, b200zk_g1_affine* out);
+/* `ncols` commitments over the same basis: cols_dev[i] points at n device-resident scalars; out gets ncols affine points.
+ * Buckets are accumulated per column and reduced once for the whole batch (the reduction tail is latency bound). */
+B200ZK_API int b200zk_msm_batch_dev(b200zk_ctx* ctx, int basis, const b200zk_fr* const* cols_dev, size_t ncols, size_t n, b200zk_g1_affine* out);
 /* best_multiexp(coeffs, bases) with caller-supplied bases (host buffers) */
 B200ZK_API int b200zk_msm_bases(b200zk_ctx* ctx, const b200zk_g1_affine* bases, const b200zk_fr* scalars, size_t n, b200zk_g1_affine* out);
 /* device bases + device scalars (bench / multi-GPU shards): point range [0, n) of bases_dev */

@@ -108,3 +108,24 @@ def test_msm_linearity_full_size(ctx):
     # Lagrange basis ties to the monomial basis: commit_lagrange(evals) == commit(coeffs)
     coeffs = ctx.lagrange_to_coeff(k, a)
     assert np.array_equal(ctx.msm(a, 1), ctx.msm(coeffs, 0))
+
+
+def test_msm_batch_matches_single(ctx):
+    k = 13
+    n = 1 << k
+    ctx.srs_setup(k)
+    rng = np.random.default_rng(8)
+    cols = [O.random_fr(rng, n), O.fr_array([int(v) for v in rng.integers(0, 1 << 12, size=n)]), np.zeros((n, 4), dtype=np.uint64), O.random_fr(rng, n)]
+    ptrs = []
+    for c in cols:
+        p = ctx.dev_alloc(32 * n)
+        ctx.h2d(p, c)
+        ptrs.append(p)
+    for basis in (0, 1):
+        got = ctx.msm_batch_dev(ptrs, n, basis)
+        for i, c in enumerate(cols):
+            assert np.array_equal(got[i], ctx.msm(c, basis)), (basis, i)
+    g, gl = ctx.srs_download()
+    assert np.array_equal(ctx.msm_batch_dev(ptrs, n, 1)[0], O.msm(cols[0], gl))
+    for p in ptrs:
+        ctx.dev_free(p)

@@ -1,12 +1,19 @@
 import sys, os
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests"))
-import numpy as np, b200zk, oracle_lib as O
+sys.path.insert(0, R)
+import numpy as np, b200zk
 k = int(sys.argv[1]) if len(sys.argv) > 1 else 18
+kind = sys.argv[2] if len(sys.argv) > 2 else "uniform"
 ctx = b200zk.Context(0)
-params = O.Params.setup(k); s, g, gl = params.get(); ctx.srs_load(k, g, gl)
+ctx.srs_setup(k)
 rng = np.random.default_rng(0)
-a = O.random_fr(rng, 1 << k)
+n = 1 << k
+a = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
+a[:, 3] &= np.uint64((1 << 60) - 1)
+if kind == "small":
+    a[:, 1:] = 0
+    a[:, 0] &= np.uint64((1 << 19) - 1)
+    a = ctx.field_vec_op(0, 6, a)
 for _ in range(2):
     r = ctx.msm(a, 0)
 print("ok", r[:2])

@@ -21,7 +21,8 @@ struct b200zk_ctx {
     if (!(ctx)) return B200ZK_EINVAL;       \
     std::lock_guard<std::mutex> _lk((ctx)->c.mu); \
     try {                                   \
-        cudaSetDevice((ctx)->c.device);
+        cudaSetDevice((ctx)->c.device);             \
+        (ctx)->c.arena.maybe_grow();
 #define API_END(ctx)                        \
     }                                       \
     catch (const CudaError& e) {            \
@@ -61,6 +62,8 @@ int b200zk_create(int device, b200zk_ctx** out) {
         uint64_t thr = ~0ull;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
+    ctx->c.arena.stream = ctx->c.stream;
+    arena_register(ctx->c.stream, &ctx->c.arena);
     *out = ctx;
     return B200ZK_OK;
 }
@@ -69,8 +72,15 @@ int b200zk_destroy(b200zk_ctx* ctx) {
     cudaSetDevice(ctx->c.device);
     cudaStreamSynchronize(ctx->c.stream);
     cudaStream_t s = ctx->c.stream;
-    delete ctx;
+    ctx->c.srs.reset();
+    ctx->c.tables.clear();
+    ctx->c.custom_table.reset();
+    ctx->c.domains.clear();
+    ctx->c.scratch.release();
     cudaStreamSynchronize(s);
+    arena_register(s, nullptr);
+    ctx->c.arena.destroy();
+    delete ctx;
     cudaStreamDestroy(s);
     return B200ZK_OK;
 }
@@ -136,13 +146,13 @@ int b200zk_set_msm_tables(b200zk_ctx* ctx, int on) {
 int b200zk_dev_alloc(b200zk_ctx* ctx, size_t bytes, void** out) {
     API_BEGIN(ctx)
     if (!out) throw std::invalid_argument("null out");
-    CUDA_CHECK(cudaMallocAsync(out, bytes, ctx->c.stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->c.stream));
+    CUDA_CHECK(cudaMalloc(out, bytes));
     API_END(ctx)
 }
 int b200zk_dev_free(b200zk_ctx* ctx, void* p) {
     API_BEGIN(ctx)
-    CUDA_CHECK(cudaFreeAsync(p, ctx->c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->c.stream));
+    CUDA_CHECK(cudaFree(p));
     API_END(ctx)
 }
 int b200zk_h2d(b200zk_ctx* ctx, void* dst, const void* src, size_t bytes) {
@@ -252,7 +262,7 @@ static NttPlan plan_for_omega(Context& c, uint32_t log_n, const Fr& omega) {
         auto t = std::make_unique<TwiddleTable>();
         t->log_n = log_n;
         t->omega = omega;
-        t->t.alloc(log_n == 0 ? 1 : (size_t)1 << (log_n - 1), c.stream);
+        t->t.alloc_persistent(log_n == 0 ? 1 : (size_t)1 << (log_n - 1), c.stream);
         build_twiddle_table(t->t.get(), omega, log_n, c.stream);
         c.custom_table = std::move(t);
     }
@@ -370,8 +380,8 @@ int b200zk_srs_load(b200zk_ctx* ctx, uint32_t k, const b200zk_g1_affine* g, cons
     auto srs = std::make_unique<Srs>();
     srs->k = k;
     srs->n = (size_t)1 << k;
-    srs->g.alloc(srs->n, c.stream);
-    srs->g_lagrange.alloc(srs->n, c.stream);
+    srs->g.alloc_persistent(srs->n, c.stream);
+    srs->g_lagrange.alloc_persistent(srs->n, c.stream);
     CUDA_CHECK(cudaMemcpyAsync(srs->g.get(), g, 64 * srs->n, cudaMemcpyHostToDevice, c.stream));
     CUDA_CHECK(cudaMemcpyAsync(srs->g_lagrange.get(), g_lagrange, 64 * srs->n, cudaMemcpyHostToDevice, c.stream));
     CUDA_CHECK(cudaStreamSynchronize(c.stream));

@@ -49,33 +49,131 @@ DEV void f_store(Field<C>* p, const Field<C>& v) {
     q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
 }
 
-// ---- device buffer with stream-ordered allocation ----------------------------------------------------
+// ---- transient device memory: a per-stream stack arena -------------------------------------------------------------------
+// create_proof allocates and frees multi-GB transient columns in a fixed pattern. cudaMallocAsync's pool re-maps physical
+// memory when that pattern fragments it (observed: random 0.5–1.2 s stalls inside a 0.2 s proof), so transient buffers
+// come from one region with stack discipline instead: allocation = pointer bump, free = mark + pop while the top is
+// free. Reuse is safe because every consumer runs on the owning stream. The first calls overflow into cudaMallocAsync
+// while the high-water mark is learnt; the arena is (re)sized when it is empty.
+struct Arena {
+    uint8_t* base = nullptr;
+    size_t cap = 0, top = 0, high_water = 0;
+    struct Block {
+        size_t off, size;
+        void* overflow;  // non-null: served by cudaMallocAsync because the arena was too small
+        bool freed;
+    };
+    std::vector<Block> blocks;
+    cudaStream_t stream = nullptr;
+
+    void* alloc(size_t bytes) {
+        const size_t sz = (bytes + 511) & ~(size_t)511;
+        Block b{top, sz, nullptr, false};
+        void* p;
+        if (top + sz <= cap) {
+            p = base + top;
+        } else {
+            cudaError_t e = cudaMallocAsync(&b.overflow, sz, stream);
+            if (e != cudaSuccess) throw CudaError(std::string("arena overflow allocation failed: ") + cudaGetErrorString(e));
+            p = b.overflow;
+        }
+        top += sz;
+        if (top > high_water) high_water = top;
+        blocks.push_back(b);
+        return p;
+    }
+    void free(void* p) {
+        for (size_t i = blocks.size(); i-- > 0;) {
+            Block& b = blocks[i];
+            if (b.freed) continue;
+            void* q = b.overflow ? b.overflow : (void*)(base + b.off);
+            if (q != p) continue;
+            b.freed = true;
+            if (b.overflow) cudaFreeAsync(b.overflow, stream);
+            break;
+        }
+        while (!blocks.empty() && blocks.back().freed) {
+            top = blocks.back().off;
+            blocks.pop_back();
+        }
+    }
+    // call between API calls: when empty and too small, grow to the learnt high-water mark (+ headroom)
+    void maybe_grow() {
+        if (!blocks.empty() || high_water <= cap) return;
+        cudaStreamSynchronize(stream);
+        if (base) cudaFree(base);
+        base = nullptr;
+        cap = 0;
+        const size_t want = high_water + high_water / 16 + ((size_t)64 << 20);
+        void* p = nullptr;
+        if (cudaMalloc(&p, want) == cudaSuccess) {
+            base = (uint8_t*)p;
+            cap = want;
+        } else {
+            cudaGetLastError();  // stay on the pool path
+            high_water = 0;
+        }
+    }
+    void destroy() {
+        if (base) cudaFree(base);
+        base = nullptr;
+        cap = top = 0;
+        blocks.clear();
+    }
+};
+Arena* arena_for(cudaStream_t s);
+void arena_register(cudaStream_t s, Arena* a);
+
+// ---- device buffer ------------------------------------------------------------------------------------------------------
 template <class T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
     cudaStream_t stream = nullptr;
+    bool persistent = false;
     DevBuf() {}
     DevBuf(size_t n_, cudaStream_t s) { alloc(n_, s); }
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), stream(o.stream) { o.p = nullptr; o.n = 0; }
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), stream(o.stream), persistent(o.persistent) { o.p = nullptr; o.n = 0; }
     DevBuf& operator=(DevBuf&& o) noexcept {
         if (this != &o) {
             release();
-            p = o.p; n = o.n; stream = o.stream;
+            p = o.p; n = o.n; stream = o.stream; persistent = o.persistent;
             o.p = nullptr; o.n = 0;
         }
         return *this;
     }
+    // transient: from the stream's arena (stack discipline)
     void alloc(size_t n_, cudaStream_t s) {
         release();
         n = n_;
         stream = s;
-        if (n) CUDA_CHECK(cudaMallocAsync((void**)&p, n * sizeof(T), s));
+        persistent = false;
+        if (!n) return;
+        Arena* a = arena_for(s);
+        if (a) p = (T*)a->alloc(n * sizeof(T));
+        else CUDA_CHECK(cudaMallocAsync((void**)&p, n * sizeof(T), s));
+    }
+    // long-lived (SRS, keys, tables): plain cudaMalloc
+    void alloc_persistent(size_t n_, cudaStream_t s) {
+        release();
+        n = n_;
+        stream = s;
+        persistent = true;
+        if (n) CUDA_CHECK(cudaMalloc((void**)&p, n * sizeof(T)));
     }
     void release() {
-        if (p) cudaFreeAsync(p, stream);
+        if (p) {
+            if (persistent) {
+                cudaStreamSynchronize(stream);
+                cudaFree(p);
+            } else {
+                Arena* a = arena_for(stream);
+                if (a) a->free(p);
+                else cudaFreeAsync(p, stream);
+            }
+        }
         p = nullptr;
         n = 0;
     }

@@ -84,6 +84,7 @@ struct Context {
     std::unique_ptr<TwiddleTable> custom_table;                // last non-standard omega
     std::map<uint32_t, std::unique_ptr<Domain>> domains;
     DevBuf<Fr> scratch;
+    Arena arena;  // transient buffers of this context's stream
     std::unique_ptr<Srs> srs;
     // multi-GPU: one process per GPU; MSMs are sharded by point range and partial window sums are exchanged through
     // this callback (the host binds it to an NCCL all-gather) — SURVEY.md §8e
@@ -99,7 +100,7 @@ struct Context {
         auto t = std::make_unique<TwiddleTable>();
         t->log_n = log_n;
         t->omega = FrConsts::root(log_n);
-        t->t.alloc(log_n == 0 ? 1 : (size_t)1 << (log_n - 1), stream);
+        t->t.alloc_persistent(log_n == 0 ? 1 : (size_t)1 << (log_n - 1), stream);
         build_twiddle_table(t->t.get(), t->omega, log_n, stream);
         auto& ref = tables[log_n];
         ref = std::move(t);
@@ -108,7 +109,7 @@ struct Context {
     Fr* get_scratch(size_t n) {
         if (scratch.size() < n) {
             CUDA_CHECK(cudaStreamSynchronize(stream));
-            scratch.alloc(n, stream);
+            scratch.alloc_persistent(n, stream);
         }
         return scratch.get();
     }
@@ -137,7 +138,7 @@ struct Context {
                     d->ifft_divisor, d->ifft_divisor, d->ifft_divisor,
                     d->extended_ifft_divisor, f_mul(d->extended_ifft_divisor, zeta2), f_mul(d->extended_ifft_divisor, zeta),
                     d->t_inv[0], d->t_inv[1], d->t_inv[2], d->t_inv[3]};
-        d->consts.alloc(13, stream);
+        d->consts.alloc_persistent(13, stream);
         CUDA_CHECK(cudaMemcpyAsync(d->consts.get(), h, sizeof(h), cudaMemcpyHostToDevice, stream));
         CUDA_CHECK(cudaStreamSynchronize(stream));
         auto& ref = domains[k];

@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(128) msm_table_step_kernel(const G1Affine* pre
 }
 void msm_build_table(Context& ctx, const G1Affine* bases, size_t n, uint32_t c, DevBuf<G1Affine>& table) {
     const uint32_t W = (255 + c - 1) / c;
-    table.alloc((size_t)W * n, ctx.stream);
+    table.alloc_persistent((size_t)W * n, ctx.stream);
     CUDA_CHECK(cudaMemcpyAsync(table.get(), bases, n * sizeof(G1Affine), cudaMemcpyDeviceToDevice, ctx.stream));
     for (uint32_t w = 1; w < W; ++w) {
         msm_table_step_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx.stream>>>(table.get() + (size_t)(w - 1) * n, table.get() + (size_t)w * n, n, c);

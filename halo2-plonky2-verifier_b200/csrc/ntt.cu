@@ -24,6 +24,19 @@ unsigned long long g_launch_count = 0;
 bool g_prof_enabled = false;
 std::vector<ProfSpan> g_prof_spans;
 
+static std::mutex g_arena_mu;
+static std::map<cudaStream_t, Arena*> g_arenas;
+Arena* arena_for(cudaStream_t s) {
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    auto it = g_arenas.find(s);
+    return it == g_arenas.end() ? nullptr : it->second;
+}
+void arena_register(cudaStream_t s, Arena* a) {
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    if (a) g_arenas[s] = a;
+    else g_arenas.erase(s);
+}
+
 struct PassParams {
     const Fr* in;
     Fr* out;

@@ -103,10 +103,10 @@ std::unique_ptr<ProvingKeyDev> keygen(Context& ctx, const Shape& sh, const Fr* f
     pk->shape = sh;
     const uint32_t NF = sh.num_fixed(), P = sh.num_perm();
     // fixed columns
-    pk->fixed_values.alloc((size_t)NF * n, s);
+    pk->fixed_values.alloc_persistent((size_t)NF * n, s);
     CUDA_CHECK(cudaMemcpyAsync(pk->fixed_values.get(), fixed_host, (size_t)NF * n * sizeof(Fr), cudaMemcpyHostToDevice, s));
     // sigma columns from the copy-constraint cycles
-    pk->sigma_values.alloc((size_t)P * n, s);
+    pk->sigma_values.alloc_persistent((size_t)P * n, s);
     {
         Assembly as(n, P);
         for (size_t i = 0; i < ncopies; ++i) as.copy(copies[4 * i], copies[4 * i + 1], copies[4 * i + 2], copies[4 * i + 3]);
@@ -128,19 +128,19 @@ std::unique_ptr<ProvingKeyDev> keygen(Context& ctx, const Shape& sh, const Fr* f
     pk->perm_commitments = commit_batch(ctx, 1, pk->sigma_values.get(), n, P, n);
     pk->transcript_repr = default_transcript_repr(*pk);
     // keygen_pk: coefficient forms and extended cosets
-    pk->fixed_polys.alloc((size_t)NF * n, s);
-    pk->sigma_polys.alloc((size_t)P * n, s);
+    pk->fixed_polys.alloc_persistent((size_t)NF * n, s);
+    pk->sigma_polys.alloc_persistent((size_t)P * n, s);
     CUDA_CHECK(cudaMemcpyAsync(pk->fixed_polys.get(), pk->fixed_values.get(), (size_t)NF * n * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
     CUDA_CHECK(cudaMemcpyAsync(pk->sigma_polys.get(), pk->sigma_values.get(), (size_t)P * n * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
     for (uint32_t i = 0; i < NF; ++i) dev_lagrange_to_coeff(ctx, sh.k, pk->fixed_polys.get() + (size_t)i * n);
     for (uint32_t j = 0; j < P; ++j) dev_lagrange_to_coeff(ctx, sh.k, pk->sigma_polys.get() + (size_t)j * n);
-    pk->fixed_cosets.alloc((size_t)NF * en, s);
-    pk->sigma_cosets.alloc((size_t)P * en, s);
+    pk->fixed_cosets.alloc_persistent((size_t)NF * en, s);
+    pk->sigma_cosets.alloc_persistent((size_t)P * en, s);
     for (uint32_t i = 0; i < NF; ++i) dev_coeff_to_extended(ctx, sh.k, pk->fixed_polys.get() + (size_t)i * n, pk->fixed_cosets.get() + (size_t)i * en);
     for (uint32_t j = 0; j < P; ++j) dev_coeff_to_extended(ctx, sh.k, pk->sigma_polys.get() + (size_t)j * n, pk->sigma_cosets.get() + (size_t)j * en);
     // l0, l_last, l_active_row = 1 - l_last - l_blind on the extended domain
     {
-        pk->l_polys.alloc(3 * en, s);
+        pk->l_polys.alloc_persistent(3 * en, s);
         DevBuf<Fr> tmp(3 * n, s);
         CUDA_CHECK(cudaMemsetAsync(tmp.get(), 0, 3 * n * sizeof(Fr), s));
         const Fr one = f_one<FrCfg>();

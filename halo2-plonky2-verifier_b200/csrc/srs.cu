@@ -81,8 +81,8 @@ void srs_setup(Context& ctx, uint32_t k, const Fr& s_trapdoor) {
     auto srs = std::make_unique<Srs>();
     srs->k = k;
     srs->n = n;
-    srs->g.alloc(n, st);
-    srs->g_lagrange.alloc(n, st);
+    srs->g.alloc_persistent(n, st);
+    srs->g_lagrange.alloc_persistent(n, st);
     // monomial basis: scalars s^i
     DevBuf<Fr> sc(n, st);
     build_twiddle_table(sc.get(), s_trapdoor, k + 1, st);  // T[i] = s^i, i < 2^k

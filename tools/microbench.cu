@@ -31,6 +31,33 @@ __global__ void imad_wide_kernel(unsigned long long* out, uint32_t a, int iters)
     for (int i = 0; i < ILP; ++i) s += x[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
+// carry-chained wide multiply-adds exactly as field.cuh issues them (mad.lo.cc / madc.hi.cc pairs -> IMAD.WIDE.U32.X)
+template <int CH>
+__global__ void imad_wide_x_kernel(uint32_t* out, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t x, int iters) {
+    uint32_t acc[CH][8];
+    for (int c = 0; c < CH; ++c)
+        for (int i = 0; i < 8; ++i) acc[c][i] = threadIdx.x + c * 8 + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            asm volatile(
+                "mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
+                "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+                "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
+                "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+                "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+                "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+                "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+                "madc.hi.u32 %7, %11, %12, %7;"
+                : "+r"(acc[c][0]), "+r"(acc[c][1]), "+r"(acc[c][2]), "+r"(acc[c][3]), "+r"(acc[c][4]), "+r"(acc[c][5]), "+r"(acc[c][6]), "+r"(acc[c][7])
+                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(x));
+        }
+    }
+    uint32_t s = 0;
+    for (int c = 0; c < CH; ++c)
+        for (int i = 0; i < 8; ++i) s += acc[c][i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
 template <int ILP>
 __global__ void fmul_kernel(Fr* out, const Fr* in, int iters) {
     Fr x[ILP];
@@ -69,6 +96,11 @@ int main() {
         float ms = time_ms([&] { imad_wide_kernel<8><<<blocks, threads>>>((unsigned long long*)buf, 3, iters); });
         double ops = (double)blocks * threads * iters * 8;
         printf(", \"imad_wide_Tops\": %.3f", ops / ms / 1e9);
+    }
+    {
+        float ms = time_ms([&] { imad_wide_x_kernel<4><<<blocks, threads>>>((uint32_t*)buf, 3, 5, 7, 11, 13, iters / 4); });
+        double ops = (double)blocks * threads * (iters / 4) * 4 * 4;  // wide multiply-adds (lo+hi pair = 1)
+        printf(", \"imad_wide_carry_chain_Tops\": %.3f", ops / ms / 1e9);
     }
     {
         float ms = time_ms([&] { fmul_kernel<2><<<blocks, threads>>>((Fr*)buf, din, 512); });

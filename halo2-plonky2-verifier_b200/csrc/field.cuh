@@ -325,6 +325,88 @@ HD Field<C> f_mul_chains(const Field<C>& a, const Field<C>& b) {
     uint32_t c = add8(t.l, E + 1, O);
     return f_reduce_once<C>(t, c);
 }
+// ---- unsaturated multiplier: 29-bit limbs, carry-free column accumulation ------------------------------------------------
+// On sm_100 the carry-chained IMAD.WIDE.U32.X issues at half the rate of plain IMAD.WIDE.U32 (tools/microbench:
+// 9.1 vs 17.2 T/s) and 104 of the 139 multiply-adds of f_mul_chains are .X forms. Here both operands are re-sliced into
+// nine 29-bit limbs, every partial product a_j·b_i (< 2^58) is added into a 64-bit column with a plain
+// `mad.wide.u32` (18 products per column at most: < 2^63, no carries), and Montgomery reduction retires one 29-bit limb
+// per row — eight rows of 29 bits and a last row of 24 bits, 8·29 + 24 = 256, so the result is still a·b·2^-256 mod P in
+// the halo2curves representation. 162 IMAD.WIDE + 12 IMAD instead of 243 issue-slot equivalents on the multiplier pipe —
+// but the limb re-slicing and carry propagation cost ≈210 ALU-pipe instructions per product, and MEASURED on B200 this
+// variant reaches 43–45 G products/s against 67 G/s for the carry chains, so it is kept only as a tested alternative
+// (-DB200ZK_MUL_U29) until values can stay in 29-bit form across whole kernels.
+template <class C>
+HD void f_unpack29(const uint32_t* w, uint32_t* L) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const int off = 29 * k, wi = off >> 5, sh = off & 31;
+        uint32_t v = w[wi] >> sh;
+        if (sh > 3 && wi + 1 < 8) v |= w[wi + 1] << (32 - sh);
+        L[k] = v & 0x1fffffffu;
+    }
+}
+template <class C>
+HD Field<C> f_mul_u29(const Field<C>& a, const Field<C>& b) {
+    constexpr uint32_t M29 = 0x1fffffffu;
+    uint32_t A[9], B[9], P[9];
+    {
+        uint32_t pw[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pw[i] = C::P(i);
+        f_unpack29<C>(pw, P);
+    }
+    f_unpack29<C>(a.l, A);
+    f_unpack29<C>(b.l, B);
+    const uint32_t pinv = C::INV;  // -P^-1 mod 2^32; its low 29 (24) bits are -P^-1 mod 2^29 (2^24)
+    uint64_t T[10];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) T[j] = 0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) T[j] += (uint64_t)A[j] * B[i];
+        const uint32_t m = ((uint32_t)T[0] * pinv) & (i < 8 ? M29 : 0x00ffffffu);
+#pragma unroll
+        for (int j = 0; j < 9; ++j) T[j] += (uint64_t)m * P[j];
+        if (i < 8) {  // T[0] is a multiple of 2^29: retire the limb
+            T[1] += T[0] >> 29;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) T[j] = T[j + 1];
+            T[9] = 0;
+        }
+    }
+    // T[0] is a multiple of 2^24 and the value is sum T[j]·2^(29j) / 2^24 < 2P: normalise to 29-bit limbs, re-slice to words
+    uint32_t L[10];
+    uint64_t c = 0;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+        const uint64_t t = T[j] + c;
+        L[j] = (uint32_t)t & M29;
+        c = t >> 29;
+    }
+    L[9] = (uint32_t)c;
+    Field<C> r;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.l[k] = 0;
+    uint32_t top = 0;
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+        const int pos = 29 * j - 24;  // bit position of limb j in the result
+        if (pos < 0) {
+            r.l[0] |= L[j] >> (-pos);
+        } else {
+            const int wi = pos >> 5, sh = pos & 31;
+            if (wi < 8) r.l[wi] |= L[j] << sh;
+            else top |= L[j] << sh;
+            if (sh > 3) {
+                if (wi + 1 < 8) r.l[wi + 1] |= L[j] >> (32 - sh);
+                else top |= L[j] >> (32 - sh);
+            }
+        }
+    }
+    return f_reduce_once<C>(r, top != 0 ? 1u : 0u);
+}
+
 // host fast path: 4×64-bit limbs, same value as f_mul_chains (checked by b200zk_host_selftest)
 template <class C>
 inline Field<C> f_mul_host64(const Field<C>& a, const Field<C>& b) {
@@ -370,7 +452,11 @@ inline Field<C> f_mul_host64(const Field<C>& a, const Field<C>& b) {
 template <class C>
 HD Field<C> f_mul(const Field<C>& a, const Field<C>& b) {
 #if defined(__CUDA_ARCH__)
+#if defined(B200ZK_MUL_U29)  // measured alternative: 43–45 G mul/s vs 67 G mul/s for the carry chains (profiles/README.md)
+    return f_mul_u29<C>(a, b);
+#else
     return f_mul_chains<C>(a, b);
+#endif
 #else
     return f_mul_host64<C>(a, b);
 #endif

@@ -2,6 +2,7 @@
 #include "../../include/b200zk.h"
 
 #include "prover.cuh"
+#include "collectives.cuh"
 
 using namespace b200zk;
 
@@ -127,20 +128,14 @@ int b200zk_set_allgather(b200zk_ctx* ctx, int rank, int world, b200zk_allgather_
     ctx->c.world = world;
     ctx->c.allgather = fn;
     ctx->c.allgather_user = user;
+    ctx->c.nccl.reset();
+    srs_build_tables(ctx->c);  // window tables follow this rank's MSM shard
     API_END(ctx)
 }
 int b200zk_set_msm_tables(b200zk_ctx* ctx, int on) {
     API_BEGIN(ctx)
     ctx->c.msm_tables_enabled = on != 0;
-    if (ctx->c.srs) {
-        if (on) {
-            srs_build_tables(ctx->c);
-        } else {
-            CUDA_CHECK(cudaStreamSynchronize(ctx->c.stream));
-            ctx->c.srs->g_tab.release();
-            ctx->c.srs->gl_tab.release();
-        }
-    }
+    srs_build_tables(ctx->c);
     API_END(ctx)
 }
 int b200zk_dev_alloc(b200zk_ctx* ctx, size_t bytes, void** out) {

@@ -1,0 +1,94 @@
+// NCCL over NVLink/NVSwitch for the bulk exchanges of the sharded prover: broadcast of per-column
+// results (coefficient forms, extended cosets) from the rank that computed them and the all-gather of h(X) row ranges.
+// One process per GPU (torchrun); the library opens the NCCL that the host process already loaded (torch's bundled
+// libnccl.so.2) with dlopen, so there is no link-time dependency and no second copy. The 128-byte ncclUniqueId is
+// bootstrapped through the host all-gather callback the caller registered with b200zk_set_allgather.
+#pragma once
+#include <dlfcn.h>
+
+#include "context.cuh"
+
+namespace b200zk {
+
+struct Nccl {
+    typedef struct { char internal[128]; } UniqueId;
+    void* lib = nullptr;
+    void* comm = nullptr;
+    int (*GetUniqueId)(UniqueId*) = nullptr;
+    int (*CommInitRank)(void**, int, UniqueId, int) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    int rank = 0, world = 1;
+
+    void check(int rc, const char* what) {
+        if (rc != 0) throw std::runtime_error(std::string("NCCL ") + what + " failed: " + (GetErrorString ? GetErrorString(rc) : "?"));
+    }
+    template <class F>
+    void sym(F& f, const char* name) {
+        f = (F)dlsym(lib, name);
+        if (!f) throw std::runtime_error(std::string("NCCL symbol missing: ") + name);
+    }
+    void init(Context& ctx) {
+        rank = ctx.rank;
+        world = ctx.world;
+        lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);  // the copy the host process (torch) already loaded
+        if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW);
+        if (!lib) throw std::runtime_error("libnccl.so.2 not found (multi-GPU needs NCCL in the host process)");
+        sym(GetUniqueId, "ncclGetUniqueId");
+        sym(CommInitRank, "ncclCommInitRank");
+        sym(Broadcast, "ncclBroadcast");
+        sym(AllGather, "ncclAllGather");
+        sym(GroupStart, "ncclGroupStart");
+        sym(GroupEnd, "ncclGroupEnd");
+        sym(CommDestroy, "ncclCommDestroy");
+        sym(GetErrorString, "ncclGetErrorString");
+        UniqueId id;
+        memset(&id, 0, sizeof(id));
+        if (rank == 0) check(GetUniqueId(&id), "GetUniqueId");
+        std::vector<UniqueId> all(world);
+        if (ctx.allgather(ctx.allgather_user, &id, sizeof(id), all.data()) != 0) throw std::runtime_error("NCCL bootstrap all-gather failed");
+        check(CommInitRank(&comm, world, all[0], rank), "CommInitRank");
+    }
+    ~Nccl() {
+        if (comm && CommDestroy) CommDestroy(comm);
+    }
+};
+
+// ownership of column-wise work in the sharded prover: item i belongs to rank i mod world
+struct Sharder {
+    Context& ctx;
+    explicit Sharder(Context& c) : ctx(c) {}
+    bool on() const { return ctx.world > 1 && ctx.allgather; }
+    int owner(size_t i) const { return on() ? (int)(i % ctx.world) : 0; }
+    bool mine(size_t i) const { return !on() || owner(i) == ctx.rank; }
+    Nccl& nccl() {
+        if (!ctx.nccl) {
+            auto n = std::make_shared<Nccl>();
+            n->init(ctx);
+            ctx.nccl = n;
+        }
+        return *ctx.nccl;
+    }
+    void group_start() {
+        if (on()) nccl().check(nccl().GroupStart(), "GroupStart");
+    }
+    void group_end() {
+        if (on()) nccl().check(nccl().GroupEnd(), "GroupEnd");
+    }
+    // every rank ends up with the owner's copy of buf[0..count)
+    void broadcast(Fr* buf, size_t count, int root) {
+        if (!on()) return;
+        nccl().check(nccl().Broadcast(buf, buf, count * sizeof(Fr), /*ncclUint8*/ 1, root, nccl().comm, ctx.stream), "Broadcast");
+    }
+    // buf holds world equal chunks; this rank filled chunk `rank`
+    void all_gather_inplace(Fr* buf, size_t chunk) {
+        if (!on()) return;
+        nccl().check(nccl().AllGather(buf + (size_t)ctx.rank * chunk, buf, chunk * sizeof(Fr), 1, nccl().comm, ctx.stream), "AllGather");
+    }
+};
+
+}  // namespace b200zk

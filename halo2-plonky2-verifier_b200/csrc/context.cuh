@@ -66,6 +66,7 @@ struct Domain {
 struct Srs {
     uint32_t k = 0;
     size_t n = 0;
+    size_t tab_lo = 0, tab_n = 0;  // point range covered by the window tables (this rank's MSM shard)
     DevBuf<G1Affine> g, g_lagrange;
     // precomputed window tables T[w][i] = 2^(tab_c·w)·P_i (msm.cu, merged-bucket mode); empty when disabled
     DevBuf<G1Affine> g_tab, gl_tab;
@@ -92,6 +93,7 @@ struct Context {
     AllGatherFn allgather = nullptr;
     void* allgather_user = nullptr;
     bool msm_tables_enabled = true;
+    std::shared_ptr<struct Nccl> nccl;  // collectives.cuh, created on first use when world > 1
 
     // table of the standard 2^t-th root with t >= log_n
     const TwiddleTable& std_table(uint32_t log_n) {

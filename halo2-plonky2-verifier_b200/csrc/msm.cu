@@ -464,7 +464,9 @@ static void check_cfg(const MsmConfig& cfg, size_t n) {
     if (n >= ((size_t)1 << 31) || (cfg.merged && cfg.table_n * cfg.W >= ((size_t)1 << 31))) throw std::invalid_argument("msm: index space must be < 2^31");
 }
 // `ncols` MSMs over the same bases: per-column bucket accumulation, ONE reduction for all columns, one exchange across ranks.
-static void msm_batch_core(Context& ctx, const G1Affine* bases, const Fr* const* cols, size_t ncols, size_t n, const MsmConfig& cfg, G1Affine* out) {
+// `bases_origin`: index of the point that bases[0] corresponds to (non-zero when `bases` is a per-shard window table)
+static void msm_batch_core(Context& ctx, const G1Affine* bases, const Fr* const* cols, size_t ncols, size_t n, const MsmConfig& cfg, G1Affine* out,
+                           size_t bases_origin) {
     check_cfg(cfg, n);
     cudaStream_t s = ctx.stream;
     size_t lo, len;
@@ -476,7 +478,7 @@ static void msm_batch_core(Context& ctx, const G1Affine* bases, const Fr* const*
         const size_t nc = std::min(round, ncols - c0);
         DevBuf<G1X> bucket_sums((size_t)nc * nb, s);
         CUDA_CHECK(cudaMemsetAsync(bucket_sums.get(), 0, (size_t)nc * nb * sizeof(G1X), s));
-        for (size_t j = 0; j < nc; ++j) msm_bucket_sums(ctx, bases + lo, cols[c0 + j] + lo, len, cfg, bucket_sums.get() + j * nb);
+        for (size_t j = 0; j < nc; ++j) msm_bucket_sums(ctx, bases + (lo - bases_origin), cols[c0 + j] + lo, len, cfg, bucket_sums.get() + j * nb);
         std::vector<G1X> ws;
         msm_reduce_groups(ctx, bucket_sums.get(), (uint32_t)(nc * cfg.groups), cfg.B, ws);
         combine_across_ranks(ctx, ws);
@@ -488,7 +490,7 @@ static void msm_batch_core(Context& ctx, const G1Affine* bases, const Fr* const*
 // arbitrary bases (best_multiexp): windows kept separate, folded on the host
 G1Affine msm_run(Context& ctx, const G1Affine* bases, const Fr* scalars, size_t n) {
     G1Affine r;
-    msm_batch_core(ctx, bases, &scalars, 1, n, msm_config(n), &r);
+    msm_batch_core(ctx, bases, &scalars, 1, n, msm_config(n), &r, 0);
     return r;
 }
 
@@ -496,10 +498,14 @@ G1Affine msm_run(Context& ctx, const G1Affine* bases, const Fr* scalars, size_t 
 void msm_batch_srs(Context& ctx, int basis, const Fr* const* cols, size_t ncols, size_t n, G1Affine* out) {
     const Srs& srs = *ctx.srs;
     const DevBuf<G1Affine>& tab = basis == 0 ? srs.g_tab : srs.gl_tab;
-    if (tab.size() == 0 || n * 8 < srs.n)
-        msm_batch_core(ctx, basis == 0 ? srs.g.get() : srs.g_lagrange.get(), cols, ncols, n, msm_config(n), out);
+    size_t lo, len;
+    shard_range(ctx, n, lo, len);
+    // the table covers points [tab_lo, tab_lo + tab_n): usable when this call's shard is exactly that range start
+    const bool table_ok = tab.size() != 0 && n * 8 >= srs.n && lo == srs.tab_lo && len <= srs.tab_n;
+    if (!table_ok)
+        msm_batch_core(ctx, basis == 0 ? srs.g.get() : srs.g_lagrange.get(), cols, ncols, n, msm_config(n), out, 0);
     else
-        msm_batch_core(ctx, tab.get(), cols, ncols, n, msm_config_merged(srs.tab_c, srs.n), out);
+        msm_batch_core(ctx, tab.get(), cols, ncols, n, msm_config_merged(srs.tab_c, srs.tab_n), out, srs.tab_lo);
 }
 G1Affine msm_run_srs(Context& ctx, int basis, const Fr* scalars, size_t n) {
     G1Affine r;

@@ -7,6 +7,8 @@
 // the reference; everything else is a launch of the kernels in ntt.cu / msm.cu / poly.cu / quotient.cu.
 #include "prover.cuh"
 
+#include "collectives.cuh"
+
 #include <algorithm>
 #include <chrono>
 
@@ -283,6 +285,8 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
     const Domain& dom = ctx.domain(sh.k);
     const TwiddleTable& tw = ctx.std_table(sh.k + 2);
     host::Transcript tr;
+    Sharder shard(ctx);
+    if (shard.on()) shard.nccl();  // communicator up before the first timed exchange
     auto clock_now = [&]() {
         CUDA_CHECK(cudaStreamSynchronize(s));
         return std::chrono::steady_clock::now();
@@ -379,8 +383,22 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
         lap(tm ? &tm->products : nullptr);
         const std::vector<G1Affine> cms = commit_batch(ctx, 1, z_polys.get(), n, NS, n);
         lap(tm ? &tm->msm : nullptr);
-        dev_lagrange_to_coeff(ctx, sh.k, z_polys.get(), NS, n);
-        for (uint32_t set = 0; set < NS; ++set) dev_coeff_to_extended(ctx, sh.k, z_polys.get() + (size_t)set * n, z_cosets.get() + (size_t)set * en);
+        if (!shard.on()) {
+            dev_lagrange_to_coeff(ctx, sh.k, z_polys.get(), NS, n);
+            for (uint32_t set = 0; set < NS; ++set) dev_coeff_to_extended(ctx, sh.k, z_polys.get() + (size_t)set * n, z_cosets.get() + (size_t)set * en);
+        } else {
+            for (uint32_t set = 0; set < NS; ++set)
+                if (shard.mine(set)) {
+                    dev_lagrange_to_coeff(ctx, sh.k, z_polys.get() + (size_t)set * n);
+                    dev_coeff_to_extended(ctx, sh.k, z_polys.get() + (size_t)set * n, z_cosets.get() + (size_t)set * en);
+                }
+            shard.group_start();
+            for (uint32_t set = 0; set < NS; ++set) {
+                shard.broadcast(z_polys.get() + (size_t)set * n, n, shard.owner(set));
+                shard.broadcast(z_cosets.get() + (size_t)set * en, en, shard.owner(set));
+            }
+            shard.group_end();
+        }
         lap(tm ? &tm->ntt : nullptr);
         for (const G1Affine& cm : cms) tr.write_point(cm);
     }
@@ -419,8 +437,22 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
     // step 8/9: advice polys + cosets, h(X) (D.8)
     DevBuf<Fr> advice_polys((size_t)NA * n, s), advice_cosets((size_t)NA * en, s);
     CUDA_CHECK(cudaMemcpyAsync(advice_polys.get(), advice.get(), (size_t)NA * n * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
-    dev_lagrange_to_coeff(ctx, sh.k, advice_polys.get(), NA, n);
-    for (uint32_t c = 0; c < NA; ++c) dev_coeff_to_extended(ctx, sh.k, advice_polys.get() + (size_t)c * n, advice_cosets.get() + (size_t)c * en);
+    if (!shard.on()) {
+        dev_lagrange_to_coeff(ctx, sh.k, advice_polys.get(), NA, n);
+        for (uint32_t c = 0; c < NA; ++c) dev_coeff_to_extended(ctx, sh.k, advice_polys.get() + (size_t)c * n, advice_cosets.get() + (size_t)c * en);
+    } else {  // column c is transformed by rank c mod world and broadcast over NCCL
+        for (uint32_t c = 0; c < NA; ++c)
+            if (shard.mine(c)) {
+                dev_lagrange_to_coeff(ctx, sh.k, advice_polys.get() + (size_t)c * n);
+                dev_coeff_to_extended(ctx, sh.k, advice_polys.get() + (size_t)c * n, advice_cosets.get() + (size_t)c * en);
+            }
+        shard.group_start();
+        for (uint32_t c = 0; c < NA; ++c) {
+            shard.broadcast(advice_polys.get() + (size_t)c * n, n, shard.owner(c));
+            shard.broadcast(advice_cosets.get() + (size_t)c * en, en, shard.owner(c));
+        }
+        shard.group_end();
+    }
     lap(tm ? &tm->ntt : nullptr);
     DevBuf<Fr> h(en, s);
     {
@@ -441,19 +473,31 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
         Q.l_active = pk.l_polys.get() + 2 * en;
         Q.y = y; Q.beta = beta; Q.gamma = gamma; Q.delta = FrConsts::delta();
         Q.beta_zeta = f_mul(beta, FrConsts::zeta());
+        // each rank evaluates a contiguous slice of the extended rows; h is all-gathered at the end
+        const size_t rows_per_rank = shard.on() ? en / ctx.world : en;
+        Q.row_begin = shard.on() ? rows_per_rank * ctx.rank : 0;
+        Q.row_end = Q.row_begin + rows_per_rank;
         h_gates(Q, h.get(), s);
         h_permutation(Q, h.get(), L == 0, s);
         lap(tm ? &tm->quotient : nullptr);
         DevBuf<Fr> lc(3 * en, s);
         for (uint32_t l = 0; l < L; ++l) {
-            dev_coeff_to_extended(ctx, sh.k, lk_z_poly.get() + (size_t)l * n, lc.get());
-            dev_coeff_to_extended(ctx, sh.k, perm_in_poly.get() + (size_t)l * n, lc.get() + en);
-            dev_coeff_to_extended(ctx, sh.k, perm_tab_poly.get() + (size_t)l * n, lc.get() + 2 * en);
+            const Fr* srcs[3] = {lk_z_poly.get() + (size_t)l * n, perm_in_poly.get() + (size_t)l * n, perm_tab_poly.get() + (size_t)l * n};
+            for (uint32_t j = 0; j < 3; ++j)
+                if (shard.mine(3 * l + j)) dev_coeff_to_extended(ctx, sh.k, srcs[j], lc.get() + (size_t)j * en);
+            shard.group_start();
+            for (uint32_t j = 0; j < 3; ++j) shard.broadcast(lc.get() + (size_t)j * en, en, shard.owner(3 * l + j));
+            shard.group_end();
             lap(tm ? &tm->ntt : nullptr);
             LookupCosets Lk{lc.get(), lc.get() + en, lc.get() + 2 * en, Q.advice[A + l], Q.fixed[sh.table_col()]};
             h_lookup(Q, Lk, h.get(), l + 1 == L, s);
             lap(tm ? &tm->quotient : nullptr);
         }
+    }
+    if (shard.on()) {
+        if (en % ctx.world) throw std::runtime_error("sharded prover: world size must divide the extended domain");
+        shard.all_gather_inplace(h.get(), en / ctx.world);
+        lap(tm ? &tm->quotient : nullptr);
     }
     // step 10: vanishing::construct (D.9) — t_inv scaling already applied by the last h kernel
     DevBuf<Fr> h_coeff(3 * n, s);

@@ -4,6 +4,7 @@
 // gates q·(a + b·c − d) on rotations 0..3 of one advice column each, a permutation argument over P columns in sets
 // of 2, L single-column lookups against one table column.
 //
+// Rows [row_begin, row_end) are evaluated (the whole extended domain on one GPU, a contiguous slice per rank when sharded).
 // One thread per extended row i (4n rows): all column reads are coalesced 32-byte elements; rotations are row
 // offsets of ±4·r inside the same column (served by L1/L2). The running value is y-Horner-accumulated in
 // registers across ALL terms of a part, so h is written once per kernel: gates → permutation → one kernel per
@@ -18,8 +19,8 @@ DEV size_t rot_idx(size_t i, int r, size_t en) { return (i + en + (size_t)((long
 
 __global__ void __launch_bounds__(256) h_gates_kernel(QuotientArgs Q, Fr* h) {
     const size_t en = (size_t)4 << Q.k;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= en) return;
+    const size_t i = Q.row_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Q.row_end) return;
     const size_t i1 = rot_idx(i, 1, en), i2 = rot_idx(i, 2, en), i3 = rot_idx(i, 3, en);
     Fr v = f_zero<FrCfg>();
     for (uint32_t c = 0; c < Q.A; ++c) {
@@ -32,8 +33,8 @@ __global__ void __launch_bounds__(256) h_gates_kernel(QuotientArgs Q, Fr* h) {
 
 __global__ void __launch_bounds__(256) h_permutation_kernel(QuotientArgs Q, Fr* h, int final_scale) {
     const size_t en = (size_t)4 << Q.k;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= en) return;
+    const size_t i = Q.row_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Q.row_end) return;
     const size_t r_next = rot_idx(i, 1, en), r_last = rot_idx(i, -(int)(Q.blinding_factors + 1), en);
     const Fr one = f_one<FrCfg>();
     const Fr l0 = f_load(Q.l0 + i), l_last = f_load(Q.l_last + i), l_active = f_load(Q.l_active + i);
@@ -65,8 +66,8 @@ __global__ void __launch_bounds__(256) h_permutation_kernel(QuotientArgs Q, Fr* 
 
 __global__ void __launch_bounds__(256) h_lookup_kernel(QuotientArgs Q, LookupCosets Lk, Fr* h, int final_scale) {
     const size_t en = (size_t)4 << Q.k;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= en) return;
+    const size_t i = Q.row_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Q.row_end) return;
     const size_t r_next = rot_idx(i, 1, en), r_prev = rot_idx(i, -1, en);
     const Fr one = f_one<FrCfg>();
     const Fr l0 = f_load(Q.l0 + i), l_last = f_load(Q.l_last + i), l_active = f_load(Q.l_active + i);
@@ -87,21 +88,21 @@ __global__ void __launch_bounds__(256) h_lookup_kernel(QuotientArgs Q, LookupCos
 }
 
 void h_gates(const QuotientArgs& Q, Fr* h, cudaStream_t s) {
-    const size_t en = (size_t)4 << Q.k;
+    const size_t en = Q.row_end - Q.row_begin;
     prof_begin(PROF_QUOTIENT, s);
     h_gates_kernel<<<(unsigned)((en + 255) / 256), 256, 0, s>>>(Q, h);
     prof_end(s);
     LAUNCHED(1);
 }
 void h_permutation(const QuotientArgs& Q, Fr* h, bool final_scale, cudaStream_t s) {
-    const size_t en = (size_t)4 << Q.k;
+    const size_t en = Q.row_end - Q.row_begin;
     prof_begin(PROF_QUOTIENT, s);
     h_permutation_kernel<<<(unsigned)((en + 255) / 256), 256, 0, s>>>(Q, h, final_scale);
     prof_end(s);
     LAUNCHED(1);
 }
 void h_lookup(const QuotientArgs& Q, const LookupCosets& Lk, Fr* h, bool final_scale, cudaStream_t s) {
-    const size_t en = (size_t)4 << Q.k;
+    const size_t en = Q.row_end - Q.row_begin;
     prof_begin(PROF_QUOTIENT, s);
     h_lookup_kernel<<<(unsigned)((en + 255) / 256), 256, 0, s>>>(Q, Lk, h, final_scale);
     prof_end(s);

@@ -9,6 +9,7 @@ constexpr int Q_MAX_ADVICE = 48, Q_MAX_FIXED = 48, Q_MAX_PERM = 64, Q_MAX_SETS =
 struct QuotientArgs {
     uint32_t k, A, L, F, P, num_sets, blinding_factors;
     uint32_t table_log;
+    unsigned long long row_begin, row_end;  // extended rows evaluated by this launch
     const Fr* table;   // twiddle table (w^j of the 2^table_log-th root), table_log >= k+2
     const Fr* t_inv;   // 4 inverted vanishing evaluations (device)
     const Fr* advice[Q_MAX_ADVICE];    // extended cosets of the A + L advice columns

@@ -44,13 +44,30 @@ uint32_t msm_table_window_bits(uint32_t k);
 
 // window tables for both bases of the loaded SRS (msm.cu merged-bucket mode)
 void srs_build_tables(Context& ctx) {
-    if (!ctx.srs || !ctx.msm_tables_enabled) return;
+    if (!ctx.srs) return;
     Srs& srs = *ctx.srs;
-    srs.tab_c = msm_table_window_bits(srs.k);
+    CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+    srs.g_tab.release();
+    srs.gl_tab.release();
+    srs.tab_n = 0;
+    if (!ctx.msm_tables_enabled) return;
+    // this rank's MSM shard (the whole SRS on one GPU): tables only for the points it will ever touch, window size
+    // chosen for the shard length
+    size_t lo = 0, len = srs.n;
+    if (ctx.world > 1 && ctx.allgather) {
+        const size_t per = srs.n / ctx.world;
+        lo = per * ctx.rank;
+        len = ctx.rank == ctx.world - 1 ? srs.n - lo : per;
+    }
+    uint32_t lg = 0;
+    while (((size_t)1 << (lg + 1)) <= len) ++lg;
+    srs.tab_c = msm_table_window_bits(lg);
     const uint32_t W = (255 + srs.tab_c - 1) / srs.tab_c;
-    if ((size_t)W * srs.n >= ((size_t)1 << 31)) return;  // entry indices are 31-bit: fall back to the generic path
-    msm_build_table(ctx, srs.g.get(), srs.n, srs.tab_c, srs.g_tab);
-    msm_build_table(ctx, srs.g_lagrange.get(), srs.n, srs.tab_c, srs.gl_tab);
+    if ((size_t)W * len >= ((size_t)1 << 31)) return;  // entry indices are 31-bit: fall back to the generic path
+    msm_build_table(ctx, srs.g.get() + lo, len, srs.tab_c, srs.g_tab);
+    msm_build_table(ctx, srs.g_lagrange.get() + lo, len, srs.tab_c, srs.gl_tab);
+    srs.tab_lo = lo;
+    srs.tab_n = len;
     CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
 }
 

@@ -222,9 +222,12 @@ class Params:
         return out
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib().oracle_params_free(ctypes.c_void_p(self.h))
-            self.h = None
+        try:
+            if getattr(self, "h", None):
+                lib().oracle_params_free(ctypes.c_void_p(self.h))
+                self.h = None
+        except Exception:  # interpreter shutdown
+            pass
 
 
 class ProvingKey:
@@ -268,9 +271,12 @@ class ProvingKey:
         return bool(ok), last_error()
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib().oracle_pk_free(ctypes.c_void_p(self.h))
-            self.h = None
+        try:
+            if getattr(self, "h", None):
+                lib().oracle_pk_free(ctypes.c_void_p(self.h))
+                self.h = None
+        except Exception:
+            pass
 
 
 def mock_check(k, A, L, F, fixed, advice, copies):

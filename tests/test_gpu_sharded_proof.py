@@ -54,4 +54,4 @@ def test_two_rank_proof_is_identical(tmp_path):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert "rank 0 sharded ok" in r.stdout and "rank 1 sharded ok" in r.stdout
+    assert r.stdout.count("sharded ok") == 2, r.stdout  # (lines of the two ranks may interleave)

@@ -157,6 +157,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: one JSON line only
+
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     k, A, L, F = args.k, SHAPE["A"], SHAPE["L"], SHAPE["F"]
     n = 1 << k

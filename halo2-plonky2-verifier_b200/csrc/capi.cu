@@ -129,7 +129,6 @@ int b200zk_set_allgather(b200zk_ctx* ctx, int rank, int world, b200zk_allgather_
     ctx->c.allgather = fn;
     ctx->c.allgather_user = user;
     ctx->c.nccl.reset();
-    srs_build_tables(ctx->c);  // window tables follow this rank's MSM shard
     API_END(ctx)
 }
 int b200zk_set_msm_tables(b200zk_ctx* ctx, int on) {

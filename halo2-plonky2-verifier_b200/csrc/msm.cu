@@ -17,6 +17,7 @@
 //                 (≈0.1 ms) because a single GPU thread would take longer than the whole MSM.
 // Bound: integer pipe (≈10 Fq products per point·window), not HBM; see DESIGN.md.
 #include <algorithm>
+#include <chrono>
 
 #include "context.cuh"
 
@@ -436,8 +437,10 @@ static void msm_reduce_groups(Context& ctx, const G1X* bucket_sums, uint32_t G, 
 }
 
 // optional cross-rank combine of partial window sums (set through b200zk_set_allgather)
+double g_exchange_seconds = 0;  // host time spent in the partial-sum exchange callback (reported under "other")
 static void combine_across_ranks(Context& ctx, std::vector<G1X>& ws) {
     if (ctx.world <= 1 || !ctx.allgather) return;
+    const auto t0 = std::chrono::steady_clock::now();
     const size_t bytes = ws.size() * sizeof(G1X);
     std::vector<G1X> all(ws.size() * ctx.world);
     if (ctx.allgather(ctx.allgather_user, ws.data(), bytes, all.data()) != 0) throw std::runtime_error("msm: all-gather callback failed");
@@ -446,6 +449,7 @@ static void combine_across_ranks(Context& ctx, std::vector<G1X>& ws) {
         for (int r = 0; r < ctx.world; ++r) acc = g1x_add(acc, all[(size_t)r * ws.size() + w]);
         ws[w] = acc;
     }
+    g_exchange_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 // point range of this rank for an n-point MSM (contiguous shards; the last rank takes the remainder)
 static void shard_range(const Context& ctx, size_t n, size_t& lo, size_t& len) {
@@ -466,11 +470,11 @@ static void check_cfg(const MsmConfig& cfg, size_t n) {
 // `ncols` MSMs over the same bases: per-column bucket accumulation, ONE reduction for all columns, one exchange across ranks.
 // `bases_origin`: index of the point that bases[0] corresponds to (non-zero when `bases` is a per-shard window table)
 static void msm_batch_core(Context& ctx, const G1Affine* bases, const Fr* const* cols, size_t ncols, size_t n, const MsmConfig& cfg, G1Affine* out,
-                           size_t bases_origin) {
+                           size_t bases_origin, bool shard_points) {
     check_cfg(cfg, n);
     cudaStream_t s = ctx.stream;
-    size_t lo, len;
-    shard_range(ctx, n, lo, len);
+    size_t lo = 0, len = n;
+    if (shard_points) shard_range(ctx, n, lo, len);
     const uint32_t nb = cfg.groups * cfg.B;
     // bound the scratch: at most 16 columns (≈1 GiB of bucket sums at c = 20) per reduction round
     const size_t round = 16;
@@ -481,7 +485,7 @@ static void msm_batch_core(Context& ctx, const G1Affine* bases, const Fr* const*
         for (size_t j = 0; j < nc; ++j) msm_bucket_sums(ctx, bases + (lo - bases_origin), cols[c0 + j] + lo, len, cfg, bucket_sums.get() + j * nb);
         std::vector<G1X> ws;
         msm_reduce_groups(ctx, bucket_sums.get(), (uint32_t)(nc * cfg.groups), cfg.B, ws);
-        combine_across_ranks(ctx, ws);
+        if (shard_points) combine_across_ranks(ctx, ws);
         for (size_t j = 0; j < nc; ++j)
             out[c0 + j] = cfg.merged ? g1x_to_affine(ws[j]) : g1x_to_affine(msm_fold_windows(ws.data() + j * cfg.W, cfg.W, cfg.c));
     }
@@ -490,22 +494,39 @@ static void msm_batch_core(Context& ctx, const G1Affine* bases, const Fr* const*
 // arbitrary bases (best_multiexp): windows kept separate, folded on the host
 G1Affine msm_run(Context& ctx, const G1Affine* bases, const Fr* scalars, size_t n) {
     G1Affine r;
-    msm_batch_core(ctx, bases, &scalars, 1, n, msm_config(n), &r, 0);
+    msm_batch_core(ctx, bases, &scalars, 1, n, msm_config(n), &r, 0, true);
     return r;
 }
 
-// SRS bases: uses the precomputed window table when it exists (one bucket set, no fold)
-void msm_batch_srs(Context& ctx, int basis, const Fr* const* cols, size_t ncols, size_t n, G1Affine* out) {
+// SRS bases: uses the precomputed window table when it exists (one bucket set, no fold).
+// Multi-GPU (both levels of the north star): a batch with at least `world` columns is dealt out by
+// COLUMN — rank r commits columns r, r+world, ... over the full point range and the 64-byte results are all-gathered —
+// while smaller batches (the random polynomial, h pieces, SHPLONK quotients) are split by POINT RANGE with the partial
+// bucket sums exchanged.
+static void msm_batch_srs_local(Context& ctx, int basis, const Fr* const* cols, size_t ncols, size_t n, G1Affine* out, bool shard_points) {
     const Srs& srs = *ctx.srs;
     const DevBuf<G1Affine>& tab = basis == 0 ? srs.g_tab : srs.gl_tab;
-    size_t lo, len;
-    shard_range(ctx, n, lo, len);
-    // the table covers points [tab_lo, tab_lo + tab_n): usable when this call's shard is exactly that range start
-    const bool table_ok = tab.size() != 0 && n * 8 >= srs.n && lo == srs.tab_lo && len <= srs.tab_n;
-    if (!table_ok)
-        msm_batch_core(ctx, basis == 0 ? srs.g.get() : srs.g_lagrange.get(), cols, ncols, n, msm_config(n), out, 0);
+    if (tab.size() == 0 || n * 8 < srs.n)
+        msm_batch_core(ctx, basis == 0 ? srs.g.get() : srs.g_lagrange.get(), cols, ncols, n, msm_config(n), out, 0, shard_points);
     else
-        msm_batch_core(ctx, tab.get(), cols, ncols, n, msm_config_merged(srs.tab_c, srs.tab_n), out, srs.tab_lo);
+        msm_batch_core(ctx, tab.get(), cols, ncols, n, msm_config_merged(srs.tab_c, srs.n), out, 0, shard_points);
+}
+void msm_batch_srs(Context& ctx, int basis, const Fr* const* cols, size_t ncols, size_t n, G1Affine* out) {
+    const bool dist = ctx.world > 1 && ctx.allgather;
+    if (!dist || ncols < (size_t)ctx.world) {
+        msm_batch_srs_local(ctx, basis, cols, ncols, n, out, dist);
+        return;
+    }
+    const size_t world = ctx.world, per = (ncols + world - 1) / world;
+    std::vector<const Fr*> mine;
+    for (size_t j = ctx.rank; j < ncols; j += world) mine.push_back(cols[j]);
+    std::vector<G1Affine> send(per), recv(per * world);
+    memset(send.data(), 0, per * sizeof(G1Affine));
+    if (!mine.empty()) msm_batch_srs_local(ctx, basis, mine.data(), mine.size(), n, send.data(), false);
+    const auto t0 = std::chrono::steady_clock::now();
+    if (ctx.allgather(ctx.allgather_user, send.data(), per * sizeof(G1Affine), recv.data()) != 0) throw std::runtime_error("msm: all-gather callback failed");
+    g_exchange_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    for (size_t j = 0; j < ncols; ++j) out[j] = recv[(j % world) * per + j / world];
 }
 G1Affine msm_run_srs(Context& ctx, int basis, const Fr* scalars, size_t n) {
     G1Affine r;

@@ -51,14 +51,8 @@ void srs_build_tables(Context& ctx) {
     srs.gl_tab.release();
     srs.tab_n = 0;
     if (!ctx.msm_tables_enabled) return;
-    // this rank's MSM shard (the whole SRS on one GPU): tables only for the points it will ever touch, window size
-    // chosen for the shard length
+    // full-range tables on every rank: column-dealt batches need all points, point-range shards index into the same table
     size_t lo = 0, len = srs.n;
-    if (ctx.world > 1 && ctx.allgather) {
-        const size_t per = srs.n / ctx.world;
-        lo = per * ctx.rank;
-        len = ctx.rank == ctx.world - 1 ? srs.n - lo : per;
-    }
     uint32_t lg = 0;
     while (((size_t)1 << (lg + 1)) <= len) ++lg;
     srs.tab_c = msm_table_window_bits(lg);

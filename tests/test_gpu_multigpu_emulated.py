@@ -62,3 +62,30 @@ def test_tables_and_generic_paths_agree(ctx):
         assert np.array_equal(x, y)
     g, gl = ctx.srs_download()
     assert np.array_equal(with_tab[1], O.msm(a, gl))
+
+
+def test_column_dealt_batch(ctx):
+    """Batches with >= world columns are dealt out by column: each rank commits its own columns over the full range."""
+    k, world = 12, 2
+    n = 1 << k
+    ctx.srs_setup(k)
+    rng = np.random.default_rng(4)
+    cols = [O.random_fr(rng, n) for _ in range(5)]
+    ptrs = []
+    for c in cols:
+        p = ctx.dev_alloc(32 * n)
+        ctx.h2d(p, c)
+        ptrs.append(p)
+    want = ctx.msm_batch_dev(ptrs, n, 1)
+    got = {}
+    try:
+        for rank in range(world):
+            ctx.set_allgather(rank, world, lambda data, rank=rank: b"".join(data if r == rank else bytes(len(data)) for r in range(world)))
+            got[rank] = ctx.msm_batch_dev(ptrs, n, 1)
+    finally:
+        ctx.set_allgather(0, 1, None)
+    for j in range(5):
+        assert np.array_equal(got[j % world][j], want[j]), j          # the owner produced the right commitment
+        assert not got[1 - j % world][j].any()                        # the other rank left it to the exchange
+    for p in ptrs:
+        ctx.dev_free(p)

@@ -31,6 +31,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 SHAPE = dict(A=14, L=3, F=1)  # S20-bn / its k-scaled versions
+emit = None
 IMAD_PEAK_TOPS = 18.0  # measured by tools/microbench.cu on this pool's B200 (profiles/microbench_r01.json)
 
 
@@ -134,11 +135,18 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
     args = parse()
+    # stdout carries exactly ONE JSON line: anything else that writes to fd 1 (NCCL's version banner, library chatter)
+    # is sent to stderr; the JSON goes through the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    global emit
+    emit = lambda line: os.write(json_fd, (json.dumps(line) + "\n").encode())  # noqa: E731
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -157,8 +165,6 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: one JSON line only
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     k, A, L, F = args.k, SHAPE["A"], SHAPE["L"], SHAPE["F"]
@@ -273,7 +279,7 @@ def main():
                                 "sample": f"oracle create_proof on the same shape at k={args.sample_k}: {secs:.3f} s, scaled x{int(scale)} (rows) to k={k}; "
                                           "restated halo2 CPU algorithms (C++ oracle, std::thread), not the rayon binary"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

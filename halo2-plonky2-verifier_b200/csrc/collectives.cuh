@@ -18,6 +18,8 @@ struct Nccl {
     int (*CommInitRank)(void**, int, UniqueId, int) = nullptr;
     int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     int (*CommDestroy)(void*) = nullptr;
@@ -42,6 +44,8 @@ struct Nccl {
         sym(CommInitRank, "ncclCommInitRank");
         sym(Broadcast, "ncclBroadcast");
         sym(AllGather, "ncclAllGather");
+        sym(Send, "ncclSend");
+        sym(Recv, "ncclRecv");
         sym(GroupStart, "ncclGroupStart");
         sym(GroupEnd, "ncclGroupEnd");
         sym(CommDestroy, "ncclCommDestroy");
@@ -83,6 +87,48 @@ struct Sharder {
     void broadcast(Fr* buf, size_t count, int root) {
         if (!on()) return;
         nccl().check(nccl().Broadcast(buf, buf, count * sizeof(Fr), /*ncclUint8*/ 1, root, nccl().comm, ctx.stream), "Broadcast");
+    }
+    // Row-slice exchange for the h(X) stage: column c (length en, complete on owner(c) only) is needed by rank d only on
+    // the extended rows d evaluates plus the rotation halo — rows [d·R − before, (d+1)·R + after) mod en, R = en / world.
+    // Owners send exactly those rows (1/world of the column per peer instead of a full broadcast); receivers keep
+    // full-length buffers and only that window is ever read.
+    template <class OwnerFn>
+    void exchange_row_slices(Fr* const* cols, size_t ncols, OwnerFn owner_of, size_t en, size_t before, size_t after) {
+        if (!on()) return;
+        Nccl& nc = nccl();
+        const size_t R = en / ctx.world;
+        auto for_segments = [&](int d, auto&& fn) {  // contiguous pieces of rank d's window
+            const long long start = (long long)(R * d) - (long long)before, end = (long long)(R * (d + 1)) + (long long)after;
+            if (end - start >= (long long)en) {
+                fn((size_t)0, en);
+                return;
+            }
+            if (start < 0) {
+                fn((size_t)(en + start), (size_t)(-start));
+                fn((size_t)0, (size_t)end);
+            } else if (end > (long long)en) {
+                fn((size_t)start, (size_t)(en - start));
+                fn((size_t)0, (size_t)(end - en));
+            } else {
+                fn((size_t)start, (size_t)(end - start));
+            }
+        };
+        nc.check(nc.GroupStart(), "GroupStart");
+        for (size_t c = 0; c < ncols; ++c) {
+            const int o = owner_of(c);
+            if (o == ctx.rank) {
+                for (int d = 0; d < ctx.world; ++d)
+                    if (d != ctx.rank)
+                        for_segments(d, [&](size_t off, size_t len) {
+                            nc.check(nc.Send(cols[c] + off, len * sizeof(Fr), 1, d, nc.comm, ctx.stream), "Send");
+                        });
+            } else {
+                for_segments(ctx.rank, [&](size_t off, size_t len) {
+                    nc.check(nc.Recv(cols[c] + off, len * sizeof(Fr), 1, o, nc.comm, ctx.stream), "Recv");
+                });
+            }
+        }
+        nc.check(nc.GroupEnd(), "GroupEnd");
     }
     // buf holds world equal chunks; this rank filled chunk `rank`
     void all_gather_inplace(Fr* buf, size_t chunk) {

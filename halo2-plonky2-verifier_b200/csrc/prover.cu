@@ -276,6 +276,8 @@ static Fr vanishing_eval(const std::vector<Fr>& roots, const Fr& z) {
 }
 
 // ---- create_proof ---------------------------------------------------------------------------------------------------------
+// rotation reach of the h(X) kernels in extended rows: -4·(blinding_factors+1) = -28 (z of the previous set) ... +12 (gate rotation 3)
+static constexpr size_t HALO_BEFORE = 32, HALO_AFTER = 16;
 std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const Fr* advice_in, bool advice_on_device, host::FrRandomStream& rng,
                                   ProofTimings* tm) {
     const Shape& sh = pk.shape;
@@ -395,11 +397,11 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
                     dev_coeff_to_extended(ctx, sh.k, z_polys.get() + (size_t)set * n, z_cosets.get() + (size_t)set * en);
                 }
             shard.group_start();
-            for (uint32_t set = 0; set < NS; ++set) {
-                shard.broadcast(z_polys.get() + (size_t)set * n, n, shard.owner(set));
-                shard.broadcast(z_cosets.get() + (size_t)set * en, en, shard.owner(set));
-            }
+            for (uint32_t set = 0; set < NS; ++set) shard.broadcast(z_polys.get() + (size_t)set * n, n, shard.owner(set));
             shard.group_end();
+            std::vector<Fr*> cs(NS);
+            for (uint32_t set = 0; set < NS; ++set) cs[set] = z_cosets.get() + (size_t)set * en;
+            shard.exchange_row_slices(cs.data(), NS, [&](size_t c) { return shard.owner(c); }, en, HALO_BEFORE, HALO_AFTER);
         }
         lap(tm ? &tm->ntt : nullptr);
         for (const G1Affine& cm : cms) tr.write_point(cm);
@@ -449,11 +451,11 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
                 dev_coeff_to_extended(ctx, sh.k, advice_polys.get() + (size_t)c * n, advice_cosets.get() + (size_t)c * en);
             }
         shard.group_start();
-        for (uint32_t c = 0; c < NA; ++c) {
-            shard.broadcast(advice_polys.get() + (size_t)c * n, n, shard.owner(c));
-            shard.broadcast(advice_cosets.get() + (size_t)c * en, en, shard.owner(c));
-        }
+        for (uint32_t c = 0; c < NA; ++c) shard.broadcast(advice_polys.get() + (size_t)c * n, n, shard.owner(c));
         shard.group_end();
+        std::vector<Fr*> cs(NA);
+        for (uint32_t c = 0; c < NA; ++c) cs[c] = advice_cosets.get() + (size_t)c * en;
+        shard.exchange_row_slices(cs.data(), NA, [&](size_t c) { return shard.owner(c); }, en, HALO_BEFORE, HALO_AFTER);
     }
     lap(tm ? &tm->ntt : nullptr);
     DevBuf<Fr> h(en, s);
@@ -487,9 +489,8 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
             const Fr* srcs[3] = {lk_z_poly.get() + (size_t)l * n, perm_in_poly.get() + (size_t)l * n, perm_tab_poly.get() + (size_t)l * n};
             for (uint32_t j = 0; j < 3; ++j)
                 if (shard.mine(3 * l + j)) dev_coeff_to_extended(ctx, sh.k, srcs[j], lc.get() + (size_t)j * en);
-            shard.group_start();
-            for (uint32_t j = 0; j < 3; ++j) shard.broadcast(lc.get() + (size_t)j * en, en, shard.owner(3 * l + j));
-            shard.group_end();
+            Fr* cs[3] = {lc.get(), lc.get() + en, lc.get() + 2 * en};
+            shard.exchange_row_slices(cs, 3, [&](size_t j) { return shard.owner(3 * l + j); }, en, HALO_BEFORE, HALO_AFTER);
             lap(tm ? &tm->ntt : nullptr);
             LookupCosets Lk{lc.get(), lc.get() + en, lc.get() + 2 * en, Q.advice[A + l], Q.fixed[sh.table_col()]};
             h_lookup(Q, Lk, h.get(), l + 1 == L, s);

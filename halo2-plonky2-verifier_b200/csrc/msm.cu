@@ -189,18 +189,18 @@ DEV uint32_t find_bucket(const uint32_t* offsets, uint32_t nb, uint32_t p) {
     return lo;
 }
 
-constexpr int ACC_T = 32;        // entries per thread, level 1
+constexpr int ACC_T_MIN = 16, ACC_T_MAX = 64;  // entries per thread, level 1 (chosen per launch, see pick_chunk)
 constexpr int COMB_T = 16;       // partial sums per thread, levels >= 2
 constexpr int ACC_THREADS = 128;
 
 __global__ void __launch_bounds__(ACC_THREADS) msm_accumulate_kernel(const G1Affine* bases, const uint32_t* entries, const uint32_t* offsets,
-                                                                     uint32_t nb, uint32_t total, G1X* bucket_sums, G1X* heads,
+                                                                     uint32_t nb, uint32_t total, uint32_t chunk, G1X* bucket_sums, G1X* heads,
                                                                      uint32_t* head_keys) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t p0l = (uint64_t)t * ACC_T;
+    const uint64_t p0l = (uint64_t)t * chunk;
     if (p0l >= total) return;
     const uint32_t p0 = (uint32_t)p0l;
-    const uint32_t p1 = total - p0 > (uint32_t)ACC_T ? p0 + ACC_T : total;
+    const uint32_t p1 = total - p0 > chunk ? p0 + chunk : total;
     uint32_t cur = find_bucket(offsets, nb, p0);
     uint32_t end = __ldg(offsets + cur + 1);
     bool started_before = __ldg(offsets + cur) < p0;
@@ -349,11 +349,15 @@ static void msm_bucket_sums(Context& ctx, const G1Affine* bases, const Fr* scala
     msm_digits_kernel<<<dblocks, 128, 0, s>>>(scalars, n, cfg, counters.get(), entries.get(), 1);
     ++g_launch_count;
     // level 1
-    uint32_t nthreads = (uint32_t)(((uint64_t)total + ACC_T - 1) / ACC_T);
+    // chunk length: long chunks halve the head list for big columns, short ones keep small columns (1–2 M entries) wide
+    // enough to fill 148 SMs
+    uint32_t chunk = ACC_T_MAX;
+    while (chunk > (uint32_t)ACC_T_MIN && (uint64_t)total / chunk < (uint64_t)148 * 16 * 32) chunk >>= 1;
+    uint32_t nthreads = (uint32_t)(((uint64_t)total + chunk - 1) / chunk);
     DevBuf<G1X> heads_a(nthreads, s), heads_b;
     DevBuf<uint32_t> keys_a(nthreads, s), keys_b;
     prof_begin(PROF_MSM_ACCUMULATE, s);
-    msm_accumulate_kernel<<<(nthreads + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, s>>>(bases, entries.get(), offsets.get(), nb, total, bucket_sums,
+    msm_accumulate_kernel<<<(nthreads + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, s>>>(bases, entries.get(), offsets.get(), nb, total, chunk, bucket_sums,
                                                                                               heads_a.get(), keys_a.get());
     prof_end(s);
     ++g_launch_count;

@@ -47,6 +47,7 @@ struct PassParams {
     uint32_t L, s0, r, logC;
     uint32_t table_shift, half_table;
     uint32_t inverse, first, last;
+    uint32_t skip2;  // first pass of a 4x zero-padded input: stages 1-2 only replicate each non-zero element 4 times
 };
 
 constexpr int NTT_THREADS = 256;
@@ -90,7 +91,8 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(PassParams P) {
         size_t src;
         if (P.first) {
             const uint32_t hrev = tile * C + c;  // bit-reversed `hi`
-            const uint32_t mrev = P.r ? (__brev(m) >> (32 - P.r)) : 0;
+            const uint32_t msrc = P.skip2 ? (m & ~3u) : m;
+            const uint32_t mrev = P.r ? (__brev(msrc) >> (32 - P.r)) : 0;
             src = ((size_t)mrev << (P.L - P.r)) + hrev;
         } else {
             src = ((size_t)hi << s1) + ((size_t)m << P.s0) + lo_base + c;
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(PassParams P) {
     }
     __syncthreads();
     // ---- butterflies ----
-    for (uint32_t t = 1; t <= P.r; ++t) {
+    for (uint32_t t = P.skip2 ? 3 : 1; t <= P.r; ++t) {
         const uint32_t half = 1u << (t - 1);
         const uint32_t s = P.s0 + t;
         const bool trivial = P.first && t == 1;  // all twiddles are w^0
@@ -199,6 +201,9 @@ void ntt_run_batch(const NttPlan& plan, const Fr* in, Fr* out, Fr* scratch, uint
         P.logC = avail < (uint32_t)NTT_MAX_LOGC ? avail : NTT_MAX_LOGC;
         P.pre3 = P.first ? plan.pre_scale3 : nullptr;
         P.in_len = P.first ? plan.in_len : 0;
+        // zero-padded to 4x (coeff_to_extended): positions with (m & 3) != 0 hold zeros after the bit reversal, so the first two
+        // stages turn [a,0,0,0] into [a,a,a,a] — load that directly and start at stage 3
+        P.skip2 = P.first && r >= 2 && plan.in_len != 0 && plan.in_len * 4 == ((size_t)1 << L) ? 1u : 0u;
         P.post3 = P.last ? plan.post_scale3 : nullptr;
         P.out_len = P.last ? plan.out_len : 0;
         const uint32_t T = 1u << (r + P.logC);

@@ -308,7 +308,17 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
     tr.common_scalar(pk.transcript_repr);
     // step 1: upload, blind, commit advice (D.3)
     DevBuf<Fr> advice((size_t)NA * n, s);
-    CUDA_CHECK(cudaMemcpyAsync(advice.get(), advice_in, (size_t)NA * n * sizeof(Fr), advice_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    if (shard.on() && !advice_on_device) {
+        // every rank holds the host witness: each uploads only its share of the columns over PCIe and the rest arrives over NVLink
+        for (uint32_t c = 0; c < NA; ++c)
+            if (shard.mine(c))
+                CUDA_CHECK(cudaMemcpyAsync(advice.get() + (size_t)c * n, advice_in + (size_t)c * n, n * sizeof(Fr), cudaMemcpyHostToDevice, s));
+        shard.group_start();
+        for (uint32_t c = 0; c < NA; ++c) shard.broadcast(advice.get() + (size_t)c * n, n, shard.owner(c));
+        shard.group_end();
+    } else {
+        CUDA_CHECK(cudaMemcpyAsync(advice.get(), advice_in, (size_t)NA * n * sizeof(Fr), advice_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    }
     {
         std::vector<Fr> blind((size_t)NA * (bf + 1));
         for (auto& b : blind) b = rng.next();

@@ -248,9 +248,11 @@ def main():
     alg_bytes = 96.0 * n
     achieved = alg_bytes / (acc_avg_ms * 1e-3) / 1e9 if acc_avg_ms > 0 else 0.0
     roofline = {"kernel": "msm_accumulate_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "launches": acc_n, "avg_launch_ms": acc_avg_ms, "share_of_step": acc_ms / (ms_dev if ms_dev else 1),
-                "note": "integer-pipe bound by design (north_star: no tensor cores, IMAD carry chains); the HBM fraction is reported because the "
-                        "contract asks for it — see int_pipe for the binding roof"}
+                "traffic": 1.844e9, "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of the 2^20 uniform-scalar launch "
+                                                      "(profiles/ncu_summary_r01.md); one 64-byte base gathered per non-zero digit",
+                "peak_source": peak_src, "launches": acc_n, "avg_launch_ms": acc_avg_ms, "share_of_step": acc_ms / (ms_dev if ms_dev else 1),
+                "note": "integer-pipe bound by design (north_star: no tensor cores, IMAD carry chains): ncu shows the FMA-heavy (IMAD) pipe 80 % "
+                        "busy in this kernel (profiles/ncu_summary_r01.md); the HBM fraction is reported because the contract asks for it"}
     line = {
         "metric": "create_proof_s", "value": ms_dev / 1e3, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
         "higher_is_better": False, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "u32 limbs (254-bit Montgomery integers)",

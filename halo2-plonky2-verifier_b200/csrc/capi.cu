@@ -63,6 +63,12 @@ int b200zk_create(int device, b200zk_ctx** out) {
         uint64_t thr = ~0ull;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
+    if (cudaStreamCreateWithFlags(&ctx->c.stream2, cudaStreamNonBlocking) != cudaSuccess) ctx->c.stream2 = nullptr;
+    for (auto& e : ctx->c.msm_events) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    if (cudaHostAlloc((void**)&ctx->c.pinned_u32, 16, cudaHostAllocDefault) != cudaSuccess) {
+        b200zk_destroy(ctx);
+        return B200ZK_ECUDA;
+    }
     ctx->c.arena.stream = ctx->c.stream;
     arena_register(ctx->c.stream, &ctx->c.arena);
     *out = ctx;
@@ -81,6 +87,13 @@ int b200zk_destroy(b200zk_ctx* ctx) {
     cudaStreamSynchronize(s);
     arena_register(s, nullptr);
     ctx->c.arena.destroy();
+    if (ctx->c.stream2) {
+        cudaStreamSynchronize(ctx->c.stream2);
+        cudaStreamDestroy(ctx->c.stream2);
+    }
+    for (auto& e : ctx->c.msm_events)
+        if (e) cudaEventDestroy(e);
+    if (ctx->c.pinned_u32) cudaFreeHost(ctx->c.pinned_u32);
     delete ctx;
     cudaStreamDestroy(s);
     return B200ZK_OK;

@@ -79,6 +79,9 @@ typedef int (*AllGatherFn)(void* user, const void* send, size_t bytes, void* rec
 struct Context {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;        // auxiliary stream: second MSM column in flight (msm.cu)
+    cudaEvent_t msm_events[4] = {};
+    uint32_t* pinned_u32 = nullptr;        // 2 pinned words for the entry-count read-backs
     std::mutex mu;
     std::string last_error;
     std::map<uint32_t, std::unique_ptr<TwiddleTable>> tables;  // standard roots, keyed by table log

@@ -328,37 +328,54 @@ G1X msm_fold_windows(const G1X* window_sums, uint32_t W, uint32_t c) {
     return acc;
 }
 
-// Phase A of one MSM: digits -> counting sort -> chunked accumulation -> head combine. Leaves the bucket sums of this
-// column in bucket_sums[0 .. groups·B) (zero-initialised by the caller). Synchronises once (entry count).
-static void msm_bucket_sums(Context& ctx, const G1Affine* bases, const Fr* scalars, size_t n, const MsmConfig& cfg, G1X* bucket_sums) {
-    cudaStream_t s = ctx.stream;
+// Phase A of one MSM column (digits -> counting sort -> chunked accumulation -> head combine), cut in two halves around
+// the one host read-back (the entry count) so that TWO columns can be in flight on two streams: while one column's
+// accumulate saturates the multiplier pipe, the other's latency-bound pieces (histogram atomics, scans, the read-back,
+// the short combine levels) fill the gaps. All scratch is preallocated at its worst-case size per slot.
+struct MsmSlot {
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev = nullptr;
+    uint32_t* total_host = nullptr;  // pinned
+    DevBuf<uint32_t> counters, offsets, entries, keys_a, keys_b;
+    DevBuf<G1X> heads_a, heads_b;
+    void alloc(Context& ctx, uint32_t nb, size_t max_entries) {
+        const size_t t1 = (max_entries + ACC_T_MIN - 1) / ACC_T_MIN + 1, t2 = (t1 + COMB_T - 1) / COMB_T + 1;
+        counters.alloc(nb + 1, ctx.stream);
+        offsets.alloc(nb + 1, ctx.stream);
+        entries.alloc(max_entries + 1, ctx.stream);
+        heads_a.alloc(t1, ctx.stream);
+        keys_a.alloc(t1, ctx.stream);
+        heads_b.alloc(t2, ctx.stream);
+        keys_b.alloc(t2, ctx.stream);
+    }
+};
+static void msm_issue_count(MsmSlot& sl, const Fr* scalars, size_t n, const MsmConfig& cfg) {
+    cudaStream_t s = sl.st;
     const uint32_t nb = cfg.groups * cfg.B;
-    if (n == 0) return;
-    DevBuf<uint32_t> counters(nb + 1, s), offsets(nb + 1, s);
-    CUDA_CHECK(cudaMemsetAsync(counters.get(), 0, (nb + 1) * 4, s));
-    const unsigned dblocks = (unsigned)((n + 127) / 128);
-    msm_digits_kernel<<<dblocks, 128, 0, s>>>(scalars, n, cfg, counters.get(), nullptr, 0);
+    CUDA_CHECK(cudaMemsetAsync(sl.counters.get(), 0, (nb + 1) * 4, s));
+    msm_digits_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(scalars, n, cfg, sl.counters.get(), nullptr, 0);
     ++g_launch_count;
-    exclusive_scan_u32(counters.get(), offsets.get(), nb + 1, s);
-    uint32_t total = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&total, offsets.get() + nb, 4, cudaMemcpyDeviceToHost, s));
-    CUDA_CHECK(cudaMemcpyAsync(counters.get(), offsets.get(), (nb + 1) * 4, cudaMemcpyDeviceToDevice, s));
-    CUDA_CHECK(cudaStreamSynchronize(s));
+    exclusive_scan_u32(sl.counters.get(), sl.offsets.get(), nb + 1, s);
+    CUDA_CHECK(cudaMemcpyAsync(sl.total_host, sl.offsets.get() + nb, 4, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaMemcpyAsync(sl.counters.get(), sl.offsets.get(), (nb + 1) * 4, cudaMemcpyDeviceToDevice, s));
+    CUDA_CHECK(cudaEventRecord(sl.ev, s));
+}
+static void msm_issue_accumulate(MsmSlot& sl, const G1Affine* bases, const Fr* scalars, size_t n, const MsmConfig& cfg, G1X* bucket_sums) {
+    cudaStream_t s = sl.st;
+    const uint32_t nb = cfg.groups * cfg.B;
+    CUDA_CHECK(cudaEventSynchronize(sl.ev));
+    const uint32_t total = *sl.total_host;
     if (total == 0) return;
-    DevBuf<uint32_t> entries(total, s);
-    msm_digits_kernel<<<dblocks, 128, 0, s>>>(scalars, n, cfg, counters.get(), entries.get(), 1);
+    msm_digits_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(scalars, n, cfg, sl.counters.get(), sl.entries.get(), 1);
     ++g_launch_count;
-    // level 1
     // chunk length: long chunks halve the head list for big columns, short ones keep small columns (1–2 M entries) wide
     // enough to fill 148 SMs
     uint32_t chunk = ACC_T_MAX;
     while (chunk > (uint32_t)ACC_T_MIN && (uint64_t)total / chunk < (uint64_t)148 * 16 * 32) chunk >>= 1;
-    uint32_t nthreads = (uint32_t)(((uint64_t)total + chunk - 1) / chunk);
-    DevBuf<G1X> heads_a(nthreads, s), heads_b;
-    DevBuf<uint32_t> keys_a(nthreads, s), keys_b;
+    const uint32_t nthreads = (uint32_t)(((uint64_t)total + chunk - 1) / chunk);
     prof_begin(PROF_MSM_ACCUMULATE, s);
-    msm_accumulate_kernel<<<(nthreads + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, s>>>(bases, entries.get(), offsets.get(), nb, total, chunk, bucket_sums,
-                                                                                              heads_a.get(), keys_a.get());
+    msm_accumulate_kernel<<<(nthreads + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, s>>>(bases, sl.entries.get(), sl.offsets.get(), nb, total, chunk, bucket_sums,
+                                                                                              sl.heads_a.get(), sl.keys_a.get());
     prof_end(s);
     ++g_launch_count;
     CUDA_CHECK(cudaGetLastError());
@@ -367,13 +384,11 @@ static void msm_bucket_sums(Context& ctx, const G1Affine* bases, const Fr* scala
     bool flip = false;
     while (true) {
         const uint32_t nt = (len + COMB_T - 1) / COMB_T;
-        DevBuf<G1X>& in_p = flip ? heads_b : heads_a;
-        DevBuf<uint32_t>& in_k = flip ? keys_b : keys_a;
-        DevBuf<G1X>& out_p = flip ? heads_a : heads_b;
-        DevBuf<uint32_t>& out_k = flip ? keys_a : keys_b;
-        out_p.alloc(nt, s);
-        out_k.alloc(nt, s);
-        msm_combine_kernel<<<(nt + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, s>>>(in_p.get(), in_k.get(), len, bucket_sums, out_p.get(), out_k.get());
+        G1X* in_p = flip ? sl.heads_b.get() : sl.heads_a.get();
+        uint32_t* in_k = flip ? sl.keys_b.get() : sl.keys_a.get();
+        G1X* out_p = flip ? sl.heads_a.get() : sl.heads_b.get();
+        uint32_t* out_k = flip ? sl.keys_a.get() : sl.keys_b.get();
+        msm_combine_kernel<<<(nt + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, s>>>(in_p, in_k, len, bucket_sums, out_p, out_k);
         ++g_launch_count;
         CUDA_CHECK(cudaGetLastError());
         if (nt == 1) break;  // a single thread has no predecessor: nothing can be left in its head slot
@@ -486,7 +501,33 @@ static void msm_batch_core(Context& ctx, const G1Affine* bases, const Fr* const*
         const size_t nc = std::min(round, ncols - c0);
         DevBuf<G1X> bucket_sums((size_t)nc * nb, s);
         CUDA_CHECK(cudaMemsetAsync(bucket_sums.get(), 0, (size_t)nc * nb * sizeof(G1X), s));
-        for (size_t j = 0; j < nc; ++j) msm_bucket_sums(ctx, bases + (lo - bases_origin), cols[c0 + j] + lo, len, cfg, bucket_sums.get() + j * nb);
+        if (len > 0) {
+            // two columns in flight: slot 0 on the context stream, slot 1 on the auxiliary stream
+            const int nslots = nc >= 2 && ctx.stream2 ? 2 : 1;
+            MsmSlot slots[2];
+            for (int q = 0; q < nslots; ++q) {
+                slots[q].st = q == 0 ? s : ctx.stream2;
+                slots[q].ev = ctx.msm_events[q];
+                slots[q].total_host = ctx.pinned_u32 + q;
+                slots[q].alloc(ctx, nb, len * cfg.W);
+            }
+            if (nslots == 2) {  // the aux stream may touch the buffers only after everything queued so far on the main stream
+                CUDA_CHECK(cudaEventRecord(ctx.msm_events[2], s));
+                CUDA_CHECK(cudaStreamWaitEvent(ctx.stream2, ctx.msm_events[2], 0));
+            }
+            const G1Affine* b = bases + (lo - bases_origin);
+            for (size_t j = 0; j < (size_t)nslots && j < nc; ++j) msm_issue_count(slots[j], cols[c0 + j] + lo, len, cfg);
+            for (size_t j = 0; j < nc; ++j) {
+                MsmSlot& sl = slots[j % nslots];
+                msm_issue_accumulate(sl, b, cols[c0 + j] + lo, len, cfg, bucket_sums.get() + j * nb);
+                if (j + nslots < nc) msm_issue_count(sl, cols[c0 + j + nslots] + lo, len, cfg);
+            }
+            if (nslots == 2) {  // main stream (reduce, frees) continues after the aux stream has drained
+                CUDA_CHECK(cudaEventRecord(ctx.msm_events[3], ctx.stream2));
+                CUDA_CHECK(cudaStreamWaitEvent(s, ctx.msm_events[3], 0));
+            }
+            CUDA_CHECK(cudaStreamSynchronize(s));  // slot buffers are released below: nothing may still be using them
+        }
         std::vector<G1X> ws;
         msm_reduce_groups(ctx, bucket_sums.get(), (uint32_t)(nc * cfg.groups), cfg.B, ws);
         if (shard_points) combine_across_ranks(ctx, ws);

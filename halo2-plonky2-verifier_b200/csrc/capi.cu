@@ -63,9 +63,12 @@ int b200zk_create(int device, b200zk_ctx** out) {
         uint64_t thr = ~0ull;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
-    if (cudaStreamCreateWithFlags(&ctx->c.stream2, cudaStreamNonBlocking) != cudaSuccess) ctx->c.stream2 = nullptr;
+    for (auto& st : ctx->c.aux_streams)
+        if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) st = nullptr;
     for (auto& e : ctx->c.msm_events) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-    if (cudaHostAlloc((void**)&ctx->c.pinned_u32, 16, cudaHostAllocDefault) != cudaSuccess) {
+    for (auto& e : ctx->c.msm_join) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->c.msm_fork, cudaEventDisableTiming);
+    if (cudaHostAlloc((void**)&ctx->c.pinned_u32, 64, cudaHostAllocDefault) != cudaSuccess) {
         b200zk_destroy(ctx);
         return B200ZK_ECUDA;
     }
@@ -87,12 +90,16 @@ int b200zk_destroy(b200zk_ctx* ctx) {
     cudaStreamSynchronize(s);
     arena_register(s, nullptr);
     ctx->c.arena.destroy();
-    if (ctx->c.stream2) {
-        cudaStreamSynchronize(ctx->c.stream2);
-        cudaStreamDestroy(ctx->c.stream2);
-    }
+    for (auto& st : ctx->c.aux_streams)
+        if (st) {
+            cudaStreamSynchronize(st);
+            cudaStreamDestroy(st);
+        }
     for (auto& e : ctx->c.msm_events)
         if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->c.msm_join)
+        if (e) cudaEventDestroy(e);
+    if (ctx->c.msm_fork) cudaEventDestroy(ctx->c.msm_fork);
     if (ctx->c.pinned_u32) cudaFreeHost(ctx->c.pinned_u32);
     delete ctx;
     cudaStreamDestroy(s);

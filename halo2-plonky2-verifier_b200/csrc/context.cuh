@@ -76,12 +76,14 @@ struct Srs {
 typedef int (*AllGatherFn)(void* user, const void* send, size_t bytes, void* recv);
 
 
+constexpr int MSM_SLOTS = 4;  // MSM columns in flight per commit batch
+
 struct Context {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t stream2 = nullptr;        // auxiliary stream: second MSM column in flight (msm.cu)
-    cudaEvent_t msm_events[4] = {};
-    uint32_t* pinned_u32 = nullptr;        // 2 pinned words for the entry-count read-backs
+    cudaStream_t aux_streams[MSM_SLOTS - 1] = {};  // further MSM columns in flight (msm.cu)
+    cudaEvent_t msm_events[MSM_SLOTS] = {}, msm_join[MSM_SLOTS - 1] = {}, msm_fork = nullptr;
+    uint32_t* pinned_u32 = nullptr;        // pinned words for the entry-count read-backs (one per slot)
     std::mutex mu;
     std::string last_error;
     std::map<uint32_t, std::unique_ptr<TwiddleTable>> tables;  // standard roots, keyed by table log

@@ -502,18 +502,18 @@ static void msm_batch_core(Context& ctx, const G1Affine* bases, const Fr* const*
         DevBuf<G1X> bucket_sums((size_t)nc * nb, s);
         CUDA_CHECK(cudaMemsetAsync(bucket_sums.get(), 0, (size_t)nc * nb * sizeof(G1X), s));
         if (len > 0) {
-            // two columns in flight: slot 0 on the context stream, slot 1 on the auxiliary stream
-            const int nslots = nc >= 2 && ctx.stream2 ? 2 : 1;
-            MsmSlot slots[2];
+            // several columns in flight: slot 0 on the context stream, the others on auxiliary streams
+            const int nslots = ctx.aux_streams[0] ? (int)std::min<size_t>(nc, MSM_SLOTS) : 1;
+            MsmSlot slots[MSM_SLOTS];
             for (int q = 0; q < nslots; ++q) {
-                slots[q].st = q == 0 ? s : ctx.stream2;
+                slots[q].st = q == 0 ? s : ctx.aux_streams[q - 1];
                 slots[q].ev = ctx.msm_events[q];
                 slots[q].total_host = ctx.pinned_u32 + q;
                 slots[q].alloc(ctx, nb, len * cfg.W);
             }
-            if (nslots == 2) {  // the aux stream may touch the buffers only after everything queued so far on the main stream
-                CUDA_CHECK(cudaEventRecord(ctx.msm_events[2], s));
-                CUDA_CHECK(cudaStreamWaitEvent(ctx.stream2, ctx.msm_events[2], 0));
+            if (nslots > 1) {  // the aux streams may touch the buffers only after everything queued so far on the main stream
+                CUDA_CHECK(cudaEventRecord(ctx.msm_fork, s));
+                for (int q = 1; q < nslots; ++q) CUDA_CHECK(cudaStreamWaitEvent(ctx.aux_streams[q - 1], ctx.msm_fork, 0));
             }
             const G1Affine* b = bases + (lo - bases_origin);
             for (size_t j = 0; j < (size_t)nslots && j < nc; ++j) msm_issue_count(slots[j], cols[c0 + j] + lo, len, cfg);
@@ -522,9 +522,9 @@ static void msm_batch_core(Context& ctx, const G1Affine* bases, const Fr* const*
                 msm_issue_accumulate(sl, b, cols[c0 + j] + lo, len, cfg, bucket_sums.get() + j * nb);
                 if (j + nslots < nc) msm_issue_count(sl, cols[c0 + j + nslots] + lo, len, cfg);
             }
-            if (nslots == 2) {  // main stream (reduce, frees) continues after the aux stream has drained
-                CUDA_CHECK(cudaEventRecord(ctx.msm_events[3], ctx.stream2));
-                CUDA_CHECK(cudaStreamWaitEvent(s, ctx.msm_events[3], 0));
+            for (int q = 1; q < nslots; ++q) {  // main stream (reduce, frees) continues after the aux streams have drained
+                CUDA_CHECK(cudaEventRecord(ctx.msm_join[q - 1], ctx.aux_streams[q - 1]));
+                CUDA_CHECK(cudaStreamWaitEvent(s, ctx.msm_join[q - 1], 0));
             }
             CUDA_CHECK(cudaStreamSynchronize(s));  // slot buffers are released below: nothing may still be using them
         }

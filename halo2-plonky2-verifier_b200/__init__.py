@@ -48,6 +48,7 @@ def lib():
         _lib.b200zk_launch_count.restype = ctypes.c_ulonglong
         _lib.b200zk_proof_size.restype = ctypes.c_size_t
         _lib.b200zk_synth_max_copies.restype = ctypes.c_size_t
+        _lib.b200zk_srs_file_size.restype = ctypes.c_size_t
     return _lib
 
 
@@ -251,6 +252,20 @@ class Context:
             self._check(lib().b200zk_srs_setup(self._h, ctypes.c_uint32(k), bytes(seed), _p(out)))
         self.srs_k = k
         return out
+
+    def srs_write(self, fmt=0):
+        """ParamsKZG::write bytes (fmt 0 = RawBytes, 1 = Processed)."""
+        size = int(lib().b200zk_srs_file_size(ctypes.c_uint32(self.srs_k), int(fmt)))
+        buf = np.empty(size, dtype=np.uint8)
+        n = ctypes.c_size_t(0)
+        self._check(lib().b200zk_srs_write(self._h, int(fmt), _p(buf), ctypes.c_size_t(size), ctypes.byref(n)))
+        return buf[: n.value].tobytes()
+
+    def srs_read(self, data, fmt=0):
+        """ParamsKZG::read: loads both G1 bases (validated on the device) and keeps the G2 bytes."""
+        buf = np.frombuffer(data, dtype=np.uint8)
+        self._check(lib().b200zk_srs_read(self._h, _p(buf), ctypes.c_size_t(len(buf)), int(fmt)))
+        self.srs_k = int.from_bytes(data[:4], "little")
 
     def srs_download(self):
         n = 1 << self.srs_k

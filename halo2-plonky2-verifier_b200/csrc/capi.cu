@@ -12,6 +12,9 @@ G1Affine msm_run_srs(Context& ctx, int basis, const Fr* scalars, size_t n);
 void msm_batch_srs(Context& ctx, int basis, const Fr* const* cols, size_t ncols, size_t n, G1Affine* out);
 void srs_setup(Context& ctx, uint32_t k, const Fr& s_trapdoor);
 void srs_build_tables(Context& ctx);
+size_t srs_file_size(uint32_t k, int format);
+void srs_read(Context& ctx, const uint8_t* data, size_t len, int format);
+size_t srs_write(Context& ctx, int format, uint8_t* out, size_t cap);
 }
 
 struct b200zk_ctx {
@@ -527,6 +530,19 @@ int b200zk_srs_setup(b200zk_ctx* ctx, uint32_t k, const uint8_t seed[32], b200zk
     const Fr s = rng.next();
     if (trapdoor_out) memcpy(trapdoor_out->l, s.l, 32);
     srs_setup(ctx->c, k, s);
+    API_END(ctx)
+}
+size_t b200zk_srs_file_size(uint32_t k, int format) { return srs_file_size(k, format); }
+int b200zk_srs_read(b200zk_ctx* ctx, const uint8_t* data, size_t len, int format) {
+    API_BEGIN(ctx)
+    if (!data) throw std::invalid_argument("srs_read: null data");
+    srs_read(ctx->c, data, len, format);
+    API_END(ctx)
+}
+int b200zk_srs_write(b200zk_ctx* ctx, int format, uint8_t* out, size_t capacity, size_t* written) {
+    API_BEGIN(ctx)
+    if (!out || !written) throw std::invalid_argument("srs_write: null argument");
+    *written = srs_write(ctx->c, format, out, capacity);
     API_END(ctx)
 }
 int b200zk_srs_download(b200zk_ctx* ctx, b200zk_g1_affine* g, b200zk_g1_affine* g_lagrange) {

@@ -71,6 +71,9 @@ struct Srs {
     // precomputed window tables T[w][i] = 2^(tab_c·w)·P_i (msm.cu, merged-bucket mode); empty when disabled
     DevBuf<G1Affine> g_tab, gl_tab;
     uint32_t tab_c = 0;
+    // the verifier-side G2 points (g2, s·g2) as file bytes: RawBytes (256 B) after setup, or whatever a read file carried
+    std::vector<uint8_t> g2_bytes;
+    int g2_format = 0;
 };
 // all-gather of `bytes` from every rank into recv[world][bytes]; returns 0 on success (host buffers)
 typedef int (*AllGatherFn)(void* user, const void* send, size_t bytes, void* recv);

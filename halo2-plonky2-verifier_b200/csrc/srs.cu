@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(128) fixed_base_kernel(const Fr* scalars, size
 }
 
 void msm_build_table(Context& ctx, const G1Affine* bases, size_t n, uint32_t c, DevBuf<G1Affine>& table);
+void srs_g2_raw(const Fr& s_trapdoor, uint8_t out[256]);
 uint32_t msm_table_window_bits(uint32_t k);
 
 // window tables for both bases of the loaded SRS (msm.cu merged-bucket mode)
@@ -111,6 +112,9 @@ void srs_setup(Context& ctx, uint32_t k, const Fr& s_trapdoor) {
     fixed_base_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(sc.get(), n, table.get(), srs->g_lagrange.get());
     LAUNCHED(2);
     CUDA_CHECK(cudaStreamSynchronize(st));
+    srs->g2_bytes.resize(256);
+    srs->g2_format = 0;
+    srs_g2_raw(s_trapdoor, srs->g2_bytes.data());
     ctx.srs = std::move(srs);
     srs_build_tables(ctx);
 }

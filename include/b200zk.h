@@ -106,6 +106,13 @@ B200ZK_API int b200zk_srs_load(b200zk_ctx* ctx, uint32_t k, const b200zk_g1_affi
  * a production SRS comes from a ceremony through b200zk_srs_load. `trapdoor_out` (optional) receives s. */
 B200ZK_API int b200zk_srs_setup(b200zk_ctx* ctx, uint32_t k, const uint8_t seed[32], b200zk_fr* trapdoor_out);
 B200ZK_API int b200zk_srs_setup_trapdoor(b200zk_ctx* ctx, uint32_t k, const b200zk_fr* s);
+/* ParamsKZG::{write, read} byte layout: k (u32 LE) | n G1 (g) | n G1 (g_lagrange) | G2 g2 | G2 s_g2.
+ * format 0 = SerdeFormat::RawBytes (64-byte G1 / 128-byte G2, raw Montgomery limbs), 1 = Processed (32-byte compressed
+ * G1; the two 64-byte G2 encodings are carried as opaque bytes). read validates every G1 point on the device. write needs
+ * the G2 bytes in the same format (available after srs_setup for RawBytes, or after a read of that format). */
+B200ZK_API size_t b200zk_srs_file_size(uint32_t k, int format);
+B200ZK_API int b200zk_srs_read(b200zk_ctx* ctx, const uint8_t* data, size_t len, int format);
+B200ZK_API int b200zk_srs_write(b200zk_ctx* ctx, int format, uint8_t* out, size_t capacity, size_t* written);
 /* copy the bases back (either may be NULL) */
 B200ZK_API int b200zk_srs_download(b200zk_ctx* ctx, b200zk_g1_affine* g, b200zk_g1_affine* g_lagrange);
 B200ZK_API int b200zk_msm(b200zk_ctx* ctx, int basis, const b200zk_fr* scalars, size_t n, b200zk_g1_affine* out);

@@ -30,7 +30,7 @@ WORKER = textwrap.dedent("""
     want = O.g1_mul(G, O.to_mont(sum(1000 + r for r in range(world))))
     assert np.array_equal(total, want)
     dist.barrier()
-    print("rank", rank, "ok")
+    print("rank-%d-ok" % rank, flush=True)
 """) % (ROOT, ROOT)
 
 
@@ -46,4 +46,4 @@ def test_allgather_and_combine_world2(tmp_path):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=240, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+    assert r.stdout.count("-ok") == 2, r.stdout  # the two ranks' lines may interleave

@@ -30,7 +30,7 @@ WORKER = textwrap.dedent("""
     want = O.g1_mul(G, O.to_mont(sum(1000 + r for r in range(world))))
     assert np.array_equal(total, want)
     dist.barrier()
-    print("rank-%d-ok" % rank, flush=True)
+    print("rank-" + str(rank) + "-ok", flush=True)
 """) % (ROOT, ROOT)
 
 

@@ -42,6 +42,9 @@ def parse():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200")
     p.add_argument("--k", type=int, default=20)
+    p.add_argument("--A", type=int, default=SHAPE["A"], help="gate advice columns (default: S20-bn)")
+    p.add_argument("--L", type=int, default=SHAPE["L"], help="lookup advice columns")
+    p.add_argument("--F", type=int, default=SHAPE["F"], help="constant columns")
     p.add_argument("--sample-k", type=int, default=17, help="k of the bounded CPU sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-extras", action="store_true", help="skip the MSM / NTT side lines")
@@ -50,7 +53,8 @@ def parse():
 
 def workload_name(k):
     A, L, F = SHAPE["A"], SHAPE["L"], SHAPE["F"]
-    return (f"S{k}-bn: halo2-base-shaped FRI-verifier stand-in, k={k}, {A} gate + {L} lookup + {F} constant columns, "
+    name = {(14, 3, 1): "bn", (4, 1, 1): "bn", (23, 6, 1): "gl"}.get((A, L, F), "custom")
+    return (f"S{k}-{name}: halo2-base-shaped FRI-verifier stand-in, k={k}, {A} gate + {L} lookup + {F} constant columns, "
             f"create_proof KZG-BN254 SHPLONK Blake2b, {A + L + 2 * L + (A + L + F + 1) // 2 + L + 6} MSMs of 2^{k}")
 
 
@@ -140,6 +144,7 @@ def run_reference(args, rank):
 
 def main():
     args = parse()
+    SHAPE.update(A=args.A, L=args.L, F=args.F)
     # stdout carries exactly ONE JSON line: anything else that writes to fd 1 (NCCL's version banner, library chatter)
     # is sent to stderr; the JSON goes through the saved descriptor
     sys.stdout.flush()
@@ -257,7 +262,7 @@ def main():
         "metric": "create_proof_s", "value": ms_dev / 1e3, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
         "higher_is_better": False, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "u32 limbs (254-bit Montgomery integers)",
         "data": "synthetic",
-        "config": {"workload": workload_name(k), "l2": "inputs larger than L2 (witness 0.57 GB, ~12 GB of device-resident columns per proof)",
+        "config": {"workload": workload_name(k), "l2": f"inputs larger than L2 (witness {advice_bytes / 1e9:.2f} GB, every stage streams multi-GB device-resident columns)",
                    "parallelism": "1 GPU" if world == 1 else f"one proof on {world} GPUs: MSM point-range shards + NCCL all-gather of partial sums, other stages replicated",
                    "rng": "StdRng::seed_from_u64(0)",
                    "srs": "ParamsKZG::setup(k, ChaCha20Rng::from_seed([0;32])) generated on device"},

@@ -647,3 +647,74 @@ int b200zk_host_selftest(uint64_t seed, size_t iters) {
 }
 
 }  // extern "C"
+
+// ---- column primitives (rows E, F, I) ------------------------------------------------------------------------------------
+extern "C" {
+
+int b200zk_batch_invert(b200zk_ctx* ctx, b200zk_fr* a, size_t n) {
+    API_BEGIN(ctx)
+    if (n && !a) throw std::invalid_argument("batch_invert: null argument");
+    cudaStream_t s = ctx->c.stream;
+    DevBuf<Fr> d(n, s);
+    if (n) {
+        CUDA_CHECK(cudaMemcpyAsync(d.get(), a, 32 * n, cudaMemcpyHostToDevice, s));
+        fr_batch_invert(d.get(), n, s);
+        CUDA_CHECK(cudaMemcpyAsync(a, d.get(), 32 * n, cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+    API_END(ctx)
+}
+int b200zk_prefix_product(b200zk_ctx* ctx, const b200zk_fr* m, const b200zk_fr* first, b200zk_fr* z, size_t n) {
+    API_BEGIN(ctx)
+    if (!first || (n && (!m || !z))) throw std::invalid_argument("prefix_product: null argument");
+    cudaStream_t s = ctx->c.stream;
+    DevBuf<Fr> dm(n, s), dz(n, s);
+    if (n) {
+        CUDA_CHECK(cudaMemcpyAsync(dm.get(), m, 32 * n, cudaMemcpyHostToDevice, s));
+        fr_prefix_product(dz.get(), dm.get(), load_fr(first), n, s);
+        CUDA_CHECK(cudaMemcpyAsync(z, dz.get(), 32 * n, cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+    API_END(ctx)
+}
+int b200zk_eval_polynomial(b200zk_ctx* ctx, const b200zk_fr* poly, size_t n, const b200zk_fr* point, b200zk_fr* out) {
+    API_BEGIN(ctx)
+    if (!point || !out || (n && !poly)) throw std::invalid_argument("eval_polynomial: null argument");
+    cudaStream_t s = ctx->c.stream;
+    Fr r = f_zero<FrCfg>();
+    if (n) {
+        DevBuf<Fr> d(n, s);
+        CUDA_CHECK(cudaMemcpyAsync(d.get(), poly, 32 * n, cudaMemcpyHostToDevice, s));
+        std::vector<const Fr*> ps = {d.get()};
+        fr_eval_many(ctx->c, ps, n, load_fr(point), &r);
+    }
+    memcpy(out->l, r.l, 32);
+    API_END(ctx)
+}
+int b200zk_kate_division(b200zk_ctx* ctx, const b200zk_fr* a, size_t n, const b200zk_fr* b, b200zk_fr* q) {
+    API_BEGIN(ctx)
+    if (!a || !b || !q || n < 2) throw std::invalid_argument("kate_division: bad arguments");
+    cudaStream_t s = ctx->c.stream;
+    DevBuf<Fr> da(n, s), dq(n, s);
+    CUDA_CHECK(cudaMemcpyAsync(da.get(), a, 32 * n, cudaMemcpyHostToDevice, s));
+    fr_kate_division(ctx->c, da.get(), dq.get(), n, load_fr(b));
+    CUDA_CHECK(cudaMemcpyAsync(q, dq.get(), 32 * (n - 1), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    API_END(ctx)
+}
+int b200zk_permute_expression_pair(b200zk_ctx* ctx, uint32_t k, const b200zk_fr* input, const b200zk_fr* table, b200zk_fr* a_out, b200zk_fr* s_out) {
+    API_BEGIN(ctx)
+    if (!input || !table || !a_out || !s_out || k < 4 || k > 26) throw std::invalid_argument("permute_expression_pair: bad arguments");
+    cudaStream_t s = ctx->c.stream;
+    const size_t n = (size_t)1 << k, u = n - (Shape::blinding_factors + 1);
+    DevBuf<Fr> din(n, s), dtab(n, s), da(n, s), ds(n, s);
+    CUDA_CHECK(cudaMemcpyAsync(din.get(), input, 32 * n, cudaMemcpyHostToDevice, s));
+    CUDA_CHECK(cudaMemcpyAsync(dtab.get(), table, 32 * n, cudaMemcpyHostToDevice, s));
+    if (!lookup_permute(ctx->c, din.get(), dtab.get(), da.get(), ds.get(), n, u)) throw SynthesisError("ConstraintSystemFailure: lookup input not in table");
+    CUDA_CHECK(cudaMemcpyAsync(a_out, da.get(), 32 * u, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaMemcpyAsync(s_out, ds.get(), 32 * u, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    API_END(ctx)
+}
+
+}  // extern "C"

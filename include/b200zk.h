@@ -126,6 +126,21 @@ B200ZK_API int b200zk_msm_bases(b200zk_ctx* ctx, const b200zk_g1_affine* bases, 
 B200ZK_API int b200zk_msm_bases_dev(b200zk_ctx* ctx, const b200zk_g1_affine* bases_dev, const b200zk_fr* scalars_dev, size_t n,
                                     b200zk_g1_affine* out);
 
+/* ---- rows E, F, I: column primitives used inside create_proof, exported for hosts that keep their own prover loop ------
+ * (host buffers; each call stages through device memory)
+ * batch_invert      : halo2 `batch_invert` — a[i] <- a[i]^-1, zeros stay zero.
+ * prefix_product    : z[0] = first, z[i] = z[i-1]·m[i-1] (the running product of permutation::prover / lookup::prover).
+ * eval_polynomial   : arithmetic::eval_polynomial(poly, point).
+ * kate_division     : arithmetic::kate_division(a, b): quotient of a(X) by (X - b), n-1 coefficients.
+ * permute_expression_pair : lookup::prover::permute_expression_pair on the first n-7 rows (values must be < n);
+ *                     returns B200ZK_ESYNTH when an input is missing from the table. Outputs n-7 rows each. */
+B200ZK_API int b200zk_batch_invert(b200zk_ctx* ctx, b200zk_fr* a, size_t n);
+B200ZK_API int b200zk_prefix_product(b200zk_ctx* ctx, const b200zk_fr* m, const b200zk_fr* first, b200zk_fr* z, size_t n);
+B200ZK_API int b200zk_eval_polynomial(b200zk_ctx* ctx, const b200zk_fr* poly, size_t n, const b200zk_fr* point, b200zk_fr* out);
+B200ZK_API int b200zk_kate_division(b200zk_ctx* ctx, const b200zk_fr* a, size_t n, const b200zk_fr* b, b200zk_fr* q);
+B200ZK_API int b200zk_permute_expression_pair(b200zk_ctx* ctx, uint32_t k, const b200zk_fr* input, const b200zk_fr* table, b200zk_fr* a_out,
+                                              b200zk_fr* s_out);
+
 /* ---- rows J, E–I: plonk::{keygen_vk, keygen_pk, create_proof} for the halo2-base ConstraintSystem -----------------
  * Shape: A gate advice columns (one `q·(a + b·c − d)` gate each, rotations 0..3), L lookup
  * advice columns against one table column, F constant columns. Fixed column order: F constants, table, A selectors.

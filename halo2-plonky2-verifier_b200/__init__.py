@@ -307,6 +307,42 @@ class Context:
         self._check(lib().b200zk_msm_bases_dev(self._h, ctypes.c_void_p(bases_ptr), ctypes.c_void_p(scalars_ptr), ctypes.c_size_t(n), _p(out)))
         return out
 
+    # ---- rows E, F, I: column primitives ----
+    def batch_invert(self, a):
+        a = _c(a).reshape(-1, 4).copy()
+        self._check(lib().b200zk_batch_invert(self._h, _p(a), ctypes.c_size_t(len(a))))
+        return a
+
+    def prefix_product(self, m, first):
+        m = _c(m).reshape(-1, 4)
+        first = _c(first)
+        z = np.empty_like(m)
+        self._check(lib().b200zk_prefix_product(self._h, _p(m), _p(first), _p(z), ctypes.c_size_t(len(m))))
+        return z
+
+    def eval_polynomial(self, poly, point):
+        poly = _c(poly).reshape(-1, 4)
+        point = _c(point)
+        out = np.empty(4, dtype=np.uint64)
+        self._check(lib().b200zk_eval_polynomial(self._h, _p(poly), ctypes.c_size_t(len(poly)), _p(point), _p(out)))
+        return out
+
+    def kate_division(self, a, b):
+        a = _c(a).reshape(-1, 4)
+        b = _c(b)
+        q = np.empty((len(a) - 1, 4), dtype=np.uint64)
+        self._check(lib().b200zk_kate_division(self._h, _p(a), ctypes.c_size_t(len(a)), _p(b), _p(q)))
+        return q
+
+    def permute_expression_pair(self, k, inp, table):
+        inp = _c(inp).reshape(-1, 4)
+        table = _c(table).reshape(-1, 4)
+        u = (1 << k) - 7
+        a = np.empty((u, 4), dtype=np.uint64)
+        s = np.empty((u, 4), dtype=np.uint64)
+        self._check(lib().b200zk_permute_expression_pair(self._h, ctypes.c_uint32(k), _p(inp), _p(table), _p(a), _p(s)))
+        return a, s
+
     # ---- rows J, E-I: keygen + create_proof ----
     def keygen(self, k, A, L, F, fixed, copies):
         """plonk::keygen_vk + keygen_pk for the halo2-base shape; returns a device-resident ProvingKey."""

@@ -275,6 +275,23 @@ static Fr vanishing_eval(const std::vector<Fr>& roots, const Fr& z) {
     return r;
 }
 
+// evaluations of many polynomials at one point; when sharded, rank r evaluates polynomials r, r+world, ... (every rank
+// holds all coefficient forms) and the 32-byte results are all-gathered through the host callback
+static void eval_many_dist(Context& ctx, Sharder& shard, const std::vector<const Fr*>& polys, size_t n, const Fr& point, Fr* out) {
+    const size_t m = polys.size(), world = ctx.world;
+    if (!shard.on() || m < 2 * world) {
+        fr_eval_many(ctx, polys, n, point, out);
+        return;
+    }
+    const size_t per = (m + world - 1) / world;
+    std::vector<const Fr*> mine;
+    for (size_t i = ctx.rank; i < m; i += world) mine.push_back(polys[i]);
+    std::vector<Fr> send(per, f_zero<FrCfg>()), recv(per * world);
+    fr_eval_many(ctx, mine, n, point, send.data());
+    if (ctx.allgather(ctx.allgather_user, send.data(), per * sizeof(Fr), recv.data()) != 0) throw std::runtime_error("evaluation all-gather failed");
+    for (size_t i = 0; i < m; ++i) out[i] = recv[(i % world) * per + i / world];
+}
+
 // ---- create_proof ---------------------------------------------------------------------------------------------------------
 // rotation reach of the h(X) kernels in extended rows: -4·(blinding_factors+1) = -28 (z of the previous set) ... +12 (gate rotation 3)
 static constexpr size_t HALO_BEFORE = 32, HALO_AFTER = 16;
@@ -376,23 +393,53 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
     DevBuf<Fr> z_polys((size_t)NS * n, s), z_cosets((size_t)NS * en, s);
     {
         DevBuf<Fr> m(n, s);
-        Fr delta_pow = one, last_z = one;
+        std::vector<Fr> dpow(P);  // delta^j·beta for permutation column j
+        dpow[0] = beta;
+        for (uint32_t j = 1; j < P; ++j) dpow[j] = f_mul(dpow[j - 1], FrConsts::delta());
+        // Sharded: set s is built by rank s mod world (the rank that also commits and transforms it). The chain
+        // z_s[0] = z_{s-1}[n-bf-1] only couples the sets through one scalar, so every owner first builds its running product
+        // from 1, the end values E_s are exchanged, and each owner rescales by the carry prod_{t<s} E_t.
+        const bool dist_sets = shard.on() && NS >= (uint32_t)ctx.world;
+        std::vector<Fr> E(NS, f_zero<FrCfg>());
+        Fr last_z = one;
         for (uint32_t set = 0; set < NS; ++set) {
             Fr* z = z_polys.get() + (size_t)set * n;  // Lagrange values first, converted in place after the commit
             const uint32_t j0 = set * Shape::chunk_len, j1 = std::min(P, j0 + Shape::chunk_len);
-            for (uint32_t j = j0; j < j1; ++j) perm_denominator(m.get(), perm_values(j), pk.sigma_values.get() + (size_t)j * n, beta, gamma, n, j == j0, s);
-            fr_batch_invert(m.get(), n, s);
-            for (uint32_t j = j0; j < j1; ++j) {
-                perm_numerator(m.get(), perm_values(j), f_mul(delta_pow, beta), gamma, tw.t.get(), tw.log_n, sh.k, s);
-                delta_pow = f_mul(delta_pow, FrConsts::delta());
+            if (!dist_sets || shard.mine(set)) {
+                for (uint32_t j = j0; j < j1; ++j) perm_denominator(m.get(), perm_values(j), pk.sigma_values.get() + (size_t)j * n, beta, gamma, n, j == j0, s);
+                fr_batch_invert(m.get(), n, s);
+                for (uint32_t j = j0; j < j1; ++j) perm_numerator(m.get(), perm_values(j), dpow[j], gamma, tw.t.get(), tw.log_n, sh.k, s);
+                fr_prefix_product(z, m.get(), dist_sets ? one : last_z, n, s);
             }
-            fr_prefix_product(z, m.get(), last_z, n, s);
-            std::vector<Fr> blind(bf);
-            for (auto& b : blind) b = rng.next();
-            CUDA_CHECK(cudaMemcpyAsync(z + (n - bf), blind.data(), bf * sizeof(Fr), cudaMemcpyHostToDevice, s));
-            CUDA_CHECK(cudaMemcpyAsync(&last_z, z + (n - bf - 1), sizeof(Fr), cudaMemcpyDeviceToHost, s));
+            if (!dist_sets) {
+                std::vector<Fr> blind(bf);
+                for (auto& b : blind) b = rng.next();
+                CUDA_CHECK(cudaMemcpyAsync(z + (n - bf), blind.data(), bf * sizeof(Fr), cudaMemcpyHostToDevice, s));
+                CUDA_CHECK(cudaMemcpyAsync(&last_z, z + (n - bf - 1), sizeof(Fr), cudaMemcpyDeviceToHost, s));
+                CUDA_CHECK(cudaStreamSynchronize(s));
+                rng.skip(1);
+            } else if (shard.mine(set)) {
+                CUDA_CHECK(cudaMemcpyAsync(&E[set], z + (n - bf - 1), sizeof(Fr), cudaMemcpyDeviceToHost, s));
+            }
+        }
+        if (dist_sets) {
             CUDA_CHECK(cudaStreamSynchronize(s));
-            rng.skip(1);
+            std::vector<Fr> all((size_t)NS * ctx.world);
+            if (ctx.allgather(ctx.allgather_user, E.data(), NS * sizeof(Fr), all.data()) != 0) throw std::runtime_error("grand-product exchange failed");
+            for (uint32_t set = 0; set < NS; ++set) E[set] = all[(size_t)shard.owner(set) * NS + set];
+            Fr carry = one;
+            for (uint32_t set = 0; set < NS; ++set) {
+                Fr* z = z_polys.get() + (size_t)set * n;
+                std::vector<Fr> blind(bf);
+                for (auto& b : blind) b = rng.next();  // every rank draws every value: the streams stay in step
+                rng.skip(1);
+                if (shard.mine(set)) {
+                    if (set > 0) fr_scale(z, carry, n, s);
+                    CUDA_CHECK(cudaMemcpyAsync(z + (n - bf), blind.data(), bf * sizeof(Fr), cudaMemcpyHostToDevice, s));
+                    CUDA_CHECK(cudaStreamSynchronize(s));
+                }
+                carry = f_mul(carry, E[set]);
+            }
         }
         lap(tm ? &tm->products : nullptr);
         const std::vector<G1Affine> cms = commit_batch(ctx, 1, z_polys.get(), n, NS, n);
@@ -420,18 +467,22 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
     DevBuf<Fr> lk_z_poly((size_t)L * n, s);
     {
         DevBuf<Fr> p(n, s);
-        for (uint32_t l = 0; l < L; ++l) {
+        for (uint32_t l = 0; l < L; ++l) {  // sharded: lookup l is built by rank l mod world and broadcast
             Fr* z = lk_z_poly.get() + (size_t)l * n;
+            std::vector<Fr> blind(bf);
+            for (auto& b : blind) b = rng.next();
+            rng.skip(1);
+            if (!shard.mine(l)) continue;
             lookup_denominator(p.get(), perm_in.get() + (size_t)l * n, perm_tab.get() + (size_t)l * n, beta, gamma, n, s);
             fr_batch_invert(p.get(), n, s);
             lookup_numerator(p.get(), advice.get() + (size_t)(A + l) * n, table_values, beta, gamma, n, s);
             fr_prefix_product(z, p.get(), one, n, s);
-            std::vector<Fr> blind(bf);
-            for (auto& b : blind) b = rng.next();
             CUDA_CHECK(cudaMemcpyAsync(z + (n - bf), blind.data(), bf * sizeof(Fr), cudaMemcpyHostToDevice, s));
             CUDA_CHECK(cudaStreamSynchronize(s));
-            rng.skip(1);
         }
+        shard.group_start();
+        for (uint32_t l = 0; l < L; ++l) shard.broadcast(lk_z_poly.get() + (size_t)l * n, n, shard.owner(l));
+        shard.group_end();
         lap(tm ? &tm->products : nullptr);
         const std::vector<G1Affine> cms = commit_batch(ctx, 1, lk_z_poly.get(), n, L, n);
         lap(tm ? &tm->msm : nullptr);
@@ -548,7 +599,7 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
     // evaluate everything grouped by point
     std::vector<Fr> ev_x(polys.size()), ev_next(polys.size()), ev_r2(A), ev_r3(A), ev_prev(L), ev_last(NS);
     {
-        fr_eval_many(ctx, polys, n, x, ev_x.data());
+        eval_many_dist(ctx, shard, polys, n, x, ev_x.data());
         std::vector<const Fr*> list;
         std::vector<Fr> out;
         // x_next: gate advice columns, permutation z, lookup z
@@ -556,20 +607,20 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
         for (uint32_t set = 0; set < NS; ++set) list.push_back(polys[id_z[set]]);
         for (uint32_t l = 0; l < L; ++l) list.push_back(polys[id_lz[l]]);
         out.resize(list.size());
-        fr_eval_many(ctx, list, n, x_next, out.data());
+        eval_many_dist(ctx, shard, list, n, x_next, out.data());
         for (uint32_t c = 0; c < A; ++c) ev_next[id_adv[c]] = out[c];
         for (uint32_t set = 0; set < NS; ++set) ev_next[id_z[set]] = out[A + set];
         for (uint32_t l = 0; l < L; ++l) ev_next[id_lz[l]] = out[A + NS + l];
         list.clear();
         for (uint32_t c = 0; c < A; ++c) list.push_back(polys[id_adv[c]]);
-        fr_eval_many(ctx, list, n, x_rot2, ev_r2.data());
-        fr_eval_many(ctx, list, n, x_rot3, ev_r3.data());
+        eval_many_dist(ctx, shard, list, n, x_rot2, ev_r2.data());
+        eval_many_dist(ctx, shard, list, n, x_rot3, ev_r3.data());
         list.clear();
         for (uint32_t l = 0; l < L; ++l) list.push_back(polys[id_la[l]]);
-        fr_eval_many(ctx, list, n, x_prev, ev_prev.data());
+        eval_many_dist(ctx, shard, list, n, x_prev, ev_prev.data());
         list.clear();
         for (uint32_t set = 0; set + 1 < NS; ++set) list.push_back(polys[id_z[set]]);
-        fr_eval_many(ctx, list, n, x_last, ev_last.data());
+        eval_many_dist(ctx, shard, list, n, x_last, ev_last.data());
     }
     std::vector<Query> q_advice, q_perm, q_lookup, q_fixed, q_sigma, q_vanish, queries;
     for (uint32_t c = 0; c < NA; ++c) {

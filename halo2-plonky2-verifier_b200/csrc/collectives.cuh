@@ -88,6 +88,20 @@ struct Sharder {
         if (!on()) return;
         nccl().check(nccl().Broadcast(buf, buf, count * sizeof(Fr), /*ncclUint8*/ 1, root, nccl().comm, ctx.stream), "Broadcast");
     }
+    // Columns base[c·len .. (c+1)·len), c < ncols, each complete on rank c mod world only: afterwards complete everywhere.
+    // One all-gather over an owner-major staging buffer instead of ncols broadcasts (NVSwitch all-gather bandwidth, one
+    // launch): stage[r][j] = column r + j·world.
+    void allgather_columns(Fr* base, size_t ncols, size_t len) {
+        if (!on() || ncols == 0) return;
+        const size_t world = ctx.world, per = (ncols + world - 1) / world;
+        DevBuf<Fr> stage(world * per * len, ctx.stream);
+        for (size_t c = ctx.rank; c < ncols; c += world)
+            CUDA_CHECK(cudaMemcpyAsync(stage.get() + ((size_t)ctx.rank * per + c / world) * len, base + c * len, len * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx.stream));
+        all_gather_inplace(stage.get(), per * len);
+        for (size_t c = 0; c < ncols; ++c)
+            if (c % world != (size_t)ctx.rank)
+                CUDA_CHECK(cudaMemcpyAsync(base + c * len, stage.get() + ((c % world) * per + c / world) * len, len * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx.stream));
+    }
     // Row-slice exchange for the h(X) stage: column c (length en, complete on owner(c) only) is needed by rank d only on
     // the extended rows d evaluates plus the rotation halo — rows [d·R − before, (d+1)·R + after) mod en, R = en / world.
     // Owners send exactly those rows (1/world of the column per peer instead of a full broadcast); receivers keep

@@ -330,9 +330,7 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
         for (uint32_t c = 0; c < NA; ++c)
             if (shard.mine(c))
                 CUDA_CHECK(cudaMemcpyAsync(advice.get() + (size_t)c * n, advice_in + (size_t)c * n, n * sizeof(Fr), cudaMemcpyHostToDevice, s));
-        shard.group_start();
-        for (uint32_t c = 0; c < NA; ++c) shard.broadcast(advice.get() + (size_t)c * n, n, shard.owner(c));
-        shard.group_end();
+        shard.allgather_columns(advice.get(), NA, n);
     } else {
         CUDA_CHECK(cudaMemcpyAsync(advice.get(), advice_in, (size_t)NA * n * sizeof(Fr), advice_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
     }
@@ -355,18 +353,29 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
     DevBuf<Fr> perm_in((size_t)L * n, s), perm_tab((size_t)L * n, s), perm_in_poly((size_t)L * n, s), perm_tab_poly((size_t)L * n, s);
     // perm_cols holds a'_0, s'_0, a'_1, s'_1, ... so that one batch commits them in transcript order
     DevBuf<Fr> perm_cols((size_t)2 * L * n, s);
-    for (uint32_t l = 0; l < L; ++l) {
+    uint32_t lookup_failed = 0;
+    for (uint32_t l = 0; l < L; ++l) {  // sharded: lookup l is permuted by rank l mod world
         Fr* a_out = perm_cols.get() + (size_t)(2 * l) * n;
         Fr* s_out = perm_cols.get() + (size_t)(2 * l + 1) * n;
-        if (!lookup_permute(ctx, advice.get() + (size_t)(A + l) * n, table_values, a_out, s_out, n, u))
-            throw SynthesisError("ConstraintSystemFailure: lookup input not in table");
         std::vector<Fr> blind(2 * (bf + 1));
         for (auto& b : blind) b = rng.next();
+        rng.skip(2);  // the two Blind(..) draws of commit_values
+        if (!shard.mine(l)) continue;
+        if (!lookup_permute(ctx, advice.get() + (size_t)(A + l) * n, table_values, a_out, s_out, n, u)) {
+            lookup_failed = 1;
+            continue;
+        }
         CUDA_CHECK(cudaMemcpyAsync(a_out + u, blind.data(), (bf + 1) * sizeof(Fr), cudaMemcpyHostToDevice, s));
         CUDA_CHECK(cudaMemcpyAsync(s_out + u, blind.data() + bf + 1, (bf + 1) * sizeof(Fr), cudaMemcpyHostToDevice, s));
         CUDA_CHECK(cudaStreamSynchronize(s));
-        rng.skip(2);  // the two Blind(..) draws of commit_values
     }
+    if (shard.on() && L) {  // a failure seen by one rank must stop every rank before the next collective
+        std::vector<uint32_t> all(ctx.world);
+        if (ctx.allgather(ctx.allgather_user, &lookup_failed, sizeof(uint32_t), all.data()) != 0) throw std::runtime_error("lookup status exchange failed");
+        for (uint32_t f : all) lookup_failed |= f;
+    }
+    if (lookup_failed) throw SynthesisError("ConstraintSystemFailure: lookup input not in table");
+    shard.allgather_columns(perm_cols.get(), L, 2 * n);  // column l = a'_l followed by s'_l
     lap(tm ? &tm->lookup : nullptr);
     {
         const std::vector<G1Affine> cms = commit_batch(ctx, 1, perm_cols.get(), n, 2 * L, n);
@@ -453,9 +462,7 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
                     dev_lagrange_to_coeff(ctx, sh.k, z_polys.get() + (size_t)set * n);
                     dev_coeff_to_extended(ctx, sh.k, z_polys.get() + (size_t)set * n, z_cosets.get() + (size_t)set * en);
                 }
-            shard.group_start();
-            for (uint32_t set = 0; set < NS; ++set) shard.broadcast(z_polys.get() + (size_t)set * n, n, shard.owner(set));
-            shard.group_end();
+            shard.allgather_columns(z_polys.get(), NS, n);
             std::vector<Fr*> cs(NS);
             for (uint32_t set = 0; set < NS; ++set) cs[set] = z_cosets.get() + (size_t)set * en;
             shard.exchange_row_slices(cs.data(), NS, [&](size_t c) { return shard.owner(c); }, en, HALO_BEFORE, HALO_AFTER);
@@ -480,9 +487,7 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
             CUDA_CHECK(cudaMemcpyAsync(z + (n - bf), blind.data(), bf * sizeof(Fr), cudaMemcpyHostToDevice, s));
             CUDA_CHECK(cudaStreamSynchronize(s));
         }
-        shard.group_start();
-        for (uint32_t l = 0; l < L; ++l) shard.broadcast(lk_z_poly.get() + (size_t)l * n, n, shard.owner(l));
-        shard.group_end();
+        shard.allgather_columns(lk_z_poly.get(), L, n);
         lap(tm ? &tm->products : nullptr);
         const std::vector<G1Affine> cms = commit_batch(ctx, 1, lk_z_poly.get(), n, L, n);
         lap(tm ? &tm->msm : nullptr);
@@ -511,9 +516,7 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
                 dev_lagrange_to_coeff(ctx, sh.k, advice_polys.get() + (size_t)c * n);
                 dev_coeff_to_extended(ctx, sh.k, advice_polys.get() + (size_t)c * n, advice_cosets.get() + (size_t)c * en);
             }
-        shard.group_start();
-        for (uint32_t c = 0; c < NA; ++c) shard.broadcast(advice_polys.get() + (size_t)c * n, n, shard.owner(c));
-        shard.group_end();
+        shard.allgather_columns(advice_polys.get(), NA, n);
         std::vector<Fr*> cs(NA);
         for (uint32_t c = 0; c < NA; ++c) cs[c] = advice_cosets.get() + (size_t)c * en;
         shard.exchange_row_slices(cs.data(), NA, [&](size_t c) { return shard.owner(c); }, en, HALO_BEFORE, HALO_AFTER);

@@ -200,8 +200,6 @@ struct NttPlan {
     const Fr* post_scale3 = nullptr;  // 3 factors applied to output element i by (i mod 3) (divisor folded in)
     size_t out_len = 0;               // outputs at index >= out_len are not stored (0 = full)
 };
-// out may alias in. scratch must hold 2^log_n elements when the plan needs more than one pass.
-void ntt_run(const NttPlan& plan, const Fr* in, Fr* out, Fr* scratch, cudaStream_t stream);
 void build_twiddle_table(Fr* table, const Fr& omega, uint32_t log_n, cudaStream_t stream);
 int ntt_num_passes(uint32_t log_n);
 extern unsigned long long g_launch_count;  // kernels launched by this library (bench "gpu_launches")

@@ -157,6 +157,7 @@ struct Context {
     }
 };
 
+// `batch` transforms of one plan; out may alias in; scratch must hold batch·2^log_n elements when more than one pass is needed
 void ntt_run_batch(const NttPlan& plan, const Fr* in, Fr* out, Fr* scratch, uint32_t batch, size_t stride_in, size_t stride_out,
                    size_t stride_scratch, cudaStream_t stream);
 
@@ -174,12 +175,6 @@ inline void dev_lagrange_to_coeff(Context& ctx, uint32_t k, Fr* a, uint32_t batc
     const Domain& d = ctx.domain(k);
     NttPlan p = make_plan(ctx, k, true);
     p.post_scale3 = d.post_l2c();
-    Fr* scratch = ntt_num_passes(k) > 1 ? ctx.get_scratch(d.n * batch) : nullptr;
-    ntt_run_batch(p, a, a, scratch, batch, stride, stride, d.n, ctx.stream);
-}
-inline void dev_coeff_to_lagrange(Context& ctx, uint32_t k, Fr* a, uint32_t batch = 1, size_t stride = 0) {
-    const Domain& d = ctx.domain(k);
-    NttPlan p = make_plan(ctx, k, false);
     Fr* scratch = ntt_num_passes(k) > 1 ? ctx.get_scratch(d.n * batch) : nullptr;
     ntt_run_batch(p, a, a, scratch, batch, stride, stride, d.n, ctx.stream);
 }

@@ -2,20 +2,24 @@
 // ParamsKZG::{commit, commit_lagrange} from create_proof — reference entry verifier/src/stark/mod.rs:543,593).
 //
 // Only the group element Σ sᵢ·Pᵢ matters (canonical affine at the boundary), so the decomposition is free:
+//   0. tables   : for the SRS bases T[w][i] = 2^(c·w)·P_i is built once (c = 20: 13 windows), so every window of a column
+//                 lands in ONE set of 2^(c-1) buckets and no doubling chain is left; caller-supplied bases keep one bucket
+//                 set per window and a short host-side fold.
 //   1. digits   : scalars leave Montgomery form; each is cut into W signed c-bit digits dₗ ∈ [-2^(c-1), 2^(c-1)];
 //                 zero digits create no work (advice-like scalars are mostly < 2^84, lookup columns < 2^(k-1)).
-//   2. sort     : counting sort of (window, |digit|) → bucket: histogram with atomics, exclusive scan, scatter.
-//                 Order inside a bucket is irrelevant to the group sum, so the result stays deterministic.
+//   2. sort     : counting sort by bucket: histogram with atomics, exclusive scan, scatter. Order inside a bucket is
+//                 irrelevant to the group sum, so the result stays deterministic.
 //   3. accumulate: the sorted entry list is cut into equal chunks of T entries, one thread each (perfect balance
 //                 whatever the bucket histogram: hot buckets simply span many chunks). A thread walks its chunk
 //                 with one XYZZ accumulator and mixed additions (8M+2S); runs that begin inside the chunk are
 //                 stored to their bucket, the run that began earlier goes to a "head" list, which is itself
 //                 segment-summed by the same scheme with chunk T2 until one thread covers it.
-//   4. reduce   : per window Σ b·B_b via running sums over chunks of m buckets plus a small double-and-add for the
-//                 chunk offset, then a block tree sum per window.
-//   5. fold     : Σ 2^(c·w)·S_w over W window sums — 254 dependent doublings, done on the host in 64-bit limbs
-//                 (≈0.1 ms) because a single GPU thread would take longer than the whole MSM.
-// Bound: integer pipe (≈10 Fq products per point·window), not HBM; see DESIGN.md.
+//   4. reduce   : Σ b·B_b via recursive chunked running sums (2 additions per bucket, Horner in the chunk size), done
+//                 ONCE for all columns of a commit batch — its deep levels are latency bound.
+// Up to four columns of a batch are in flight on separate streams so that the latency-bound phases of one column
+// (atomics, scans, the entry-count read-back, short combine levels) hide under another column's accumulate.
+// Multi-GPU: batches are dealt by column, small batches split by point range (see msm_batch_srs).
+// Bound: the FMA-heavy (IMAD) pipe — 80 % busy in msm_accumulate_kernel (profiles/ncu_summary_r01.md) — not HBM.
 #include <algorithm>
 #include <chrono>
 

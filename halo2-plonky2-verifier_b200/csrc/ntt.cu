@@ -218,10 +218,6 @@ void ntt_run_batch(const NttPlan& plan, const Fr* in, Fr* out, Fr* scratch, uint
     }
 }
 
-void ntt_run(const NttPlan& plan, const Fr* in, Fr* out, Fr* scratch, cudaStream_t stream) {
-    ntt_run_batch(plan, in, out, scratch, 1, 0, 0, 0, stream);
-}
-
 // ---- twiddle table: T[i] = w^i, i < 2^(log_n-1), from two small power tables -----------------------------
 __global__ void twiddle_small_kernel(Fr* lo, Fr* hi, Fr omega, uint32_t lo_bits, uint32_t count_hi) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

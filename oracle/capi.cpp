@@ -336,3 +336,38 @@ EXPORT int oracle_permute_expression_pair(uint32_t k, const u64* input, const u6
     memcpy(s_out, s.data(), 32 * s.size());
     return 1;
 }
+
+// ---- verifier-only handles: check a proof against externally produced vk commitments (no oracle keygen needed) -------
+// params: trapdoor only (the verifier here never touches the G1 bases); vk: shape + commitments + transcript_repr.
+EXPORT void* oracle_verifier_new(uint32_t k, uint32_t A, uint32_t L, uint32_t F, const u64* trapdoor, const u64* fixed_commitments,
+                                 const u64* perm_commitments, const u64* transcript_repr) {
+    struct Bundle {
+        Params params;
+        VerifyingKey vk;
+    };
+    Bundle* b = new Bundle;
+    b->params.k = k;
+    b->params.n = (size_t)1 << k;
+    memcpy(b->params.s.l, trapdoor, 32);
+    b->vk.shape = Shape{k, A, L, F};
+    b->vk.fixed_commitments.assign((const G1Affine*)fixed_commitments, (const G1Affine*)fixed_commitments + b->vk.shape.num_fixed());
+    b->vk.perm_commitments.assign((const G1Affine*)perm_commitments, (const G1Affine*)perm_commitments + b->vk.shape.num_perm());
+    memcpy(b->vk.transcript_repr.l, transcript_repr, 32);
+    return b;
+}
+EXPORT int oracle_verifier_verify(void* h, const uint8_t* proof, size_t len) {
+    struct Bundle {
+        Params params;
+        VerifyingKey vk;
+    };
+    Bundle* b = (Bundle*)h;
+    g_err = verify_proof(b->params, b->vk, proof, len);
+    return g_err.empty();
+}
+EXPORT void oracle_verifier_free(void* h) {
+    struct Bundle {
+        Params params;
+        VerifyingKey vk;
+    };
+    delete (Bundle*)h;
+}

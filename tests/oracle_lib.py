@@ -34,7 +34,7 @@ def lib():
         build_oracle()
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.oracle_last_error.restype = ctypes.c_char_p
-        for name in ("oracle_params_setup", "oracle_params_from_trapdoor", "oracle_params_load", "oracle_keygen"):
+        for name in ("oracle_params_setup", "oracle_params_from_trapdoor", "oracle_params_load", "oracle_keygen", "oracle_verifier_new"):
             getattr(_lib, name).restype = ctypes.c_void_p
         for name in ("oracle_create_proof", "oracle_proof_size", "oracle_transcript_script"):
             getattr(_lib, name).restype = ctypes.c_size_t
@@ -285,3 +285,29 @@ def mock_check(k, A, L, F, fixed, advice, copies):
     copies = np.ascontiguousarray(copies, dtype=np.uint32).reshape(-1, 4)
     ok = lib().oracle_mock_check(k, A, L, F, ptr(fixed), ptr(advice), ptr(copies), ctypes.c_size_t(len(copies)))
     return bool(ok), last_error()
+
+
+class Verifier:
+    """Oracle verifier over externally produced vk commitments (e.g. the GPU keygen's): verifies proofs at sizes where the
+    oracle's own keygen would take minutes. Needs the SRS trapdoor (openings are checked in G1 instead of by a pairing)."""
+
+    def __init__(self, k, A, L, F, trapdoor, fixed_commitments, perm_commitments, transcript_repr):
+        t = np.ascontiguousarray(trapdoor, dtype=np.uint64)
+        fc = np.ascontiguousarray(fixed_commitments, dtype=np.uint64)
+        pc = np.ascontiguousarray(perm_commitments, dtype=np.uint64)
+        tr = np.ascontiguousarray(transcript_repr, dtype=np.uint64)
+        assert fc.shape == (F + 1 + A, 8) and pc.shape == (F + A + L, 8)
+        self.h = lib().oracle_verifier_new(k, A, L, F, ptr(t), ptr(fc), ptr(pc), ptr(tr))
+
+    def verify(self, proof):
+        buf = np.frombuffer(proof, dtype=np.uint8)
+        ok = lib().oracle_verifier_verify(ctypes.c_void_p(self.h), ptr(buf), ctypes.c_size_t(len(buf)))
+        return bool(ok), last_error()
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                lib().oracle_verifier_free(ctypes.c_void_p(self.h))
+                self.h = None
+        except Exception:
+            pass

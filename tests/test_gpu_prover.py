@@ -119,3 +119,26 @@ def test_gpu_reproduces_golden_proofs(ctx):
         assert hashlib.sha256(dg.tobytes() + dgl.tobytes()).hexdigest() == case["srs_sha256"]
         pk = ctx.keygen(k, A, L, F, fixed, copies)
         assert pk.create_proof(advice, case["rng_seed"]).hex() == case["proof_hex"]
+
+
+def test_full_size_proof_verifies(ctx):
+    """BASELINE size (S20-bn: k=20, 14+3+1 columns): the GPU proof must be accepted by the oracle verifier (vanishing
+    identity at x + SHPLONK opening, all challenges re-derived from the proof bytes) using the GPU key's commitments; a
+    tampered proof and a proof of a broken witness must be rejected. Byte equality with the oracle prover at this size is
+    recorded in profiles/ (tools/prove.py --check: the CPU prover needs ~90 s)."""
+    k, A, L, F = 20, 14, 3, 1
+    trapdoor = ctx.srs_setup(k)
+    fixed, advice, copies = b200zk.synth_circuit(k, A, L, F, seed=0)
+    pk = ctx.keygen(k, A, L, F, fixed, copies)
+    fc, pc = pk.commitments()
+    ver = O.Verifier(k, A, L, F, trapdoor, fc, pc, pk.transcript_repr())
+    proof = pk.create_proof(advice, 0)
+    assert len(proof) == 5632
+    ok, err = ver.verify(proof)
+    assert ok, err
+    assert proof == pk.create_proof(advice, 0)  # deterministic
+    bad = bytearray(proof)
+    bad[32 * 50 + 3] ^= 0x10
+    assert not ver.verify(bytes(bad))[0]
+    advice[3, 12345] = advice[3, 12346]  # break one gate / copy
+    assert not ver.verify(pk.create_proof(advice, 0))[0]

@@ -248,12 +248,16 @@ __global__ void __launch_bounds__(KD_T) suffix_horner_phase1(Fr* A, size_t T, Fr
     if (t < T) f_store(A + t, sh[cur][threadIdx.x]);
     if (threadIdx.x == 0) f_store(block_head + blockIdx.x, sh[cur][0]);
 }
+// powers[j] = B^(j+1), j < KD_T
+__global__ void __launch_bounds__(KD_T) power_table_kernel(Fr* powers, Fr B) {
+    f_store(powers + threadIdx.x, f_pow_u64(B, (uint64_t)threadIdx.x + 1));
+}
 // S_t += B^(KD_T - threadIdx)·S_next_block_start
-__global__ void __launch_bounds__(KD_T) suffix_horner_phase3(Fr* A, size_t T, Fr B, const Fr* block_S, size_t nblocks_) {
+__global__ void __launch_bounds__(KD_T) suffix_horner_phase3(Fr* A, size_t T, const Fr* powers, const Fr* block_S, size_t nblocks_) {
     const size_t t = (size_t)blockIdx.x * KD_T + threadIdx.x;
     if (t >= T || blockIdx.x + 1 >= nblocks_) return;
     const Fr inflow = f_load(block_S + blockIdx.x + 1);
-    const Fr p = f_pow_u64(B, (uint64_t)(KD_T - threadIdx.x));
+    const Fr p = f_load_ro(powers + (KD_T - 1 - threadIdx.x));  // B^(KD_T - threadIdx)
     f_store(A + t, f_add(f_load(A + t), f_mul(p, inflow)));
 }
 static void suffix_horner_scan(Fr* A, size_t T, const Fr& B, cudaStream_t s) {
@@ -263,9 +267,11 @@ static void suffix_horner_scan(Fr* A, size_t T, const Fr& B, cudaStream_t s) {
     suffix_horner_phase1<<<(unsigned)nb, KD_T, 0, s>>>(A, T, B, heads.get());
     LAUNCHED(1);
     if (nb > 1) {
+        DevBuf<Fr> powers(KD_T, s);
+        power_table_kernel<<<1, KD_T, 0, s>>>(powers.get(), B);
         suffix_horner_scan(heads.get(), nb, f_pow_u64(B, KD_T), s);
-        suffix_horner_phase3<<<(unsigned)nb, KD_T, 0, s>>>(A, T, B, heads.get(), nb);
-        LAUNCHED(1);
+        suffix_horner_phase3<<<(unsigned)nb, KD_T, 0, s>>>(A, T, powers.get(), heads.get(), nb);
+        LAUNCHED(2);
     }
 }
 __global__ void __launch_bounds__(256) kate_local_kernel(const Fr* a, size_t n, Fr b, Fr* chunk_A) {

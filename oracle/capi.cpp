@@ -320,6 +320,40 @@ EXPORT int oracle_verify_proof(void* params, void* pkp, const uint8_t* proof, si
     g_err = verify_proof(*(Params*)params, pk->vk, proof, len);
     return g_err.empty();
 }
+// same with the real pairing equation (slower: two Miller loops and one final exponentiation)
+EXPORT int oracle_verify_proof_pairing(void* params, void* pkp, const uint8_t* proof, size_t len) {
+    ProvingKey* pk = (ProvingKey*)pkp;
+    g_err = verify_proof(*(Params*)params, pk->vk, proof, len, nullptr, true);
+    return g_err.empty();
+}
+// pairing KATs: returns a bit mask of the identities that hold:
+//  1: e(aP, bQ) == e(P, Q)^(ab)   2: e(P, Q) != 1   4: e(P, Q)^r == 1   8: e(P1 + P2, Q) == e(P1, Q)·e(P2, Q)
+//  16: e(P, Q1 + Q2) == e(P, Q1)·e(P, Q2)   32: s·g2 is on the twist
+EXPORT int oracle_pairing_selfcheck(const u64* a_mont, const u64* b_mont) {
+    Fr a, b;
+    memcpy(a.l, a_mont, 32);
+    memcpy(b.l, b_mont, 32);
+    const G1Affine P = G1Affine::generator();
+    const G2Affine Q = G2Affine::generator();
+    const Fq12 e = pairing(P, Q);
+    int mask = 0;
+    const G1Affine aP = G1::from_affine(P).mul(a).to_affine();
+    const G2Affine bQ = Q.mul(b);
+    if (pairing(aP, bQ) == e.pow_fr(a * b)) mask |= 1;
+    if (!(e == Fq12::one())) mask |= 2;
+    {
+        // r = -1 + ... : e^r == 1  <=>  e^(r-1) · e == 1
+        Fr minus_one = -Fr::one();
+        if (e.pow_fr(minus_one) * e == Fq12::one()) mask |= 4;
+    }
+    const G1Affine P2 = G1::from_affine(P).mul(Fr::from_u64(7)).to_affine();
+    const G1Affine Psum = G1::from_affine(aP).add_affine(P2).to_affine();
+    if (pairing(Psum, Q) == pairing(aP, Q) * pairing(P2, Q)) mask |= 8;
+    const G2Affine Q2 = Q.mul(Fr::from_u64(11));
+    if (pairing(P, bQ.add(Q2)) == pairing(P, bQ) * pairing(P, Q2)) mask |= 16;
+    if (bQ.is_on_curve() && Q.is_on_curve()) mask |= 32;
+    return mask;
+}
 EXPORT int oracle_mock_check(uint32_t k, uint32_t A, uint32_t L, uint32_t F, const u64* fixed, const u64* advice, const uint32_t* copies,
                              size_t ncopies) {
     Shape sh{k, A, L, F};
@@ -355,13 +389,13 @@ EXPORT void* oracle_verifier_new(uint32_t k, uint32_t A, uint32_t L, uint32_t F,
     memcpy(b->vk.transcript_repr.l, transcript_repr, 32);
     return b;
 }
-EXPORT int oracle_verifier_verify(void* h, const uint8_t* proof, size_t len) {
+EXPORT int oracle_verifier_verify(void* h, const uint8_t* proof, size_t len, int use_pairing) {
     struct Bundle {
         Params params;
         VerifyingKey vk;
     };
     Bundle* b = (Bundle*)h;
-    g_err = verify_proof(b->params, b->vk, proof, len);
+    g_err = verify_proof(b->params, b->vk, proof, len, nullptr, use_pairing != 0);
     return g_err.empty();
 }
 EXPORT void oracle_verifier_free(void* h) {

@@ -19,6 +19,7 @@
 #include <set>
 
 #include "kzg.hpp"
+#include "pairing.hpp"
 #include "transcript.hpp"
 
 namespace oracle {
@@ -720,8 +721,10 @@ inline std::vector<uint8_t> create_proof(const Params& params, const ProvingKey&
 
 // plonk::verify_proof with VerifierSHPLONK; the final pairing e(L,[1]_2) == e(H',[s]_2) is checked in G1
 // with the trapdoor. Returns "" on success, else the failing check.
+// `use_pairing`: check the final equation as halo2 does, e(L, g2)·e(−H', s_g2) == 1 with g2 = the BN254 G2 generator and
+// s_g2 = s·g2 (what ParamsKZG carries for the verifier), instead of L == s·H' in G1.
 inline std::string verify_proof(const Params& params, const VerifyingKey& vk, const uint8_t* proof, size_t len,
-                                const Fr* transcript_repr_override = nullptr) {
+                                const Fr* transcript_repr_override = nullptr, bool use_pairing = false) {
     const Shape& sh = vk.shape;
     Domain dom(Shape::degree, sh.k);
     const size_t n = sh.n();
@@ -886,7 +889,12 @@ inline std::string verify_proof(const Params& params, const VerifyingKey& vk, co
         outer = outer.add(G1::from_affine(h1).mul(-z_0));
         outer = outer.add(G1::from_affine(h2).mul(uu));
         // e(outer, [1]_2) == e(h2, [s]_2)
-        if (!outer.eq(G1::from_affine(h2).mul(params.s))) return "SHPLONK opening check failed";
+        if (use_pairing) {
+            const G2Affine g2 = G2Affine::generator(), s_g2 = g2.mul(params.s);
+            if (!pairing_product_is_one(outer.to_affine(), g2, h2.neg(), s_g2)) return "SHPLONK opening check failed (pairing)";
+        } else if (!outer.eq(G1::from_affine(h2).mul(params.s))) {
+            return "SHPLONK opening check failed";
+        }
         return "";
     } catch (const std::exception& e) {
         return std::string("malformed proof: ") + e.what();

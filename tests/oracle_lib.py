@@ -265,9 +265,11 @@ class ProvingKey:
         self.last_seconds = secs.value
         return buf.tobytes()
 
-    def verify(self, proof):
+    def verify(self, proof, pairing=False):
+        """verify_proof; `pairing=True` checks the opening with the real pairing equation instead of the trapdoor."""
         buf = np.frombuffer(proof, dtype=np.uint8)
-        ok = lib().oracle_verify_proof(ctypes.c_void_p(self.params.h), ctypes.c_void_p(self.h), ptr(buf), ctypes.c_size_t(len(buf)))
+        fn = lib().oracle_verify_proof_pairing if pairing else lib().oracle_verify_proof
+        ok = fn(ctypes.c_void_p(self.params.h), ctypes.c_void_p(self.h), ptr(buf), ctypes.c_size_t(len(buf)))
         return bool(ok), last_error()
 
     def __del__(self):
@@ -299,9 +301,9 @@ class Verifier:
         assert fc.shape == (F + 1 + A, 8) and pc.shape == (F + A + L, 8)
         self.h = lib().oracle_verifier_new(k, A, L, F, ptr(t), ptr(fc), ptr(pc), ptr(tr))
 
-    def verify(self, proof):
+    def verify(self, proof, pairing=False):
         buf = np.frombuffer(proof, dtype=np.uint8)
-        ok = lib().oracle_verifier_verify(ctypes.c_void_p(self.h), ptr(buf), ctypes.c_size_t(len(buf)))
+        ok = lib().oracle_verifier_verify(ctypes.c_void_p(self.h), ptr(buf), ctypes.c_size_t(len(buf)), ctypes.c_int(int(pairing)))
         return bool(ok), last_error()
 
     def __del__(self):

@@ -134,7 +134,7 @@ def test_full_size_proof_verifies(ctx):
     ver = O.Verifier(k, A, L, F, trapdoor, fc, pc, pk.transcript_repr())
     proof = pk.create_proof(advice, 0)
     assert len(proof) == 5632
-    ok, err = ver.verify(proof)
+    ok, err = ver.verify(proof, pairing=True)
     assert ok, err
     assert proof == pk.create_proof(advice, 0)  # deterministic
     bad = bytearray(proof)

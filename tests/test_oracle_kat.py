@@ -213,3 +213,12 @@ def test_permute_expression_pair_vs_python_model():
     # an input outside the table is a synthesis failure
     bad = list(inp_vals); bad[5] = n // 2 + 3
     assert O.lib().oracle_permute_expression_pair(k, O.ptr(O.fr_array(bad)), O.ptr(O.fr_array(table_vals)), O.ptr(a_out), O.ptr(s_out)) == 0
+
+
+def test_pairing_identities():
+    """oracle/pairing.hpp: bilinearity in both arguments, non-degeneracy, e(P,Q)^r == 1, s·g2 stays on the twist."""
+    rnd = random.Random(5)
+    for _ in range(2):
+        a, b = rnd.randrange(1, O.R_MOD), rnd.randrange(1, O.R_MOD)
+        mask = O.lib().oracle_pairing_selfcheck(O.ptr(O.to_mont(a)), O.ptr(O.to_mont(b)))
+        assert mask == 63, bin(mask)

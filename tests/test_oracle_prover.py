@@ -1,5 +1,5 @@
 """The oracle prover end to end on CPU: proofs of satisfying witnesses verify (vanishing identity at x + SHPLONK opening
-checked in G1 with the trapdoor), tampering and unsatisfied witnesses are rejected, outputs are deterministic, and the
+checked in G1 with the trapdoor AND with the real BN254 pairing), tampering and unsatisfied witnesses are rejected, outputs are deterministic, and the
 committed golden vectors (tests/golden/, made by tests/golden/make_golden.py) still reproduce."""
 import hashlib
 import json
@@ -26,12 +26,14 @@ def test_oracle_proof_verifies_and_rejects_tampering(shape):
     proof = pk.create_proof(advice, 0)
     assert len(proof) == O.lib().oracle_proof_size(k, A, L, F)
     assert pk.verify(proof) == (True, "")
+    assert pk.verify(proof, pairing=True) == (True, "")  # e(L, g2)·e(−H', s·g2) == 1, as halo2's verifier checks it
     assert proof == pk.create_proof(advice, 0)           # deterministic
     assert proof != pk.create_proof(advice, 1)           # rng seed matters (blinding)
     npoints = (A + L) + 2 * L + (A + L + F + 1) // 2 + L + 1 + 3
     for pos in (1, 32 * npoints + 5, len(proof) - 70, len(proof) - 3):
         bad = bytearray(proof); bad[pos] ^= 1
         assert not pk.verify(bytes(bad))[0]
+        assert not pk.verify(bytes(bad), pairing=True)[0]
     assert not pk.verify(proof[:-32])[0]
     bad_w = advice.copy(); bad_w[0, 3] = bad_w[0, 2]
     assert not O.mock_check(k, A, L, F, fixed, bad_w, copies)[0]

@@ -47,6 +47,7 @@ def lib():
         _lib.b200zk_stream.restype = ctypes.c_void_p
         _lib.b200zk_launch_count.restype = ctypes.c_ulonglong
         _lib.b200zk_proof_size.restype = ctypes.c_size_t
+        _lib.b200zk_num_sets.restype = ctypes.c_uint32
         _lib.b200zk_synth_max_copies.restype = ctypes.c_size_t
         _lib.b200zk_srs_file_size.restype = ctypes.c_size_t
     return _lib
@@ -293,6 +294,16 @@ class Context:
         self._check(lib().b200zk_msm_batch_dev(self._h, int(basis), arr, ctypes.c_size_t(len(col_ptrs)), ctypes.c_size_t(n), _p(out)))
         return out
 
+    def msm_batch(self, cols, basis=0):
+        """ParamsKZG::commit / commit_lagrange over several HOST columns ([ncols, n, 4] uint64 or a list of [n, 4] arrays)."""
+        cols = [_c(c).reshape(-1, 4) for c in cols]
+        n = len(cols[0]) if cols else 0
+        assert all(len(c) == n for c in cols)
+        arr = (ctypes.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+        out = np.empty((len(cols), 8), dtype=np.uint64)
+        self._check(lib().b200zk_msm_batch(self._h, int(basis), arr, ctypes.c_size_t(len(cols)), ctypes.c_size_t(n), _p(out)))
+        return out
+
     def msm_bases(self, scalars, bases):
         """halo2curves::msm::best_multiexp(coeffs, bases) with caller-supplied bases."""
         scalars = _c(scalars).reshape(-1, 4)
@@ -395,6 +406,26 @@ class ProvingKey:
 
     def proof_size(self):
         return int(lib().b200zk_proof_size(*self.shape))
+
+    def num_sets(self):
+        _, A, L, F = self.shape
+        return int(lib().b200zk_num_sets(A, L, F))
+
+    def evaluate_h(self, advice_coeff, perm_z_coeff, lookup_coeff, y, beta, gamma):
+        """evaluation::Evaluator::evaluate_h + divide_by_vanishing_poly on coefficient-form inputs: advice_coeff
+        [(A+L), n, 4], perm_z_coeff [num_sets, n, 4], lookup_coeff [L, 3, n, 4] (Z, a', s' per lookup) or None;
+        returns h on the extended domain [4n, 4]."""
+        k, A, L, F = self.shape
+        n = 1 << k
+        advice_coeff, perm_z_coeff = _c(advice_coeff), _c(perm_z_coeff)
+        assert advice_coeff.size == (A + L) * n * 4 and perm_z_coeff.size == self.num_sets() * n * 4
+        if L:
+            lookup_coeff = _c(lookup_coeff)
+            assert lookup_coeff.size == 3 * L * n * 4
+        out = np.empty((4 * n, 4), dtype=np.uint64)
+        self.ctx._check(lib().b200zk_evaluate_h(self.ctx._h, self._h, _p(advice_coeff), _p(perm_z_coeff), _p(lookup_coeff) if L else None,
+                                                _p(_c(y)), _p(_c(beta)), _p(_c(gamma)), _p(out)))
+        return out
 
     def create_proof(self, advice, rng_seed=0, timings=False, device_ptr=None):
         """plonk::create_proof with StdRng::seed_from_u64(rng_seed) and a Blake2b transcript; returns the proof bytes.

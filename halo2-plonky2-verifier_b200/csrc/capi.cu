@@ -71,6 +71,9 @@ int b200zk_create(int device, b200zk_ctx** out) {
     for (auto& e : ctx->c.msm_events) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     for (auto& e : ctx->c.msm_join) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->c.msm_fork, cudaEventDisableTiming);
+    if (cudaStreamCreateWithFlags(&ctx->c.copy_stream, cudaStreamNonBlocking) != cudaSuccess) ctx->c.copy_stream = nullptr;
+    cudaEventCreateWithFlags(&ctx->c.copy_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->c.copy_done, cudaEventDisableTiming);
     if (cudaHostAlloc((void**)&ctx->c.pinned_u32, 64, cudaHostAllocDefault) != cudaSuccess) {
         b200zk_destroy(ctx);
         return B200ZK_ECUDA;
@@ -103,6 +106,12 @@ int b200zk_destroy(b200zk_ctx* ctx) {
     for (auto& e : ctx->c.msm_join)
         if (e) cudaEventDestroy(e);
     if (ctx->c.msm_fork) cudaEventDestroy(ctx->c.msm_fork);
+    if (ctx->c.copy_stream) {
+        cudaStreamSynchronize(ctx->c.copy_stream);
+        cudaStreamDestroy(ctx->c.copy_stream);
+    }
+    if (ctx->c.copy_fork) cudaEventDestroy(ctx->c.copy_fork);
+    if (ctx->c.copy_done) cudaEventDestroy(ctx->c.copy_done);
     if (ctx->c.pinned_u32) cudaFreeHost(ctx->c.pinned_u32);
     delete ctx;
     cudaStreamDestroy(s);
@@ -436,6 +445,28 @@ int b200zk_msm_batch_dev(b200zk_ctx* ctx, int basis, const b200zk_fr* const* col
     memcpy(out, r.data(), 64 * ncols);
     API_END(ctx)
 }
+int b200zk_msm_batch(b200zk_ctx* ctx, int basis, const b200zk_fr* const* cols, size_t ncols, size_t n, b200zk_g1_affine* out) {
+    API_BEGIN(ctx)
+    if (!out || (ncols && !cols)) throw std::invalid_argument("msm_batch: null argument");
+    Context& c = ctx->c;
+    srs_basis(c, basis, n);
+    // groups of up to 8 columns share one staging buffer; within a group the uploads queue on the stream ahead of the MSM
+    const size_t group = 8;
+    DevBuf<Fr> d(std::min(group, ncols) * n, c.stream);
+    std::vector<G1Affine> r(ncols);
+    for (size_t g0 = 0; g0 < ncols; g0 += group) {
+        const size_t g = std::min(group, ncols - g0);
+        std::vector<const Fr*> ptrs(g);
+        for (size_t i = 0; i < g; ++i) {
+            if (!cols[g0 + i]) throw std::invalid_argument("msm_batch: null column");
+            ptrs[i] = d.get() + i * n;
+            CUDA_CHECK(cudaMemcpyAsync(d.get() + i * n, cols[g0 + i], 32 * n, cudaMemcpyHostToDevice, c.stream));
+        }
+        msm_batch_srs(c, basis, ptrs.data(), g, n, r.data() + g0);
+    }
+    memcpy(out, r.data(), 64 * ncols);
+    API_END(ctx)
+}
 int b200zk_msm(b200zk_ctx* ctx, int basis, const b200zk_fr* scalars, size_t n, b200zk_g1_affine* out) {
     API_BEGIN(ctx)
     if (!out || (n && !scalars)) throw std::invalid_argument("msm: null argument");
@@ -569,6 +600,22 @@ static int create_proof_impl(b200zk_ctx* ctx, const b200zk_pk* pk, const b200zk_
         memcpy(timings, t, sizeof(t));
     }
     API_END(ctx)
+}
+int b200zk_evaluate_h(b200zk_ctx* ctx, const b200zk_pk* pk, const b200zk_fr* advice_coeff, const b200zk_fr* perm_z_coeff, const b200zk_fr* lookup_coeff,
+                      const b200zk_fr* y, const b200zk_fr* beta, const b200zk_fr* gamma, b200zk_fr* h_ext_out) {
+    API_BEGIN(ctx)
+    if (!pk || !advice_coeff || !perm_z_coeff || !y || !beta || !gamma || !h_ext_out) throw std::invalid_argument("evaluate_h: null argument");
+    if (pk->pk->shape.L && !lookup_coeff) throw std::invalid_argument("evaluate_h: lookup_coeff is NULL but the shape has lookups");
+    Fr ch[3];
+    memcpy(&ch[0], y, 32);
+    memcpy(&ch[1], beta, 32);
+    memcpy(&ch[2], gamma, 32);
+    evaluate_h(ctx->c, *pk->pk, (const Fr*)advice_coeff, (const Fr*)perm_z_coeff, (const Fr*)lookup_coeff, ch[0], ch[1], ch[2], (Fr*)h_ext_out);
+    API_END(ctx)
+}
+uint32_t b200zk_num_sets(uint32_t A, uint32_t L, uint32_t F) {
+    Shape sh{1, A, L, F};
+    return sh.num_sets();
 }
 int b200zk_create_proof(b200zk_ctx* ctx, const b200zk_pk* pk, const b200zk_fr* advice, uint64_t rng_seed, uint8_t* proof_out, size_t* proof_len,
                         double* timings) {

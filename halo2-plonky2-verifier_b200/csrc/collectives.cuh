@@ -65,8 +65,9 @@ struct Nccl {
 // ownership of column-wise work in the sharded prover: item i belongs to rank i mod world
 struct Sharder {
     Context& ctx;
+    bool enabled = true;  // false: this call works on the local GPU alone even inside a multi-rank job
     explicit Sharder(Context& c) : ctx(c) {}
-    bool on() const { return ctx.world > 1 && ctx.allgather; }
+    bool on() const { return enabled && ctx.world > 1 && ctx.allgather; }
     int owner(size_t i) const { return on() ? (int)(i % ctx.world) : 0; }
     bool mine(size_t i) const { return !on() || owner(i) == ctx.rank; }
     Nccl& nccl() {

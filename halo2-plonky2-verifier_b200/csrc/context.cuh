@@ -86,6 +86,8 @@ struct Context {
     cudaStream_t stream = nullptr;
     cudaStream_t aux_streams[MSM_SLOTS - 1] = {};  // further MSM columns in flight (msm.cu)
     cudaEvent_t msm_events[MSM_SLOTS] = {}, msm_join[MSM_SLOTS - 1] = {}, msm_fork = nullptr;
+    cudaStream_t copy_stream = nullptr;    // witness upload overlapped with the first advice commitments (prover.cu)
+    cudaEvent_t copy_fork = nullptr, copy_done = nullptr;
     uint32_t* pinned_u32 = nullptr;        // pinned words for the entry-count read-backs (one per slot)
     std::mutex mu;
     std::string last_error;

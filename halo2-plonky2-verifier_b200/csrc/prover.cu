@@ -295,6 +295,94 @@ static void eval_many_dist(Context& ctx, Sharder& shard, const std::vector<const
 // ---- create_proof ---------------------------------------------------------------------------------------------------------
 // rotation reach of the h(X) kernels in extended rows: -4·(blinding_factors+1) = -28 (z of the previous set) ... +12 (gate rotation 3)
 static constexpr size_t HALO_BEFORE = 32, HALO_AFTER = 16;
+// Row H: evaluation::Evaluator::evaluate_h followed by divide_by_vanishing_poly (the t_inv scaling is fused into the last
+// kernel), on the extended domain. Inputs: the advice and permutation-product cosets (NA resp. NS columns of 4n), and per
+// lookup the coefficient forms of Z, a', s' (their cosets are made here, three at a time, so they never all coexist).
+// Sharded: every rank evaluates a contiguous slice of the extended rows and h is all-gathered at the end.
+template <class Lap>
+static void evaluate_h_dev(Context& ctx, Sharder& shard, const ProvingKeyDev& pk, const Fr* advice_cosets, const Fr* z_cosets, const Fr* lk_z_poly,
+                           const Fr* perm_in_poly, const Fr* perm_tab_poly, const Fr& y, const Fr& beta, const Fr& gamma, Fr* h, ProofTimings* tm,
+                           Lap&& lap) {
+    const Shape& sh = pk.shape;
+    cudaStream_t s = ctx.stream;
+    const size_t n = sh.n(), en = 4 * n;
+    const uint32_t bf = Shape::blinding_factors, NA = sh.num_advice(), A = sh.A, L = sh.L, F = sh.F, P = sh.num_perm(), NS = sh.num_sets();
+    const Domain& dom = ctx.domain(sh.k);
+    const TwiddleTable& tw = ctx.std_table(sh.k + 2);
+    if (shard.on() && en % ctx.world) throw std::runtime_error("sharded prover: world size must divide the extended domain");
+    QuotientArgs Q{};
+    Q.k = sh.k; Q.A = A; Q.L = L; Q.F = F; Q.P = P; Q.num_sets = NS; Q.blinding_factors = bf;
+    Q.table = tw.t.get();
+    Q.table_log = tw.log_n;
+    Q.t_inv = dom.t_inv_dev();
+    for (uint32_t c = 0; c < NA; ++c) Q.advice[c] = advice_cosets + (size_t)c * en;
+    for (uint32_t i = 0; i < sh.num_fixed(); ++i) Q.fixed[i] = pk.fixed_cosets.get() + (size_t)i * en;
+    for (uint32_t j = 0; j < P; ++j) {
+        Q.perm_cols[j] = sh.perm_is_fixed(j) ? Q.fixed[sh.perm_col_index(j)] : Q.advice[sh.perm_col_index(j)];
+        Q.sigma[j] = pk.sigma_cosets.get() + (size_t)j * en;
+    }
+    for (uint32_t set = 0; set < NS; ++set) Q.z[set] = z_cosets + (size_t)set * en;
+    Q.l0 = pk.l_polys.get();
+    Q.l_last = pk.l_polys.get() + en;
+    Q.l_active = pk.l_polys.get() + 2 * en;
+    Q.y = y; Q.beta = beta; Q.gamma = gamma; Q.delta = FrConsts::delta();
+    Q.beta_zeta = f_mul(beta, FrConsts::zeta());
+    const size_t rows_per_rank = shard.on() ? en / ctx.world : en;
+    Q.row_begin = shard.on() ? rows_per_rank * ctx.rank : 0;
+    Q.row_end = Q.row_begin + rows_per_rank;
+    h_gates(Q, h, s);
+    h_permutation(Q, h, L == 0, s);
+    lap(tm ? &tm->quotient : nullptr);
+    if (L) {
+        DevBuf<Fr> lc(3 * en, s);
+        for (uint32_t l = 0; l < L; ++l) {
+            const Fr* srcs[3] = {lk_z_poly + (size_t)l * n, perm_in_poly + (size_t)l * n, perm_tab_poly + (size_t)l * n};
+            for (uint32_t j = 0; j < 3; ++j)
+                if (shard.mine(3 * l + j)) dev_coeff_to_extended(ctx, sh.k, srcs[j], lc.get() + (size_t)j * en);
+            Fr* cs[3] = {lc.get(), lc.get() + en, lc.get() + 2 * en};
+            shard.exchange_row_slices(cs, 3, [&](size_t j) { return shard.owner(3 * l + j); }, en, HALO_BEFORE, HALO_AFTER);
+            lap(tm ? &tm->ntt : nullptr);
+            LookupCosets Lk{lc.get(), lc.get() + en, lc.get() + 2 * en, Q.advice[A + l], Q.fixed[sh.table_col()]};
+            h_lookup(Q, Lk, h, l + 1 == L, s);
+            lap(tm ? &tm->quotient : nullptr);
+        }
+    }
+    if (shard.on()) {
+        shard.all_gather_inplace(h, en / ctx.world);
+        lap(tm ? &tm->quotient : nullptr);
+    }
+}
+
+// b200zk_evaluate_h: row H on its own, for a host that keeps halo2's create_proof and replaces only evaluate_h. All
+// polynomials arrive in coefficient form (as halo2 holds them at that point); returns h on the extended domain, already
+// divided by the vanishing polynomial. Runs unsharded on the calling rank's GPU.
+void evaluate_h(Context& ctx, const ProvingKeyDev& pk, const Fr* advice_coeff, const Fr* z_coeff, const Fr* lookup_coeff, const Fr& y, const Fr& beta,
+                const Fr& gamma, Fr* h_out) {
+    const Shape& sh = pk.shape;
+    cudaStream_t s = ctx.stream;
+    const size_t n = sh.n(), en = 4 * n;
+    const uint32_t NA = sh.num_advice(), L = sh.L, NS = sh.num_sets();
+    Sharder shard(ctx);
+    shard.enabled = false;
+    DevBuf<Fr> polys((size_t)std::max<uint32_t>(NA, std::max<uint32_t>(NS, 3 * L)) * n, s);
+    DevBuf<Fr> advice_cosets((size_t)NA * en, s), z_cosets((size_t)NS * en, s), h(en, s);
+    auto to_cosets = [&](const Fr* host, uint32_t count, Fr* cosets) {
+        CUDA_CHECK(cudaMemcpyAsync(polys.get(), host, (size_t)count * n * sizeof(Fr), cudaMemcpyHostToDevice, s));
+        for (uint32_t c = 0; c < count; ++c) dev_coeff_to_extended(ctx, sh.k, polys.get() + (size_t)c * n, cosets + (size_t)c * en);
+    };
+    to_cosets(advice_coeff, NA, advice_cosets.get());
+    to_cosets(z_coeff, NS, z_cosets.get());
+    // lookup_coeff: per lookup l the three polynomials Z_l, a'_l, s'_l, each n coefficients
+    DevBuf<Fr> lk((size_t)3 * L * n, s);
+    for (uint32_t l = 0; l < L; ++l)
+        for (uint32_t j = 0; j < 3; ++j)
+            CUDA_CHECK(cudaMemcpyAsync(lk.get() + ((size_t)j * L + l) * n, lookup_coeff + ((size_t)3 * l + j) * n, n * sizeof(Fr), cudaMemcpyHostToDevice, s));
+    evaluate_h_dev(ctx, shard, pk, advice_cosets.get(), z_cosets.get(), lk.get(), lk.get() + (size_t)L * n, lk.get() + (size_t)2 * L * n, y, beta, gamma,
+                   h.get(), nullptr, [](double*) {});
+    CUDA_CHECK(cudaMemcpyAsync(h_out, h.get(), en * sizeof(Fr), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
 std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const Fr* advice_in, bool advice_on_device, host::FrRandomStream& rng,
                                   ProofTimings* tm) {
     const Shape& sh = pk.shape;
@@ -325,26 +413,54 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
     tr.common_scalar(pk.transcript_repr);
     // step 1: upload, blind, commit advice (D.3)
     DevBuf<Fr> advice((size_t)NA * n, s);
+    std::vector<Fr> blind((size_t)NA * (bf + 1));
+    for (auto& b : blind) b = rng.next();
+    rng.skip(NA);  // Blind(..) per column: drawn upstream, unused by KZG commitments
+    // columns [c0, c1) from the caller's buffer, then their blinding rows, in order on one stream
+    auto upload = [&](uint32_t c0, uint32_t c1, cudaStream_t st) {
+        if (c0 >= c1) return;
+        CUDA_CHECK(cudaMemcpyAsync(advice.get() + (size_t)c0 * n, advice_in + (size_t)c0 * n, (size_t)(c1 - c0) * n * sizeof(Fr),
+                                   advice_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        for (uint32_t c = c0; c < c1; ++c)
+            CUDA_CHECK(cudaMemcpyAsync(advice.get() + (size_t)c * n + u, blind.data() + (size_t)c * (bf + 1), (bf + 1) * sizeof(Fr),
+                                       cudaMemcpyHostToDevice, st));
+    };
+    // the copy stream must be idle before `advice` can go back to the arena, whichever way this function is left
+    struct CopyJoin {
+        cudaStream_t st;
+        ~CopyJoin() {
+            if (st) cudaStreamSynchronize(st);
+        }
+    } copy_join{nullptr};
+    // host witness on one GPU: the first quarter of the columns goes up on the compute stream, the rest follows on the copy
+    // stream while that quarter is being committed (pinned host memory overlaps; pageable memory degrades to in-order)
+    const uint32_t ahead = (!advice_on_device && !shard.on() && ctx.copy_stream && NA >= 8) ? NA / 4 : NA;
     if (shard.on() && !advice_on_device) {
         // every rank holds the host witness: each uploads only its share of the columns over PCIe and the rest arrives over NVLink
         for (uint32_t c = 0; c < NA; ++c)
             if (shard.mine(c))
                 CUDA_CHECK(cudaMemcpyAsync(advice.get() + (size_t)c * n, advice_in + (size_t)c * n, n * sizeof(Fr), cudaMemcpyHostToDevice, s));
         shard.allgather_columns(advice.get(), NA, n);
-    } else {
-        CUDA_CHECK(cudaMemcpyAsync(advice.get(), advice_in, (size_t)NA * n * sizeof(Fr), advice_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
-    }
-    {
-        std::vector<Fr> blind((size_t)NA * (bf + 1));
-        for (auto& b : blind) b = rng.next();
         for (uint32_t c = 0; c < NA; ++c)
             CUDA_CHECK(cudaMemcpyAsync(advice.get() + (size_t)c * n + u, blind.data() + (size_t)c * (bf + 1), (bf + 1) * sizeof(Fr),
                                        cudaMemcpyHostToDevice, s));
-        rng.skip(NA);  // Blind(..) per column: drawn upstream, unused by KZG commitments
-        CUDA_CHECK(cudaStreamSynchronize(s));
+    } else if (ahead < NA) {
+        CUDA_CHECK(cudaEventRecord(ctx.copy_fork, s));
+        CUDA_CHECK(cudaStreamWaitEvent(ctx.copy_stream, ctx.copy_fork, 0));
+        copy_join.st = ctx.copy_stream;
+        upload(0, ahead, s);
+        upload(ahead, NA, ctx.copy_stream);
+        CUDA_CHECK(cudaEventRecord(ctx.copy_done, ctx.copy_stream));
+    } else {
+        upload(0, NA, s);
     }
+    CUDA_CHECK(cudaStreamSynchronize(s));
     lap(tm ? &tm->upload : nullptr);
-    for (const G1Affine& cm : commit_batch(ctx, 1, advice.get(), n, NA, n)) tr.write_point(cm);
+    for (const G1Affine& cm : commit_batch(ctx, 1, advice.get(), n, ahead, n)) tr.write_point(cm);
+    if (ahead < NA) {
+        CUDA_CHECK(cudaStreamWaitEvent(s, ctx.copy_done, 0));
+        for (const G1Affine& cm : commit_batch(ctx, 1, advice.get() + (size_t)ahead * n, n, NA - ahead, n)) tr.write_point(cm);
+    }
     lap(tm ? &tm->msm : nullptr);
     const Fr theta = tr.squeeze_challenge();
     (void)theta;  // single-expression lookups: theta-compression is the identity
@@ -523,49 +639,8 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
     }
     lap(tm ? &tm->ntt : nullptr);
     DevBuf<Fr> h(en, s);
-    {
-        QuotientArgs Q{};
-        Q.k = sh.k; Q.A = A; Q.L = L; Q.F = F; Q.P = P; Q.num_sets = NS; Q.blinding_factors = bf;
-        Q.table = tw.t.get();
-        Q.table_log = tw.log_n;
-        Q.t_inv = dom.t_inv_dev();
-        for (uint32_t c = 0; c < NA; ++c) Q.advice[c] = advice_cosets.get() + (size_t)c * en;
-        for (uint32_t i = 0; i < sh.num_fixed(); ++i) Q.fixed[i] = pk.fixed_cosets.get() + (size_t)i * en;
-        for (uint32_t j = 0; j < P; ++j) {
-            Q.perm_cols[j] = sh.perm_is_fixed(j) ? Q.fixed[sh.perm_col_index(j)] : Q.advice[sh.perm_col_index(j)];
-            Q.sigma[j] = pk.sigma_cosets.get() + (size_t)j * en;
-        }
-        for (uint32_t set = 0; set < NS; ++set) Q.z[set] = z_cosets.get() + (size_t)set * en;
-        Q.l0 = pk.l_polys.get();
-        Q.l_last = pk.l_polys.get() + en;
-        Q.l_active = pk.l_polys.get() + 2 * en;
-        Q.y = y; Q.beta = beta; Q.gamma = gamma; Q.delta = FrConsts::delta();
-        Q.beta_zeta = f_mul(beta, FrConsts::zeta());
-        // each rank evaluates a contiguous slice of the extended rows; h is all-gathered at the end
-        const size_t rows_per_rank = shard.on() ? en / ctx.world : en;
-        Q.row_begin = shard.on() ? rows_per_rank * ctx.rank : 0;
-        Q.row_end = Q.row_begin + rows_per_rank;
-        h_gates(Q, h.get(), s);
-        h_permutation(Q, h.get(), L == 0, s);
-        lap(tm ? &tm->quotient : nullptr);
-        DevBuf<Fr> lc(3 * en, s);
-        for (uint32_t l = 0; l < L; ++l) {
-            const Fr* srcs[3] = {lk_z_poly.get() + (size_t)l * n, perm_in_poly.get() + (size_t)l * n, perm_tab_poly.get() + (size_t)l * n};
-            for (uint32_t j = 0; j < 3; ++j)
-                if (shard.mine(3 * l + j)) dev_coeff_to_extended(ctx, sh.k, srcs[j], lc.get() + (size_t)j * en);
-            Fr* cs[3] = {lc.get(), lc.get() + en, lc.get() + 2 * en};
-            shard.exchange_row_slices(cs, 3, [&](size_t j) { return shard.owner(3 * l + j); }, en, HALO_BEFORE, HALO_AFTER);
-            lap(tm ? &tm->ntt : nullptr);
-            LookupCosets Lk{lc.get(), lc.get() + en, lc.get() + 2 * en, Q.advice[A + l], Q.fixed[sh.table_col()]};
-            h_lookup(Q, Lk, h.get(), l + 1 == L, s);
-            lap(tm ? &tm->quotient : nullptr);
-        }
-    }
-    if (shard.on()) {
-        if (en % ctx.world) throw std::runtime_error("sharded prover: world size must divide the extended domain");
-        shard.all_gather_inplace(h.get(), en / ctx.world);
-        lap(tm ? &tm->quotient : nullptr);
-    }
+    evaluate_h_dev(ctx, shard, pk, advice_cosets.get(), z_cosets.get(), lk_z_poly.get(), perm_in_poly.get(), perm_tab_poly.get(), y, beta, gamma,
+                   h.get(), tm, lap);
     // step 10: vanishing::construct (D.9) — t_inv scaling already applied by the last h kernel
     DevBuf<Fr> h_coeff(3 * n, s);
     dev_extended_to_coeff(ctx, sh.k, h.get(), h_coeff.get());

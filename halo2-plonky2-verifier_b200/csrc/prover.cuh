@@ -48,6 +48,8 @@ struct ProofTimings {
 };
 
 std::unique_ptr<ProvingKeyDev> keygen(Context& ctx, const Shape& sh, const Fr* fixed_host, const uint32_t* copies, size_t ncopies);
+void evaluate_h(Context& ctx, const ProvingKeyDev& pk, const Fr* advice_coeff, const Fr* z_coeff, const Fr* lookup_coeff, const Fr& y, const Fr& beta,
+                const Fr& gamma, Fr* h_out);
 std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const Fr* advice_in, bool advice_on_device, host::FrRandomStream& rng,
                                   ProofTimings* tm);
 

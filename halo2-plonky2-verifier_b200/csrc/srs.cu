@@ -59,8 +59,16 @@ void srs_build_tables(Context& ctx) {
     srs.tab_c = msm_table_window_bits(lg);
     const uint32_t W = (255 + srs.tab_c - 1) / srs.tab_c;
     if ((size_t)W * len >= ((size_t)1 << 31)) return;  // entry indices are 31-bit: fall back to the generic path
-    msm_build_table(ctx, srs.g.get() + lo, len, srs.tab_c, srs.g_tab);
-    msm_build_table(ctx, srs.g_lagrange.get() + lo, len, srs.tab_c, srs.gl_tab);
+    // a table is W× the basis (56 GiB at k = 26): build it only while at least 35 % of the device (and 16 GiB) stays free
+    // for the prover's columns; a basis without a table takes the generic windowed path
+    auto fits = [&]() {
+        size_t free_b = 0, total_b = 0;
+        CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+        const size_t need = (size_t)W * len * sizeof(G1Affine), keep = std::max<size_t>((size_t)16 << 30, total_b / 100 * 35);
+        return free_b >= need + keep;
+    };
+    if (fits()) msm_build_table(ctx, srs.g.get() + lo, len, srs.tab_c, srs.g_tab);
+    if (fits()) msm_build_table(ctx, srs.g_lagrange.get() + lo, len, srs.tab_c, srs.gl_tab);
     srs.tab_lo = lo;
     srs.tab_n = len;
     CUDA_CHECK(cudaStreamSynchronize(ctx.stream));

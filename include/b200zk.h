@@ -120,6 +120,10 @@ B200ZK_API int b200zk_msm_dev(b200zk_ctx* ctx, int basis, const b200zk_fr* scala
 /* `ncols` commitments over the same basis: cols_dev[i] points at n device-resident scalars; out gets ncols affine points.
  * Buckets are accumulated per column and reduced once for the whole batch (the reduction tail is latency bound). */
 B200ZK_API int b200zk_msm_batch_dev(b200zk_ctx* ctx, int basis, const b200zk_fr* const* cols_dev, size_t ncols, size_t n, b200zk_g1_affine* out);
+/* the same with HOST columns (cols[i] points at n scalars in host memory): what a patched ParamsKZG::commit /
+ * commit_lagrange loop over several polynomials binds (SURVEY.md §8b `b200zk_msm_batch`). Uploads are pipelined with
+ * the accumulation of the previous column. */
+B200ZK_API int b200zk_msm_batch(b200zk_ctx* ctx, int basis, const b200zk_fr* const* cols, size_t ncols, size_t n, b200zk_g1_affine* out);
 /* best_multiexp(coeffs, bases) with caller-supplied bases (host buffers) */
 B200ZK_API int b200zk_msm_bases(b200zk_ctx* ctx, const b200zk_g1_affine* bases, const b200zk_fr* scalars, size_t n, b200zk_g1_affine* out);
 /* device bases + device scalars (bench / multi-GPU shards): point range [0, n) of bases_dev */
@@ -168,6 +172,19 @@ B200ZK_API int b200zk_create_proof(b200zk_ctx* ctx, const b200zk_pk* pk, const b
 /* same with the advice columns already resident in device memory (the witness upload excluded) */
 B200ZK_API int b200zk_create_proof_dev(b200zk_ctx* ctx, const b200zk_pk* pk, const b200zk_fr* advice_dev, uint64_t rng_seed, uint8_t* proof_out,
                                        size_t* proof_len, double* timings);
+/* Row H on its own — evaluation::Evaluator::evaluate_h + EvaluationDomain::divide_by_vanishing_poly — for a host that
+ * keeps halo2's create_proof loop and replaces only this step (SURVEY.md §8b `b200zk_evaluate_h`). All inputs are host
+ * buffers in COEFFICIENT form, as halo2 holds them at that point:
+ *   advice_coeff : (A+L) × 2^k,   perm_z_coeff : num_sets × 2^k (permutation product polynomials),
+ *   lookup_coeff : L × 3 × 2^k, per lookup Z, a' (permuted input), s' (permuted table); may be NULL when L = 0.
+ * y, beta, gamma: the transcript challenges (theta is not needed: halo2-base lookups are single-column).
+ * h_ext_out: 4·2^k values of h on the extended coset domain, already divided by the vanishing polynomial, i.e. the
+ * input of extended_to_coeff. Runs on this context's GPU alone, also inside a multi-rank job. */
+B200ZK_API int b200zk_evaluate_h(b200zk_ctx* ctx, const b200zk_pk* pk, const b200zk_fr* advice_coeff, const b200zk_fr* perm_z_coeff,
+                                 const b200zk_fr* lookup_coeff, const b200zk_fr* y, const b200zk_fr* beta, const b200zk_fr* gamma,
+                                 b200zk_fr* h_ext_out);
+/* number of permutation product polynomials (sets of 3 columns) for a shape */
+B200ZK_API uint32_t b200zk_num_sets(uint32_t A, uint32_t L, uint32_t F);
 /* ---- host-only helpers (no CUDA device needed) -------------------------------------------------------------------
  * Sum of n affine G1 points (canonical affine out): combines per-GPU partial MSM results. */
 B200ZK_API int b200zk_g1_sum_host(const b200zk_g1_affine* points, size_t n, b200zk_g1_affine* out);

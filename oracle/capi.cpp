@@ -314,6 +314,38 @@ EXPORT size_t oracle_create_proof(void* params, void* pkp, const u64* advice, u6
         return 0;
     }
 }
+// evaluate_h on its own: coefficient-form inputs (advice (A+L)×n, permutation products num_sets×n, per lookup Z, a', s'
+// = L×3×n), challenges y/beta/gamma; h_out = 4n extended-domain values divided by the vanishing polynomial.
+EXPORT int oracle_evaluate_h(void* pkp, const u64* advice_coeff, const u64* z_coeff, const u64* lookup_coeff, const u64* y, const u64* beta,
+                             const u64* gamma, u64* h_out) {
+    try {
+        ProvingKey* pk = (ProvingKey*)pkp;
+        const Shape& sh = pk->vk.shape;
+        const Domain& dom = pk->domain;
+        const size_t n = sh.n();
+        std::vector<Poly> advice_cosets, z_cosets, lz(sh.L), la(sh.L), ls(sh.L);
+        for (auto& p : unpack_cols(advice_coeff, sh.num_advice(), n)) advice_cosets.push_back(dom.coeff_to_extended(p));
+        for (auto& p : unpack_cols(z_coeff, sh.num_sets(), n)) z_cosets.push_back(dom.coeff_to_extended(p));
+        if (sh.L) {
+            auto lk = unpack_cols(lookup_coeff, 3 * sh.L, n);
+            for (uint32_t l = 0; l < sh.L; ++l) {
+                lz[l] = lk[3 * l];
+                la[l] = lk[3 * l + 1];
+                ls[l] = lk[3 * l + 2];
+            }
+        }
+        Challenges ch{};
+        memcpy(ch.y.l, y, 32);
+        memcpy(ch.beta.l, beta, 32);
+        memcpy(ch.gamma.l, gamma, 32);
+        Poly h = evaluate_h(*pk, dom, advice_cosets, z_cosets, lz, la, ls, ch);
+        memcpy(h_out, h.data(), h.size() * 32);
+        return 1;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 0;
+    }
+}
 // 1 = accepted
 EXPORT int oracle_verify_proof(void* params, void* pkp, const uint8_t* proof, size_t len) {
     ProvingKey* pk = (ProvingKey*)pkp;
@@ -353,6 +385,29 @@ EXPORT int oracle_pairing_selfcheck(const u64* a_mont, const u64* b_mont) {
     if (pairing(P, bQ.add(Q2)) == pairing(P, bQ) * pairing(P, Q2)) mask |= 16;
     if (bQ.is_on_curve() && Q.is_on_curve()) mask |= 32;
     return mask;
+}
+// e(p0, q0)·e(p1, q1) == 1 for raw inputs: G1 = 8 u64 (x, y Montgomery limbs), G2 = 16 u64 (x.c0, x.c1, y.c0, y.c1), the
+// RawBytes layout of a ParamsKZG file. Returns 1/0, or -1 when a point is off its curve.
+EXPORT int oracle_pairing_product_is_one(const u64* p0, const u64* q0, const u64* p1, const u64* q1) {
+    auto g1 = [](const u64* p) {
+        G1Affine a;
+        memcpy(a.x.l, p, 32);
+        memcpy(a.y.l, p + 4, 32);
+        return a;
+    };
+    auto g2 = [](const u64* q) {
+        G2Affine a;
+        memcpy(a.x.c0.l, q, 32);
+        memcpy(a.x.c1.l, q + 4, 32);
+        memcpy(a.y.c0.l, q + 8, 32);
+        memcpy(a.y.c1.l, q + 12, 32);
+        a.inf = false;
+        return a;
+    };
+    const G1Affine a0 = g1(p0), a1 = g1(p1);
+    const G2Affine b0 = g2(q0), b1 = g2(q1);
+    if (!a0.is_on_curve() || !a1.is_on_curve() || !b0.is_on_curve() || !b1.is_on_curve()) return -1;
+    return pairing_product_is_one(a0, b0, a1, b1) ? 1 : 0;
 }
 EXPORT int oracle_mock_check(uint32_t k, uint32_t A, uint32_t L, uint32_t F, const u64* fixed, const u64* advice, const uint32_t* copies,
                              size_t ncopies) {

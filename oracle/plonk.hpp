@@ -363,13 +363,98 @@ struct Challenges {
     Fr theta, beta, gamma, y, x;
 };
 
+// evaluation::Evaluator::evaluate_h for the halo2-base constraint system, followed by
+// EvaluationDomain::divide_by_vanishing_poly: h on the extended domain from the advice / permutation-product cosets and
+// the coefficient forms of each lookup's Z, a', s'.
+inline Poly evaluate_h(const ProvingKey& pk, const Domain& dom, const std::vector<Poly>& advice_cosets, const std::vector<Poly>& z_cosets,
+                       const std::vector<Poly>& lk_z_poly, const std::vector<Poly>& perm_in_poly, const std::vector<Poly>& perm_tab_poly,
+                       const Challenges& ch) {
+    const Shape& sh = pk.vk.shape;
+    const size_t en = dom.extended_n;
+    const uint32_t bf = Shape::blinding_factors;
+    Poly h(en, Fr::zero());
+    const int rot_scale = 1 << (dom.extended_k - dom.k);
+    auto rot = [&](size_t idx, int r) -> size_t { return (size_t)(((int64_t)idx + (int64_t)r * rot_scale + (int64_t)en) % (int64_t)en); };
+    const Fr one = Fr::one();
+    // gates
+    parallel_chunks(en, [&](size_t b, size_t e, int) {
+        for (size_t i = b; i < e; ++i) {
+            Fr v = h[i];
+            for (uint32_t c = 0; c < sh.A; ++c) {
+                const Poly& a = advice_cosets[c];
+                Fr g = pk.fixed_cosets[sh.selector_col(c)][i] * (a[i] + a[rot(i, 1)] * a[rot(i, 2)] - a[rot(i, 3)]);
+                v = v * ch.y + g;
+            }
+            h[i] = v;
+        }
+    });
+    // permutation
+    {
+        auto coset_of = [&](uint32_t j) -> const Poly& {
+            return sh.perm_is_fixed(j) ? pk.fixed_cosets[sh.perm_col_index(j)] : advice_cosets[sh.perm_col_index(j)];
+        };
+        const int last_rotation = -(int)(bf + 1);
+        const Fr delta_start = ch.beta * FrConst::zeta();
+        const size_t ns = z_cosets.size();
+        parallel_chunks(en, [&](size_t b, size_t e, int) {
+            Fr beta_term = dom.extended_omega.pow_u64(b);
+            for (size_t i = b; i < e; ++i) {
+                size_t r_next = rot(i, 1), r_last = rot(i, last_rotation);
+                Fr v = h[i];
+                v = v * ch.y + (one - z_cosets[0][i]) * pk.l0[i];
+                const Fr& zl = z_cosets[ns - 1][i];
+                v = v * ch.y + (zl * zl - zl) * pk.l_last[i];
+                for (size_t s = 1; s < ns; ++s) v = v * ch.y + (z_cosets[s][i] - z_cosets[s - 1][r_last]) * pk.l0[i];
+                Fr current_delta = delta_start * beta_term;
+                for (size_t s = 0; s < ns; ++s) {
+                    uint32_t j0 = s * Shape::chunk_len, j1 = std::min<uint32_t>(sh.num_perm(), j0 + Shape::chunk_len);
+                    Fr left = z_cosets[s][r_next];
+                    for (uint32_t j = j0; j < j1; ++j) left *= coset_of(j)[i] + ch.beta * pk.sigma_cosets[j][i] + ch.gamma;
+                    Fr right = z_cosets[s][i];
+                    for (uint32_t j = j0; j < j1; ++j) {
+                        right *= coset_of(j)[i] + current_delta + ch.gamma;
+                        current_delta *= FrConst::delta();
+                    }
+                    v = v * ch.y + (left - right) * pk.l_active_row[i];
+                }
+                h[i] = v;
+                beta_term *= dom.extended_omega;
+            }
+        });
+    }
+    // lookups
+    for (uint32_t l = 0; l < sh.L; ++l) {
+        Poly zc = dom.coeff_to_extended(lk_z_poly[l]);
+        Poly ac = dom.coeff_to_extended(perm_in_poly[l]);
+        Poly sc = dom.coeff_to_extended(perm_tab_poly[l]);
+        const Poly& in_c = advice_cosets[sh.A + l];
+        const Poly& tab_c = pk.fixed_cosets[sh.table_col()];
+        parallel_chunks(en, [&](size_t b, size_t e, int) {
+            for (size_t i = b; i < e; ++i) {
+                Fr table_value = (in_c[i] + ch.beta) * (tab_c[i] + ch.gamma);
+                size_t r_next = rot(i, 1), r_prev = rot(i, -1);
+                Fr a_minus_s = ac[i] - sc[i];
+                Fr v = h[i];
+                v = v * ch.y + (one - zc[i]) * pk.l0[i];
+                v = v * ch.y + (zc[i] * zc[i] - zc[i]) * pk.l_last[i];
+                v = v * ch.y + (zc[r_next] * (ac[i] + ch.beta) * (sc[i] + ch.gamma) - zc[i] * table_value) * pk.l_active_row[i];
+                v = v * ch.y + a_minus_s * pk.l0[i];
+                v = v * ch.y + a_minus_s * (ac[i] - ac[r_prev]) * pk.l_active_row[i];
+                h[i] = v;
+            }
+        });
+    }
+    dom.divide_by_vanishing_poly(h);
+    return h;
+}
+
 // plonk::create_proof (SURVEY.md §3.2 steps 0–12). `advice` = A+L Lagrange columns of n values; the last
 // blinding_factors+1 rows are overwritten with blinding values drawn from `rng` [UNVERIFIED-1: draw order].
 inline std::vector<uint8_t> create_proof(const Params& params, const ProvingKey& pk, std::vector<Poly> advice,
                                          ChaChaRng& rng, const Fr* transcript_repr_override = nullptr) {
     const Shape& sh = pk.vk.shape;
     const Domain& dom = pk.domain;
-    const size_t n = sh.n(), u = sh.usable_rows(), en = dom.extended_n;
+    const size_t n = sh.n(), u = sh.usable_rows();
     const uint32_t bf = Shape::blinding_factors, NA = sh.num_advice();
     TranscriptWrite tr;
     auto commit_affine_batch = [&](const std::vector<G1>& pts) {
@@ -488,80 +573,7 @@ inline std::vector<uint8_t> create_proof(const Params& params, const ProvingKey&
         advice_polys[c] = dom.lagrange_to_coeff(advice[c]);
         advice_cosets[c] = dom.coeff_to_extended(advice_polys[c]);
     }
-    Poly h(en, Fr::zero());
-    const int rot_scale = 1 << (dom.extended_k - dom.k);
-    auto rot = [&](size_t idx, int r) -> size_t { return (size_t)(((int64_t)idx + (int64_t)r * rot_scale + (int64_t)en) % (int64_t)en); };
-    const Fr one = Fr::one();
-    // gates
-    parallel_chunks(en, [&](size_t b, size_t e, int) {
-        for (size_t i = b; i < e; ++i) {
-            Fr v = h[i];
-            for (uint32_t c = 0; c < sh.A; ++c) {
-                const Poly& a = advice_cosets[c];
-                Fr g = pk.fixed_cosets[sh.selector_col(c)][i] * (a[i] + a[rot(i, 1)] * a[rot(i, 2)] - a[rot(i, 3)]);
-                v = v * ch.y + g;
-            }
-            h[i] = v;
-        }
-    });
-    // permutation
-    {
-        auto coset_of = [&](uint32_t j) -> const Poly& {
-            return sh.perm_is_fixed(j) ? pk.fixed_cosets[sh.perm_col_index(j)] : advice_cosets[sh.perm_col_index(j)];
-        };
-        const int last_rotation = -(int)(bf + 1);
-        const Fr delta_start = ch.beta * FrConst::zeta();
-        const size_t ns = z_cosets.size();
-        parallel_chunks(en, [&](size_t b, size_t e, int) {
-            Fr beta_term = dom.extended_omega.pow_u64(b);
-            for (size_t i = b; i < e; ++i) {
-                size_t r_next = rot(i, 1), r_last = rot(i, last_rotation);
-                Fr v = h[i];
-                v = v * ch.y + (one - z_cosets[0][i]) * pk.l0[i];
-                const Fr& zl = z_cosets[ns - 1][i];
-                v = v * ch.y + (zl * zl - zl) * pk.l_last[i];
-                for (size_t s = 1; s < ns; ++s) v = v * ch.y + (z_cosets[s][i] - z_cosets[s - 1][r_last]) * pk.l0[i];
-                Fr current_delta = delta_start * beta_term;
-                for (size_t s = 0; s < ns; ++s) {
-                    uint32_t j0 = s * Shape::chunk_len, j1 = std::min<uint32_t>(sh.num_perm(), j0 + Shape::chunk_len);
-                    Fr left = z_cosets[s][r_next];
-                    for (uint32_t j = j0; j < j1; ++j) left *= coset_of(j)[i] + ch.beta * pk.sigma_cosets[j][i] + ch.gamma;
-                    Fr right = z_cosets[s][i];
-                    for (uint32_t j = j0; j < j1; ++j) {
-                        right *= coset_of(j)[i] + current_delta + ch.gamma;
-                        current_delta *= FrConst::delta();
-                    }
-                    v = v * ch.y + (left - right) * pk.l_active_row[i];
-                }
-                h[i] = v;
-                beta_term *= dom.extended_omega;
-            }
-        });
-    }
-    // lookups
-    for (uint32_t l = 0; l < sh.L; ++l) {
-        Poly zc = dom.coeff_to_extended(lk_z_poly[l]);
-        Poly ac = dom.coeff_to_extended(perm_in_poly[l]);
-        Poly sc = dom.coeff_to_extended(perm_tab_poly[l]);
-        const Poly& in_c = advice_cosets[sh.A + l];
-        const Poly& tab_c = pk.fixed_cosets[sh.table_col()];
-        parallel_chunks(en, [&](size_t b, size_t e, int) {
-            for (size_t i = b; i < e; ++i) {
-                Fr table_value = (in_c[i] + ch.beta) * (tab_c[i] + ch.gamma);
-                size_t r_next = rot(i, 1), r_prev = rot(i, -1);
-                Fr a_minus_s = ac[i] - sc[i];
-                Fr v = h[i];
-                v = v * ch.y + (one - zc[i]) * pk.l0[i];
-                v = v * ch.y + (zc[i] * zc[i] - zc[i]) * pk.l_last[i];
-                v = v * ch.y + (zc[r_next] * (ac[i] + ch.beta) * (sc[i] + ch.gamma) - zc[i] * table_value) * pk.l_active_row[i];
-                v = v * ch.y + a_minus_s * pk.l0[i];
-                v = v * ch.y + a_minus_s * (ac[i] - ac[r_prev]) * pk.l_active_row[i];
-                h[i] = v;
-            }
-        });
-    }
-    // step 10: vanishing::construct (D.9)
-    dom.divide_by_vanishing_poly(h);
+    Poly h = evaluate_h(pk, dom, advice_cosets, z_cosets, lk_z_poly, perm_in_poly, perm_tab_poly, ch);
     Poly h_coeff = dom.extended_to_coeff(std::move(h));
     std::vector<Poly> h_pieces;
     for (uint32_t j = 0; j < dom.quotient_poly_degree; ++j) h_pieces.emplace_back(h_coeff.begin() + j * n, h_coeff.begin() + (j + 1) * n);

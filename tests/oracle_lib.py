@@ -265,6 +265,17 @@ class ProvingKey:
         self.last_seconds = secs.value
         return buf.tobytes()
 
+    def evaluate_h(self, advice_coeff, z_coeff, lookup_coeff, y, beta, gamma):
+        """evaluate_h + divide_by_vanishing_poly on coefficient-form inputs -> [4n, 4]"""
+        k, _, L, _ = self.shape
+        n = 1 << k
+        out = np.empty((4 * n, 4), dtype=np.uint64)
+        lk = np.ascontiguousarray(lookup_coeff) if L else None
+        ok = lib().oracle_evaluate_h(ctypes.c_void_p(self.h), ptr(np.ascontiguousarray(advice_coeff)), ptr(np.ascontiguousarray(z_coeff)),
+                                     ptr(lk) if L else None, ptr(y), ptr(beta), ptr(gamma), ptr(out))
+        assert ok, last_error()
+        return out
+
     def verify(self, proof, pairing=False):
         """verify_proof; `pairing=True` checks the opening with the real pairing equation instead of the trapdoor."""
         buf = np.frombuffer(proof, dtype=np.uint8)

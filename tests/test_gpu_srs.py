@@ -93,6 +93,13 @@ def test_srs_file_round_trip_and_g2(ctx):
     sg2 = tuple(O.from_mont(g2[1][i], Q) for i in range(4))
     want = _g2_scalar_mul(((gen[0], gen[1]), (gen[2], gen[3])), O.from_mont(s))
     assert sg2 == (want[0][0], want[0][1], want[1][0], want[1][1])
+    # the KZG relation of the file, trapdoor-free, with the oracle's pairing: e(g[i+1], g2) == e(g[i], s·g2)
+    g2_raw = np.frombuffer(raw[-256:], dtype=np.uint64).copy()
+    for i in (0, n - 2):
+        neg = g[i].copy()
+        neg[4:] = O.to_mont((Q - O.from_mont(g[i][4:], Q)) % Q, Q)
+        assert O.lib().oracle_pairing_product_is_one(O.ptr(np.ascontiguousarray(g[i + 1])), O.ptr(g2_raw[:16]), O.ptr(neg), O.ptr(g2_raw[16:])) == 1
+    assert O.lib().oracle_pairing_product_is_one(O.ptr(np.ascontiguousarray(g[2])), O.ptr(g2_raw[:16]), O.ptr(neg), O.ptr(g2_raw[16:])) == 0
     # read back (RawBytes) into the context: same bases, same commitments
     rng = np.random.default_rng(1)
     a = O.random_fr(rng, n)

@@ -222,3 +222,26 @@ def test_pairing_identities():
         a, b = rnd.randrange(1, O.R_MOD), rnd.randrange(1, O.R_MOD)
         mask = O.lib().oracle_pairing_selfcheck(O.ptr(O.to_mont(a)), O.ptr(O.to_mont(b)))
         assert mask == 63, bin(mask)
+
+
+def test_pairing_checks_the_kzg_relation_of_the_srs():
+    """e(g[i+1], g2) == e(g[i], s·g2) for the oracle's ParamsKZG::setup, with s·g2 from independent Python Fq2 arithmetic."""
+    from test_gpu_srs import Q, _g2_scalar_mul
+
+    gen = ((10857046999023057135944570762232829481370756359578518086990519993285655852781,
+            11559732032986387107991004021392285783925812861821192530917403151452391805634),
+           (8495653923123431417604973247489272438418190587263600148770280649306958101930,
+            4082367875863433681332203403145435568316851327593401208105741076214120093531))
+    s, g, _ = O.Params.setup(5).get()
+    sg2 = _g2_scalar_mul(gen, O.from_mont(s))
+    raw = lambda pt: np.concatenate([O.to_mont(c, Q) for c in (pt[0][0], pt[0][1], pt[1][0], pt[1][1])]).astype(np.uint64)
+    g2r, sg2r = raw(gen), raw(sg2)
+    check = O.lib().oracle_pairing_product_is_one
+    for i in (0, 30):
+        neg = g[i].copy()
+        neg[4:] = O.to_mont((Q - O.from_mont(g[i][4:], Q)) % Q, Q)
+        assert check(O.ptr(np.ascontiguousarray(g[i + 1])), O.ptr(g2r), O.ptr(neg), O.ptr(sg2r)) == 1
+    assert check(O.ptr(np.ascontiguousarray(g[2])), O.ptr(g2r), O.ptr(neg), O.ptr(sg2r)) == 0
+    off = g2r.copy()
+    off[0] ^= np.uint64(1)
+    assert check(O.ptr(np.ascontiguousarray(g[1])), O.ptr(off), O.ptr(neg), O.ptr(sg2r)) == -1  # not on the twist

@@ -1,8 +1,8 @@
 """BASELINE.json configs [2] and [3]: G1 MSM sweep (uniform / advice-like / sorted-lookup scalars) and Fr NTT sweep
-(forward, lagrange_to_coeff, coeff_to_extended, extended_to_coeff; batch 17), device-resident inputs, CUDA events on the
+(forward, lagrange_to_coeff, coeff_to_extended, extended_to_coeff; batches 17 and 29), device-resident inputs, CUDA events on the
 library's stream. Under torchrun the MSM sweep is sharded by point range across the ranks (partial sums over NCCL).
 
-    python tools/sweep.py [--max-k 24] [--out gpurun_out/sweep.json]
+    python tools/sweep.py [--max-k 26] [--out gpurun_out/sweep.json]
 """
 import argparse
 import json
@@ -18,7 +18,7 @@ import torch
 import b200zk
 
 p = argparse.ArgumentParser()
-p.add_argument("--max-k", type=int, default=24)
+p.add_argument("--max-k", type=int, default=26)
 p.add_argument("--min-k", type=int, default=16)
 p.add_argument("--out", default="gpurun_out/sweep.json")
 p.add_argument("--no-ntt", action="store_true")
@@ -109,15 +109,16 @@ for k in range(args.min_k, kmax + 1, 2):
             print("msm", k, kind, round(ms, 3), "ms", round(n / ms / 1e3, 1), "Mpts/s", flush=True)
         del buf
 if not args.no_ntt and world == 1:
-    B = 17
-    for k in range(args.min_k, min(kmax, 24) + 1, 2):
+    root = np.array([[0xd34f1ed960c37c9c, 0x3215cf6dd39329c8, 0x98865ea93dd31f74, 0x03ddb9f5166d18b7]], dtype=np.uint64)
+    cases = [(k, B) for B in (17, 29) for k in range(args.min_k, min(kmax, 22) + 1, 2)]  # S20-bn's and S22-gl's A+L
+    if kmax >= 24:
+        cases.append((24, 4))
+    for k, batch in cases:
         n = 1 << k
-        batch = B if k <= 22 else 4
         col = rng.integers(0, 1 << 62, size=(n, 4), dtype=np.uint64)
         buf = torch.empty(batch * n * 4, dtype=torch.int64, device="cuda")
         for b in range(batch):
             ctx.h2d(buf.data_ptr() + 32 * n * b, col)
-        root = np.array([[0xd34f1ed960c37c9c, 0x3215cf6dd39329c8, 0x98865ea93dd31f74, 0x03ddb9f5166d18b7]], dtype=np.uint64)
         w = ctx.field_vec_op(0, 6, root)
         for _ in range(28 - k):
             w = ctx.field_vec_op(0, 2, w, w)
@@ -125,19 +126,18 @@ if not args.no_ntt and world == 1:
         ms_f = timed(lambda: ctx.ntt_dev(buf.data_ptr(), k, omega, batch, n), 5)
         row = {"batch": batch, "forward_ms": ms_f, "forward_GBps_64nB": 64.0 * n * batch / ms_f / 1e6, "forward_frac_hbm": 64.0 * n * batch / ms_f / 1e6 / HBM,
                "Gbutterfly_s": batch * (n // 2) * k / ms_f / 1e6}
-        if k + 2 <= 26:
-            ms_l = timed(lambda: ctx.lagrange_to_coeff_dev(k, buf.data_ptr(), batch, n), 5)
-            row["lagrange_to_coeff_ms"] = ms_l
-            ext = torch.empty(4 * n * 4, dtype=torch.int64, device="cuda")
-            ms_c = timed(lambda: ctx.coeff_to_extended_dev(k, buf.data_ptr(), ext.data_ptr()), 5)
-            row["coeff_to_extended_ms"] = ms_c
-            row["coeff_to_extended_GBps_160n"] = 160.0 * n / ms_c / 1e6
-            out3 = torch.empty(3 * n * 4, dtype=torch.int64, device="cuda")
-            ms_e = timed(lambda: ctx.extended_to_coeff_dev(k, ext.data_ptr(), out3.data_ptr()), 5)
-            row["extended_to_coeff_ms"] = ms_e
-            row["extended_to_coeff_GBps_224n"] = 224.0 * n / ms_e / 1e6
-            del ext, out3
-        res["ntt"][f"2^{k}"] = row
+        ms_l = timed(lambda: ctx.lagrange_to_coeff_dev(k, buf.data_ptr(), batch, n), 5)
+        row["lagrange_to_coeff_ms"] = ms_l
+        ext = torch.empty(4 * n * 4, dtype=torch.int64, device="cuda")
+        ms_c = timed(lambda: ctx.coeff_to_extended_dev(k, buf.data_ptr(), ext.data_ptr()), 5)
+        row["coeff_to_extended_ms"] = ms_c
+        row["coeff_to_extended_GBps_160n"] = 160.0 * n / ms_c / 1e6
+        out3 = torch.empty(3 * n * 4, dtype=torch.int64, device="cuda")
+        ms_e = timed(lambda: ctx.extended_to_coeff_dev(k, ext.data_ptr(), out3.data_ptr()), 5)
+        row["extended_to_coeff_ms"] = ms_e
+        row["extended_to_coeff_GBps_224n"] = 224.0 * n / ms_e / 1e6
+        del ext, out3
+        res["ntt"][f"2^{k}/B{batch}"] = row
         print("ntt", k, {a: (round(b, 3) if isinstance(b, float) else b) for a, b in row.items()}, flush=True)
         del buf
 if rank == 0:

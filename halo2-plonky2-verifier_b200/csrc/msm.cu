@@ -62,6 +62,8 @@ MsmConfig msm_config_merged(uint32_t c, size_t table_n) {
     m.table_n = table_n;
     return m;
 }
+// measured at S20-bn / S22-bn: the msm stage is flat for caps 17..21 (fewer buckets trade against more windows) and
+// worse below 16; 20 keeps the table smallest
 uint32_t msm_table_window_bits(uint32_t k) { return k < 8 ? 8 : (k > 20 ? 20 : k); }
 
 DEV G1X g1x_load(const G1X* p) {
@@ -92,8 +94,10 @@ constexpr int MAX_W = 64;
 // mode 0: histogram; mode 1: scatter (counters = running offsets)
 __global__ void msm_digits_kernel(const Fr* scalars, size_t n, MsmConfig cfg, uint32_t* counters, uint32_t* entries, int mode) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const Fr s = f_from_mont(f_load(scalars + i));
+    const bool valid = i < n;  // no early exit: the warp votes below need every lane
+    const uint32_t lane = threadIdx.x & 31, lanes_below = (1u << lane) - 1;
+    Fr s = f_zero<FrCfg>();
+    if (valid) s = f_from_mont(f_load(scalars + i));
     const uint32_t c = cfg.c, mask = (1u << c) - 1, halfv = 1u << (c - 1);
     uint32_t carry = 0;
     for (uint32_t w = 0; w < cfg.W; ++w) {
@@ -113,14 +117,23 @@ __global__ void msm_digits_kernel(const Fr* scalars, size_t n, MsmConfig cfg, ui
         const bool neg = v > halfv;
         const uint32_t mag = neg ? (1u << c) - v : v;
         carry = neg ? 1u : 0u;
-        if (mag == 0) continue;
+        const bool act = valid && mag != 0;
+        if (!__any_sync(0xffffffffu, act)) continue;
         const uint32_t bucket = cfg.merged ? mag - 1 : w * cfg.B + mag - 1;
-        if (mode == 0) {
-            atomicAdd(counters + bucket, 1u);
-        } else {
-            const uint32_t pos = atomicAdd(counters + bucket, 1u);
-            const uint32_t base_index = cfg.merged ? (uint32_t)(w * cfg.table_n + i) : (uint32_t)i;
-            entries[pos] = base_index | (neg ? 0x80000000u : 0u);
+        // Warp-aggregated atomics: lanes that hit the same bucket elect a leader that adds the group size once. Range-check
+        // witnesses put most carries of the low window into buckets 0 and 1 — without this those two counters serialise
+        // ~10^6 atomics per column (0.37 ms per pass, profiles/launches_msm_batch4_r01.csv.gz).
+        const uint32_t key = act ? bucket : 0xffffffe0u + lane;  // idle lanes: singleton groups (buckets stay below 2^31)
+        const uint32_t peers = __match_any_sync(0xffffffffu, key);
+        const uint32_t leader = __ffs(peers) - 1, cnt = __popc(peers), rank = __popc(peers & lanes_below);
+        uint32_t base = 0;
+        if (act && lane == leader) base = atomicAdd(counters + bucket, cnt);
+        if (mode != 0) {
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (act) {
+                const uint32_t base_index = cfg.merged ? (uint32_t)(w * cfg.table_n + i) : (uint32_t)i;
+                entries[base + rank] = base_index | (neg ? 0x80000000u : 0u);
+            }
         }
     }
 }
@@ -194,7 +207,7 @@ DEV uint32_t find_bucket(const uint32_t* offsets, uint32_t nb, uint32_t p) {
 }
 
 constexpr int ACC_T_MIN = 16, ACC_T_MAX = 64;  // entries per thread, level 1 (chosen per launch, see pick_chunk)
-constexpr int COMB_T = 16;       // partial sums per thread, levels >= 2
+constexpr int COMB_T = 32;       // fan-in of the head combine levels (one warp per COMB_T partial sums)
 constexpr int ACC_THREADS = 128;
 
 __global__ void __launch_bounds__(ACC_THREADS) msm_accumulate_kernel(const G1Affine* bases, const uint32_t* entries, const uint32_t* offsets,
@@ -228,39 +241,40 @@ __global__ void __launch_bounds__(ACC_THREADS) msm_accumulate_kernel(const G1Aff
     g1x_store(started_before ? heads + t : bucket_sums + cur, acc);
 }
 
-// segmented sum of a key-sorted list of partial sums (INVALID_KEY entries are holes)
+// Segmented sum of a key-sorted list of partial sums (INVALID_KEY entries are holes), one entry per lane: a 5-step shuffle
+// scan leaves the total of every run of equal keys in the run's first lane. A run that starts inside the warp is added into
+// its bucket (one writer per bucket and launch); the part of a run that began in an earlier warp goes to the next level,
+// which is 32x shorter. Latency per level: at most 5 dependent additions.
+DEV G1X g1x_shfl_down(const G1X& v, uint32_t d) {
+    G1X r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        r.x.l[i] = __shfl_down_sync(0xffffffffu, v.x.l[i], d);
+        r.y.l[i] = __shfl_down_sync(0xffffffffu, v.y.l[i], d);
+        r.zz.l[i] = __shfl_down_sync(0xffffffffu, v.zz.l[i], d);
+        r.zzz.l[i] = __shfl_down_sync(0xffffffffu, v.zzz.l[i], d);
+    }
+    return r;
+}
 __global__ void __launch_bounds__(ACC_THREADS) msm_combine_kernel(const G1X* pts, const uint32_t* keys, uint32_t n, G1X* bucket_sums, G1X* heads_out,
                                                                   uint32_t* keys_out) {
-    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t p0l = (uint64_t)u * COMB_T;
-    if (p0l >= n) return;
-    const uint32_t p0 = (uint32_t)p0l;
-    const uint32_t p1 = n - p0 > (uint32_t)COMB_T ? p0 + COMB_T : n;
-    bool have = false, started_before = false;
-    uint32_t cur = INVALID_KEY, out_key = INVALID_KEY;
-    G1X acc = g1x_identity();
-    for (uint32_t p = p0; p < p1; ++p) {
-        const uint32_t k = __ldg(keys + p);
-        if (have && k != cur) {
-            if (started_before) g1x_store(heads_out + u, acc);
-            else g1x_store(bucket_sums + cur, g1x_add(g1x_load(bucket_sums + cur), acc));
-            have = false;
-        }
-        if (k == INVALID_KEY) continue;
-        if (!have) {
-            cur = k;
-            have = true;
-            acc = g1x_identity();
-            started_before = p == p0 && p0 > 0 && __ldg(keys + p0 - 1) == k;
-            if (started_before) out_key = k;
-        }
-        acc = g1x_add(acc, g1x_load(pts + p));
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31, warp = p >> 5;
+    if ((p & ~31u) >= n) return;  // whole warps only
+    const uint32_t key = p < n ? __ldg(keys + p) : INVALID_KEY;
+    const bool live = key != INVALID_KEY;
+    G1X acc = live ? g1x_load(pts + p) : g1x_identity();
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+        const uint32_t okey = __shfl_down_sync(0xffffffffu, key, d);
+        const G1X o = g1x_shfl_down(acc, d);
+        if (live && lane + d < 32 && okey == key) acc = g1x_add(acc, o);
     }
-    if (have) {
-        if (started_before) g1x_store(heads_out + u, acc);
-        else g1x_store(bucket_sums + cur, g1x_add(g1x_load(bucket_sums + cur), acc));
-    }
-    keys_out[u] = out_key;
+    uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+    if (lane == 0) prev = p > 0 ? __ldg(keys + p - 1) : INVALID_KEY;
+    const bool run_start = live && (lane == 0 || prev != key);
+    const bool started_before = live && lane == 0 && prev == key;
+    if (started_before) g1x_store(heads_out + warp, acc);
+    else if (run_start) g1x_store(bucket_sums + key, g1x_add(g1x_load(bucket_sums + key), acc));
+    if (lane == 0) keys_out[warp] = started_before ? key : INVALID_KEY;
 }
 
 // ---- bucket reduction: per window F(B) = sum_b (b+1)·B[b] ---------------------------------------------------
@@ -383,7 +397,7 @@ static void msm_issue_accumulate(MsmSlot& sl, const G1Affine* bases, const Fr* s
     prof_end(s);
     ++g_launch_count;
     CUDA_CHECK(cudaGetLastError());
-    // levels >= 2: segment-sum the head list until a single thread covers it
+    // levels >= 2: segment-sum the head list until a single warp covers it
     uint32_t len = nthreads;
     bool flip = false;
     while (true) {
@@ -392,10 +406,10 @@ static void msm_issue_accumulate(MsmSlot& sl, const G1Affine* bases, const Fr* s
         uint32_t* in_k = flip ? sl.keys_b.get() : sl.keys_a.get();
         G1X* out_p = flip ? sl.heads_a.get() : sl.heads_b.get();
         uint32_t* out_k = flip ? sl.keys_a.get() : sl.keys_b.get();
-        msm_combine_kernel<<<(nt + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, s>>>(in_p, in_k, len, bucket_sums, out_p, out_k);
+        msm_combine_kernel<<<(len + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, s>>>(in_p, in_k, len, bucket_sums, out_p, out_k);
         ++g_launch_count;
         CUDA_CHECK(cudaGetLastError());
-        if (nt == 1) break;  // a single thread has no predecessor: nothing can be left in its head slot
+        if (nt == 1) break;  // a single warp has no predecessor: nothing can be left in its head slot
         len = nt;
         flip = !flip;
     }

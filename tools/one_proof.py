@@ -10,5 +10,5 @@ ctx.srs_setup(k)
 fixed, advice, copies = b200zk.synth_circuit(k, A, L, F, seed=0)
 pk = ctx.keygen(k, A, L, F, fixed, copies)
 for _ in range(reps):
-    t = time.time(); proof = pk.create_proof(advice, 0); print("proof s", round(time.time() - t, 4), flush=True)
+    t = time.time(); proof, tm = pk.create_proof(advice, 0, timings=True); print("proof s", round(time.time() - t, 4), {a: round(b * 1e3, 1) for a, b in tm.items()}, flush=True)
 os._exit(0)

@@ -513,8 +513,8 @@ static void msm_batch_core(Context& ctx, const G1Affine* bases, const Fr* const*
     size_t lo = 0, len = n;
     if (shard_points) shard_range(ctx, n, lo, len);
     const uint32_t nb = cfg.groups * cfg.B;
-    // bound the scratch: at most 16 columns (≈1 GiB of bucket sums at c = 20) per reduction round
-    const size_t round = 16;
+    // bound the scratch: at most 32 columns (≈2 GiB of bucket sums at c = 20) per reduction round
+    const size_t round = 32;
     for (size_t c0 = 0; c0 < ncols; c0 += round) {
         const size_t nc = std::min(round, ncols - c0);
         DevBuf<G1X> bucket_sums((size_t)nc * nb, s);

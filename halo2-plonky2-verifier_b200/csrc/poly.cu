@@ -105,7 +105,8 @@ __global__ void __launch_bounds__(128) batch_invert_kernel(Fr* a, Fr* scratch, s
 }
 void fr_batch_invert(Fr* a, size_t n, cudaStream_t s) {
     if (!n) return;
-    size_t per = n >= ((size_t)1 << 18) ? 64 : (n >= 4096 ? 16 : 4);
+    // elements per inversion: longer groups amortise the ~380-product inversion, shorter ones keep enough threads in flight
+    size_t per = n >= ((size_t)1 << 22) ? 128 : (n >= ((size_t)1 << 18) ? 64 : (n >= 4096 ? 16 : 4));
     size_t G = (n + per - 1) / per;
     DevBuf<Fr> scratch(n, s);
     batch_invert_kernel<<<nblocks(G, 128), 128, 0, s>>>(a, scratch.get(), n, G);

@@ -517,55 +517,55 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
     };
     DevBuf<Fr> z_polys((size_t)NS * n, s), z_cosets((size_t)NS * en, s);
     {
-        DevBuf<Fr> m(n, s);
         std::vector<Fr> dpow(P);  // delta^j·beta for permutation column j
         dpow[0] = beta;
         for (uint32_t j = 1; j < P; ++j) dpow[j] = f_mul(dpow[j - 1], FrConsts::delta());
-        // Sharded: set s is built by rank s mod world (the rank that also commits and transforms it). The chain
-        // z_s[0] = z_{s-1}[n-bf-1] only couples the sets through one scalar, so every owner first builds its running product
-        // from 1, the end values E_s are exchanged, and each owner rescales by the carry prod_{t<s} E_t.
+        // The chain z_s[0] = z_{s-1}[n-bf-1] only couples the sets through one scalar: every set is first built as a running
+        // product from 1 (all denominators inverted by ONE batch inversion), then the end values E_s are read back and set s
+        // is rescaled by the carry prod_{t<s} E_t — the same field elements as the sequential chain, without a host round
+        // trip per set. Sharded: set s is built by rank s mod world (the rank that also commits and transforms it) and the
+        // end values are exchanged.
         const bool dist_sets = shard.on() && NS >= (uint32_t)ctx.world;
+        auto builds = [&](uint32_t set) { return !dist_sets || shard.mine(set); };
+        std::vector<uint32_t> my_sets;
+        for (uint32_t set = 0; set < NS; ++set)
+            if (builds(set)) my_sets.push_back(set);
         std::vector<Fr> E(NS, f_zero<FrCfg>());
-        Fr last_z = one;
-        for (uint32_t set = 0; set < NS; ++set) {
-            Fr* z = z_polys.get() + (size_t)set * n;  // Lagrange values first, converted in place after the commit
-            const uint32_t j0 = set * Shape::chunk_len, j1 = std::min(P, j0 + Shape::chunk_len);
-            if (!dist_sets || shard.mine(set)) {
-                for (uint32_t j = j0; j < j1; ++j) perm_denominator(m.get(), perm_values(j), pk.sigma_values.get() + (size_t)j * n, beta, gamma, n, j == j0, s);
-                fr_batch_invert(m.get(), n, s);
-                for (uint32_t j = j0; j < j1; ++j) perm_numerator(m.get(), perm_values(j), dpow[j], gamma, tw.t.get(), tw.log_n, sh.k, s);
-                fr_prefix_product(z, m.get(), dist_sets ? one : last_z, n, s);
+        {
+            DevBuf<Fr> m(my_sets.size() * n, s);
+            for (size_t li = 0; li < my_sets.size(); ++li) {
+                const uint32_t j0 = my_sets[li] * Shape::chunk_len, j1 = std::min(P, j0 + Shape::chunk_len);
+                for (uint32_t j = j0; j < j1; ++j)
+                    perm_denominator(m.get() + li * n, perm_values(j), pk.sigma_values.get() + (size_t)j * n, beta, gamma, n, j == j0, s);
             }
-            if (!dist_sets) {
-                std::vector<Fr> blind(bf);
-                for (auto& b : blind) b = rng.next();
-                CUDA_CHECK(cudaMemcpyAsync(z + (n - bf), blind.data(), bf * sizeof(Fr), cudaMemcpyHostToDevice, s));
-                CUDA_CHECK(cudaMemcpyAsync(&last_z, z + (n - bf - 1), sizeof(Fr), cudaMemcpyDeviceToHost, s));
-                CUDA_CHECK(cudaStreamSynchronize(s));
-                rng.skip(1);
-            } else if (shard.mine(set)) {
+            fr_batch_invert(m.get(), my_sets.size() * n, s);
+            for (size_t li = 0; li < my_sets.size(); ++li) {
+                const uint32_t set = my_sets[li], j0 = set * Shape::chunk_len, j1 = std::min(P, j0 + Shape::chunk_len);
+                Fr* z = z_polys.get() + (size_t)set * n;  // Lagrange values first, converted in place after the commit
+                for (uint32_t j = j0; j < j1; ++j) perm_numerator(m.get() + li * n, perm_values(j), dpow[j], gamma, tw.t.get(), tw.log_n, sh.k, s);
+                fr_prefix_product(z, m.get() + li * n, one, n, s);
                 CUDA_CHECK(cudaMemcpyAsync(&E[set], z + (n - bf - 1), sizeof(Fr), cudaMemcpyDeviceToHost, s));
             }
+            CUDA_CHECK(cudaStreamSynchronize(s));
         }
         if (dist_sets) {
-            CUDA_CHECK(cudaStreamSynchronize(s));
             std::vector<Fr> all((size_t)NS * ctx.world);
             if (ctx.allgather(ctx.allgather_user, E.data(), NS * sizeof(Fr), all.data()) != 0) throw std::runtime_error("grand-product exchange failed");
             for (uint32_t set = 0; set < NS; ++set) E[set] = all[(size_t)shard.owner(set) * NS + set];
-            Fr carry = one;
-            for (uint32_t set = 0; set < NS; ++set) {
-                Fr* z = z_polys.get() + (size_t)set * n;
-                std::vector<Fr> blind(bf);
-                for (auto& b : blind) b = rng.next();  // every rank draws every value: the streams stay in step
-                rng.skip(1);
-                if (shard.mine(set)) {
-                    if (set > 0) fr_scale(z, carry, n, s);
-                    CUDA_CHECK(cudaMemcpyAsync(z + (n - bf), blind.data(), bf * sizeof(Fr), cudaMemcpyHostToDevice, s));
-                    CUDA_CHECK(cudaStreamSynchronize(s));
-                }
-                carry = f_mul(carry, E[set]);
-            }
         }
+        std::vector<Fr> blind((size_t)NS * bf);
+        Fr carry = one;
+        for (uint32_t set = 0; set < NS; ++set) {
+            Fr* z = z_polys.get() + (size_t)set * n;
+            for (uint32_t i = 0; i < bf; ++i) blind[(size_t)set * bf + i] = rng.next();  // every rank draws every value: the streams stay in step
+            rng.skip(1);
+            if (builds(set)) {
+                if (set > 0) fr_scale(z, carry, n, s);
+                CUDA_CHECK(cudaMemcpyAsync(z + (n - bf), blind.data() + (size_t)set * bf, bf * sizeof(Fr), cudaMemcpyHostToDevice, s));
+            }
+            carry = f_mul(carry, E[set]);
+        }
+        CUDA_CHECK(cudaStreamSynchronize(s));
         lap(tm ? &tm->products : nullptr);
         const std::vector<G1Affine> cms = commit_batch(ctx, 1, z_polys.get(), n, NS, n);
         lap(tm ? &tm->msm : nullptr);
@@ -589,20 +589,28 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
     // step 6: lookup grand products (D.6)
     DevBuf<Fr> lk_z_poly((size_t)L * n, s);
     {
-        DevBuf<Fr> p(n, s);
-        for (uint32_t l = 0; l < L; ++l) {  // sharded: lookup l is built by rank l mod world and broadcast
-            Fr* z = lk_z_poly.get() + (size_t)l * n;
-            std::vector<Fr> blind(bf);
-            for (auto& b : blind) b = rng.next();
+        // sharded: lookup l is built by rank l mod world and broadcast; one batch inversion serves all of a rank's lookups
+        std::vector<Fr> blind((size_t)L * bf);
+        std::vector<uint32_t> my_lookups;
+        for (uint32_t l = 0; l < L; ++l) {
+            for (uint32_t i = 0; i < bf; ++i) blind[(size_t)l * bf + i] = rng.next();
             rng.skip(1);
-            if (!shard.mine(l)) continue;
-            lookup_denominator(p.get(), perm_in.get() + (size_t)l * n, perm_tab.get() + (size_t)l * n, beta, gamma, n, s);
-            fr_batch_invert(p.get(), n, s);
-            lookup_numerator(p.get(), advice.get() + (size_t)(A + l) * n, table_values, beta, gamma, n, s);
-            fr_prefix_product(z, p.get(), one, n, s);
-            CUDA_CHECK(cudaMemcpyAsync(z + (n - bf), blind.data(), bf * sizeof(Fr), cudaMemcpyHostToDevice, s));
-            CUDA_CHECK(cudaStreamSynchronize(s));
+            if (shard.mine(l)) my_lookups.push_back(l);
         }
+        DevBuf<Fr> p(my_lookups.size() * n, s);
+        for (size_t li = 0; li < my_lookups.size(); ++li) {
+            const uint32_t l = my_lookups[li];
+            lookup_denominator(p.get() + li * n, perm_in.get() + (size_t)l * n, perm_tab.get() + (size_t)l * n, beta, gamma, n, s);
+        }
+        fr_batch_invert(p.get(), my_lookups.size() * n, s);
+        for (size_t li = 0; li < my_lookups.size(); ++li) {
+            const uint32_t l = my_lookups[li];
+            Fr* z = lk_z_poly.get() + (size_t)l * n;
+            lookup_numerator(p.get() + li * n, advice.get() + (size_t)(A + l) * n, table_values, beta, gamma, n, s);
+            fr_prefix_product(z, p.get() + li * n, one, n, s);
+            CUDA_CHECK(cudaMemcpyAsync(z + (n - bf), blind.data() + (size_t)l * bf, bf * sizeof(Fr), cudaMemcpyHostToDevice, s));
+        }
+        CUDA_CHECK(cudaStreamSynchronize(s));
         shard.allgather_columns(lk_z_poly.get(), L, n);
         lap(tm ? &tm->products : nullptr);
         const std::vector<G1Affine> cms = commit_batch(ctx, 1, lk_z_poly.get(), n, L, n);

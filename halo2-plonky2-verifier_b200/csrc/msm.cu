@@ -506,8 +506,9 @@ static void check_cfg(const MsmConfig& cfg, size_t n) {
 }
 // `ncols` MSMs over the same bases: per-column bucket accumulation, ONE reduction for all columns, one exchange across ranks.
 // `bases_origin`: index of the point that bases[0] corresponds to (non-zero when `bases` is a per-shard window table)
+// `col_bases` (optional): one base pointer per column, for batches that mix the coefficient and the Lagrange basis.
 static void msm_batch_core(Context& ctx, const G1Affine* bases, const Fr* const* cols, size_t ncols, size_t n, const MsmConfig& cfg, G1Affine* out,
-                           size_t bases_origin, bool shard_points) {
+                           size_t bases_origin, bool shard_points, const G1Affine* const* col_bases = nullptr) {
     check_cfg(cfg, n);
     cudaStream_t s = ctx.stream;
     size_t lo = 0, len = n;
@@ -533,10 +534,10 @@ static void msm_batch_core(Context& ctx, const G1Affine* bases, const Fr* const*
                 CUDA_CHECK(cudaEventRecord(ctx.msm_fork, s));
                 for (int q = 1; q < nslots; ++q) CUDA_CHECK(cudaStreamWaitEvent(ctx.aux_streams[q - 1], ctx.msm_fork, 0));
             }
-            const G1Affine* b = bases + (lo - bases_origin);
             for (size_t j = 0; j < (size_t)nslots && j < nc; ++j) msm_issue_count(slots[j], cols[c0 + j] + lo, len, cfg);
             for (size_t j = 0; j < nc; ++j) {
                 MsmSlot& sl = slots[j % nslots];
+                const G1Affine* b = (col_bases ? col_bases[c0 + j] : bases) + (lo - bases_origin);
                 msm_issue_accumulate(sl, b, cols[c0 + j] + lo, len, cfg, bucket_sums.get() + j * nb);
                 if (j + nslots < nc) msm_issue_count(sl, cols[c0 + j + nslots] + lo, len, cfg);
             }
@@ -566,15 +567,32 @@ G1Affine msm_run(Context& ctx, const G1Affine* bases, const Fr* scalars, size_t 
 // COLUMN — rank r commits columns r, r+world, ... over the full point range and the 64-byte results are all-gathered —
 // while smaller batches (the random polynomial, h pieces, SHPLONK quotients) are split by POINT RANGE with the partial
 // bucket sums exchanged.
-static void msm_batch_srs_local(Context& ctx, int basis, const Fr* const* cols, size_t ncols, size_t n, G1Affine* out, bool shard_points) {
+// `basis[j]` selects g (0) or g_lagrange (1) for column j
+static void msm_batch_srs_local(Context& ctx, const int* basis, const Fr* const* cols, size_t ncols, size_t n, G1Affine* out, bool shard_points) {
+    if (ncols == 0) return;
     const Srs& srs = *ctx.srs;
-    const DevBuf<G1Affine>& tab = basis == 0 ? srs.g_tab : srs.gl_tab;
-    if (tab.size() == 0 || n * 8 < srs.n)
-        msm_batch_core(ctx, basis == 0 ? srs.g.get() : srs.g_lagrange.get(), cols, ncols, n, msm_config(n), out, 0, shard_points);
-    else
-        msm_batch_core(ctx, tab.get(), cols, ncols, n, msm_config_merged(srs.tab_c, srs.n), out, 0, shard_points);
+    bool uniform = true;
+    for (size_t j = 1; j < ncols; ++j) uniform = uniform && basis[j] == basis[0];
+    const bool tables = srs.g_tab.size() != 0 && srs.gl_tab.size() != 0 && n * 8 >= srs.n;
+    if (!uniform && !tables) {  // without both window tables the two bases use different configurations: one call per run
+        for (size_t j0 = 0; j0 < ncols;) {
+            size_t j1 = j0 + 1;
+            while (j1 < ncols && basis[j1] == basis[j0]) ++j1;
+            msm_batch_srs_local(ctx, basis + j0, cols + j0, j1 - j0, n, out + j0, shard_points);
+            j0 = j1;
+        }
+        return;
+    }
+    const DevBuf<G1Affine>& tab = basis[0] == 0 ? srs.g_tab : srs.gl_tab;
+    if (uniform && (tab.size() == 0 || n * 8 < srs.n)) {
+        msm_batch_core(ctx, basis[0] == 0 ? srs.g.get() : srs.g_lagrange.get(), cols, ncols, n, msm_config(n), out, 0, shard_points);
+        return;
+    }
+    std::vector<const G1Affine*> col_bases(ncols);
+    for (size_t j = 0; j < ncols; ++j) col_bases[j] = basis[j] == 0 ? srs.g_tab.get() : srs.gl_tab.get();
+    msm_batch_core(ctx, tab.get(), cols, ncols, n, msm_config_merged(srs.tab_c, srs.n), out, 0, shard_points, uniform ? nullptr : col_bases.data());
 }
-void msm_batch_srs(Context& ctx, int basis, const Fr* const* cols, size_t ncols, size_t n, G1Affine* out) {
+void msm_batch_srs_mixed(Context& ctx, const int* basis, const Fr* const* cols, size_t ncols, size_t n, G1Affine* out) {
     const bool dist = ctx.world > 1 && ctx.allgather;
     if (!dist || ncols < (size_t)ctx.world) {
         msm_batch_srs_local(ctx, basis, cols, ncols, n, out, dist);
@@ -582,14 +600,22 @@ void msm_batch_srs(Context& ctx, int basis, const Fr* const* cols, size_t ncols,
     }
     const size_t world = ctx.world, per = (ncols + world - 1) / world;
     std::vector<const Fr*> mine;
-    for (size_t j = ctx.rank; j < ncols; j += world) mine.push_back(cols[j]);
+    std::vector<int> mine_basis;
+    for (size_t j = ctx.rank; j < ncols; j += world) {
+        mine.push_back(cols[j]);
+        mine_basis.push_back(basis[j]);
+    }
     std::vector<G1Affine> send(per), recv(per * world);
     memset(send.data(), 0, per * sizeof(G1Affine));
-    if (!mine.empty()) msm_batch_srs_local(ctx, basis, mine.data(), mine.size(), n, send.data(), false);
+    if (!mine.empty()) msm_batch_srs_local(ctx, mine_basis.data(), mine.data(), mine.size(), n, send.data(), false);
     const auto t0 = std::chrono::steady_clock::now();
     if (ctx.allgather(ctx.allgather_user, send.data(), per * sizeof(G1Affine), recv.data()) != 0) throw std::runtime_error("msm: all-gather callback failed");
     g_exchange_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     for (size_t j = 0; j < ncols; ++j) out[j] = recv[(j % world) * per + j / world];
+}
+void msm_batch_srs(Context& ctx, int basis, const Fr* const* cols, size_t ncols, size_t n, G1Affine* out) {
+    std::vector<int> b(ncols, basis);
+    msm_batch_srs_mixed(ctx, b.data(), cols, ncols, n, out);
 }
 G1Affine msm_run_srs(Context& ctx, int basis, const Fr* scalars, size_t n) {
     G1Affine r;

@@ -86,13 +86,15 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(PassParams P) {
         lo_base = (tile & ((1u << lo_tiles_log) - 1)) << P.logC;
     }
     // ---- load ----
-    for (uint32_t e = tid; e < T; e += NTT_THREADS) {
-        const uint32_t c = e & (C - 1), m = e >> P.logC;
+    // zero-padded to 4x (skip2): after the bit reversal only every fourth row holds data and the first two stages just copy
+    // it into the three rows above, so each distinct element is loaded and pre-scaled ONCE and stored four times
+    const uint32_t load_rows_log = P.skip2 ? 2 : 0;
+    for (uint32_t e = tid; e < (T >> load_rows_log); e += NTT_THREADS) {
+        const uint32_t c = e & (C - 1), m = (e >> P.logC) << load_rows_log;
         size_t src;
         if (P.first) {
             const uint32_t hrev = tile * C + c;  // bit-reversed `hi`
-            const uint32_t msrc = P.skip2 ? (m & ~3u) : m;
-            const uint32_t mrev = P.r ? (__brev(msrc) >> (32 - P.r)) : 0;
+            const uint32_t mrev = P.r ? (__brev(m) >> (32 - P.r)) : 0;
             src = ((size_t)mrev << (P.L - P.r)) + hrev;
         } else {
             src = ((size_t)hi << s1) + ((size_t)m << P.s0) + lo_base + c;
@@ -108,6 +110,11 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(PassParams P) {
             }
         }
         tile_put(slo, shi, swz(m, c, P.logC), v);
+        if (P.skip2) {
+            tile_put(slo, shi, swz(m + 1, c, P.logC), v);
+            tile_put(slo, shi, swz(m + 2, c, P.logC), v);
+            tile_put(slo, shi, swz(m + 3, c, P.logC), v);
+        }
     }
     __syncthreads();
     // ---- butterflies ----

@@ -17,6 +17,7 @@ namespace b200zk {
 G1Affine msm_run_srs(Context& ctx, int basis, const Fr* scalars, size_t n);
 extern double g_exchange_seconds;
 void msm_batch_srs(Context& ctx, int basis, const Fr* const* cols, size_t ncols, size_t n, G1Affine* out);
+void msm_batch_srs_mixed(Context& ctx, const int* basis, const Fr* const* cols, size_t ncols, size_t n, G1Affine* out);
 
 static const Srs& need_srs(Context& ctx, uint32_t k) {
     if (!ctx.srs) throw std::runtime_error("no SRS loaded");
@@ -567,24 +568,6 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
         }
         CUDA_CHECK(cudaStreamSynchronize(s));
         lap(tm ? &tm->products : nullptr);
-        const std::vector<G1Affine> cms = commit_batch(ctx, 1, z_polys.get(), n, NS, n);
-        lap(tm ? &tm->msm : nullptr);
-        if (!shard.on()) {
-            dev_lagrange_to_coeff(ctx, sh.k, z_polys.get(), NS, n);
-            for (uint32_t set = 0; set < NS; ++set) dev_coeff_to_extended(ctx, sh.k, z_polys.get() + (size_t)set * n, z_cosets.get() + (size_t)set * en);
-        } else {
-            for (uint32_t set = 0; set < NS; ++set)
-                if (shard.mine(set)) {
-                    dev_lagrange_to_coeff(ctx, sh.k, z_polys.get() + (size_t)set * n);
-                    dev_coeff_to_extended(ctx, sh.k, z_polys.get() + (size_t)set * n, z_cosets.get() + (size_t)set * en);
-                }
-            shard.allgather_columns(z_polys.get(), NS, n);
-            std::vector<Fr*> cs(NS);
-            for (uint32_t set = 0; set < NS; ++set) cs[set] = z_cosets.get() + (size_t)set * en;
-            shard.exchange_row_slices(cs.data(), NS, [&](size_t c) { return shard.owner(c); }, en, HALO_BEFORE, HALO_AFTER);
-        }
-        lap(tm ? &tm->ntt : nullptr);
-        for (const G1Affine& cm : cms) tr.write_point(cm);
     }
     // step 6: lookup grand products (D.6)
     DevBuf<Fr> lk_z_poly((size_t)L * n, s);
@@ -613,11 +596,6 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
         CUDA_CHECK(cudaStreamSynchronize(s));
         shard.allgather_columns(lk_z_poly.get(), L, n);
         lap(tm ? &tm->products : nullptr);
-        const std::vector<G1Affine> cms = commit_batch(ctx, 1, lk_z_poly.get(), n, L, n);
-        lap(tm ? &tm->msm : nullptr);
-        if (L) dev_lagrange_to_coeff(ctx, sh.k, lk_z_poly.get(), L, n);
-        lap(tm ? &tm->ntt : nullptr);
-        for (const G1Affine& cm : cms) tr.write_point(cm);
     }
     // step 7: vanishing::commit (D.7): n sequential Fr::random draws = n consecutive ChaCha blocks, generated in place
     DevBuf<Fr> random_poly(n, s);
@@ -625,8 +603,36 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
     rng.skip(n);
     rng.skip(1);
     lap(tm ? &tm->other : nullptr);
-    tr.write_point(commit_coeff(ctx, random_poly.get(), n));
-    lap(tm ? &tm->msm : nullptr);
+    // The permutation products, the lookup products (Lagrange basis) and the random polynomial (coefficient basis) are
+    // written to the transcript back to back with no challenge in between: ONE commit batch, one bucket reduction. Sharded,
+    // column j of the batch is committed by rank j mod world — for the leading z columns that is the rank that built them.
+    {
+        std::vector<const Fr*> cols;
+        std::vector<int> basis;
+        for (uint32_t set = 0; set < NS; ++set) cols.push_back(z_polys.get() + (size_t)set * n), basis.push_back(1);
+        for (uint32_t l = 0; l < L; ++l) cols.push_back(lk_z_poly.get() + (size_t)l * n), basis.push_back(1);
+        cols.push_back(random_poly.get()), basis.push_back(0);
+        std::vector<G1Affine> cms(cols.size());
+        msm_batch_srs_mixed(ctx, basis.data(), cols.data(), cols.size(), n, cms.data());
+        lap(tm ? &tm->msm : nullptr);
+        for (const G1Affine& cm : cms) tr.write_point(cm);
+    }
+    if (!shard.on()) {
+        dev_lagrange_to_coeff(ctx, sh.k, z_polys.get(), NS, n);
+        for (uint32_t set = 0; set < NS; ++set) dev_coeff_to_extended(ctx, sh.k, z_polys.get() + (size_t)set * n, z_cosets.get() + (size_t)set * en);
+    } else {
+        for (uint32_t set = 0; set < NS; ++set)
+            if (shard.mine(set)) {
+                dev_lagrange_to_coeff(ctx, sh.k, z_polys.get() + (size_t)set * n);
+                dev_coeff_to_extended(ctx, sh.k, z_polys.get() + (size_t)set * n, z_cosets.get() + (size_t)set * en);
+            }
+        shard.allgather_columns(z_polys.get(), NS, n);
+        std::vector<Fr*> cs(NS);
+        for (uint32_t set = 0; set < NS; ++set) cs[set] = z_cosets.get() + (size_t)set * en;
+        shard.exchange_row_slices(cs.data(), NS, [&](size_t c) { return shard.owner(c); }, en, HALO_BEFORE, HALO_AFTER);
+    }
+    if (L) dev_lagrange_to_coeff(ctx, sh.k, lk_z_poly.get(), L, n);
+    lap(tm ? &tm->ntt : nullptr);
     const Fr y = tr.squeeze_challenge();
     // step 8/9: advice polys + cosets, h(X) (D.8)
     DevBuf<Fr> advice_polys((size_t)NA * n, s), advice_cosets((size_t)NA * en, s);

@@ -110,6 +110,9 @@ int b200zk_destroy(b200zk_ctx* ctx) {
         cudaStreamSynchronize(ctx->c.copy_stream);
         cudaStreamDestroy(ctx->c.copy_stream);
     }
+    if (ctx->c.stage_buf) cudaFreeHost(ctx->c.stage_buf);
+    for (auto& e : ctx->c.stage_ev)
+        if (e) cudaEventDestroy(e);
     if (ctx->c.copy_fork) cudaEventDestroy(ctx->c.copy_fork);
     if (ctx->c.copy_done) cudaEventDestroy(ctx->c.copy_done);
     if (ctx->c.pinned_u32) cudaFreeHost(ctx->c.pinned_u32);

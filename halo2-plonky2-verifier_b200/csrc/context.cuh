@@ -80,6 +80,7 @@ typedef int (*AllGatherFn)(void* user, const void* send, size_t bytes, void* rec
 
 
 constexpr int MSM_SLOTS = 4;  // MSM columns in flight per commit batch
+constexpr int STAGE_WORKERS = 6, STAGE_SLOTS = 2;  // pinned staging of pageable uploads (upload.cuh)
 
 struct Context {
     int device = 0;
@@ -88,6 +89,8 @@ struct Context {
     cudaEvent_t msm_events[MSM_SLOTS] = {}, msm_join[MSM_SLOTS - 1] = {}, msm_fork = nullptr;
     cudaStream_t copy_stream = nullptr;    // witness upload overlapped with the first advice commitments (prover.cu)
     cudaEvent_t copy_fork = nullptr, copy_done = nullptr;
+    uint8_t* stage_buf = nullptr;          // pinned staging slots for pageable host buffers, allocated on first use
+    cudaEvent_t stage_ev[STAGE_WORKERS * STAGE_SLOTS] = {};
     uint32_t* pinned_u32 = nullptr;        // pinned words for the entry-count read-backs (one per slot)
     std::mutex mu;
     std::string last_error;

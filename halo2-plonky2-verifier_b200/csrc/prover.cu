@@ -6,6 +6,7 @@
 // PCIe bus after the witness upload. The transcript and the Fr::random stream are host-side (row L), exactly as in
 // the reference; everything else is a launch of the kernels in ntt.cu / msm.cu / poly.cu / quotient.cu.
 #include "prover.cuh"
+#include "upload.cuh"
 
 #include "collectives.cuh"
 
@@ -417,15 +418,6 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
     std::vector<Fr> blind((size_t)NA * (bf + 1));
     for (auto& b : blind) b = rng.next();
     rng.skip(NA);  // Blind(..) per column: drawn upstream, unused by KZG commitments
-    // columns [c0, c1) from the caller's buffer, then their blinding rows, in order on one stream
-    auto upload = [&](uint32_t c0, uint32_t c1, cudaStream_t st) {
-        if (c0 >= c1) return;
-        CUDA_CHECK(cudaMemcpyAsync(advice.get() + (size_t)c0 * n, advice_in + (size_t)c0 * n, (size_t)(c1 - c0) * n * sizeof(Fr),
-                                   advice_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
-        for (uint32_t c = c0; c < c1; ++c)
-            CUDA_CHECK(cudaMemcpyAsync(advice.get() + (size_t)c * n + u, blind.data() + (size_t)c * (bf + 1), (bf + 1) * sizeof(Fr),
-                                       cudaMemcpyHostToDevice, st));
-    };
     // the copy stream must be idle before `advice` can go back to the arena, whichever way this function is left
     struct CopyJoin {
         cudaStream_t st;
@@ -433,32 +425,55 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
             if (st) cudaStreamSynchronize(st);
         }
     } copy_join{nullptr};
+    // a pageable witness (a Rust Vec) goes through pinned staging chunks filled by worker threads (upload.cuh)
+    const bool pageable = !advice_on_device && host_pointer_is_pageable(advice_in);
+    StagedUpload stager(ctx);
+    // columns [c0, c1) from the caller's buffer, queued on `st`; with `wait` the call returns once everything is queued
+    auto upload = [&](uint32_t c0, uint32_t c1, cudaStream_t st, bool wait) {
+        if (c0 >= c1) return;
+        Fr* dst = advice.get() + (size_t)c0 * n;
+        const Fr* src = advice_in + (size_t)c0 * n;
+        const size_t bytes = (size_t)(c1 - c0) * n * sizeof(Fr);
+        if (pageable) {
+            stager.start(dst, src, bytes, st);
+            if (wait) stager.join();
+        } else {
+            CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, advice_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        }
+    };
+    // blinding rows of columns [c0, c1): must be queued behind the column data
+    auto blind_rows = [&](uint32_t c0, uint32_t c1, cudaStream_t st) {
+        for (uint32_t c = c0; c < c1; ++c)
+            CUDA_CHECK(cudaMemcpyAsync(advice.get() + (size_t)c * n + u, blind.data() + (size_t)c * (bf + 1), (bf + 1) * sizeof(Fr),
+                                       cudaMemcpyHostToDevice, st));
+    };
     // host witness on one GPU: the first quarter of the columns goes up on the compute stream, the rest follows on the copy
-    // stream while that quarter is being committed (pinned host memory overlaps; pageable memory degrades to in-order)
+    // stream while that quarter is being committed
     const uint32_t ahead = (!advice_on_device && !shard.on() && ctx.copy_stream && NA >= 8) ? NA / 4 : NA;
     if (shard.on() && !advice_on_device) {
         // every rank holds the host witness: each uploads only its share of the columns over PCIe and the rest arrives over NVLink
         for (uint32_t c = 0; c < NA; ++c)
-            if (shard.mine(c))
-                CUDA_CHECK(cudaMemcpyAsync(advice.get() + (size_t)c * n, advice_in + (size_t)c * n, n * sizeof(Fr), cudaMemcpyHostToDevice, s));
+            if (shard.mine(c)) upload(c, c + 1, s, true);
         shard.allgather_columns(advice.get(), NA, n);
-        for (uint32_t c = 0; c < NA; ++c)
-            CUDA_CHECK(cudaMemcpyAsync(advice.get() + (size_t)c * n + u, blind.data() + (size_t)c * (bf + 1), (bf + 1) * sizeof(Fr),
-                                       cudaMemcpyHostToDevice, s));
+        blind_rows(0, NA, s);
     } else if (ahead < NA) {
         CUDA_CHECK(cudaEventRecord(ctx.copy_fork, s));
         CUDA_CHECK(cudaStreamWaitEvent(ctx.copy_stream, ctx.copy_fork, 0));
         copy_join.st = ctx.copy_stream;
-        upload(0, ahead, s);
-        upload(ahead, NA, ctx.copy_stream);
-        CUDA_CHECK(cudaEventRecord(ctx.copy_done, ctx.copy_stream));
+        upload(0, ahead, s, true);
+        blind_rows(0, ahead, s);
+        upload(ahead, NA, ctx.copy_stream, false);
     } else {
-        upload(0, NA, s);
+        upload(0, NA, s, true);
+        blind_rows(0, NA, s);
     }
     CUDA_CHECK(cudaStreamSynchronize(s));
     lap(tm ? &tm->upload : nullptr);
     for (const G1Affine& cm : commit_batch(ctx, 1, advice.get(), n, ahead, n)) tr.write_point(cm);
     if (ahead < NA) {
+        stager.join();
+        blind_rows(ahead, NA, ctx.copy_stream);
+        CUDA_CHECK(cudaEventRecord(ctx.copy_done, ctx.copy_stream));
         CUDA_CHECK(cudaStreamWaitEvent(s, ctx.copy_done, 0));
         for (const G1Affine& cm : commit_batch(ctx, 1, advice.get() + (size_t)ahead * n, n, NA - ahead, n)) tr.write_point(cm);
     }

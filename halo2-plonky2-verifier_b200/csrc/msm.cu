@@ -354,6 +354,7 @@ struct MsmSlot {
     cudaStream_t st = nullptr;
     cudaEvent_t ev = nullptr;
     uint32_t* total_host = nullptr;  // pinned
+    bool empty = false;              // the column in flight has no points on this rank
     DevBuf<uint32_t> counters, offsets, entries, keys_a, keys_b;
     DevBuf<G1X> heads_a, heads_b;
     void alloc(Context& ctx, uint32_t nb, size_t max_entries) {
@@ -369,6 +370,8 @@ struct MsmSlot {
 };
 static void msm_issue_count(MsmSlot& sl, const Fr* scalars, size_t n, const MsmConfig& cfg) {
     cudaStream_t s = sl.st;
+    sl.empty = n == 0;
+    if (sl.empty) return;
     const uint32_t nb = cfg.groups * cfg.B;
     CUDA_CHECK(cudaMemsetAsync(sl.counters.get(), 0, (nb + 1) * 4, s));
     msm_digits_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(scalars, n, cfg, sl.counters.get(), nullptr, 0);
@@ -381,6 +384,7 @@ static void msm_issue_count(MsmSlot& sl, const Fr* scalars, size_t n, const MsmC
 static void msm_issue_accumulate(MsmSlot& sl, const G1Affine* bases, const Fr* scalars, size_t n, const MsmConfig& cfg, G1X* bucket_sums) {
     cudaStream_t s = sl.st;
     const uint32_t nb = cfg.groups * cfg.B;
+    if (sl.empty) return;
     CUDA_CHECK(cudaEventSynchronize(sl.ev));
     const uint32_t total = *sl.total_host;
     if (total == 0) return;
@@ -475,19 +479,6 @@ static void msm_reduce_groups(Context& ctx, const G1X* bucket_sums, uint32_t G, 
 
 // optional cross-rank combine of partial window sums (set through b200zk_set_allgather)
 double g_exchange_seconds = 0;  // host time spent in the partial-sum exchange callback (reported under "other")
-static void combine_across_ranks(Context& ctx, std::vector<G1X>& ws) {
-    if (ctx.world <= 1 || !ctx.allgather) return;
-    const auto t0 = std::chrono::steady_clock::now();
-    const size_t bytes = ws.size() * sizeof(G1X);
-    std::vector<G1X> all(ws.size() * ctx.world);
-    if (ctx.allgather(ctx.allgather_user, ws.data(), bytes, all.data()) != 0) throw std::runtime_error("msm: all-gather callback failed");
-    for (size_t w = 0; w < ws.size(); ++w) {
-        G1X acc = g1x_identity();
-        for (int r = 0; r < ctx.world; ++r) acc = g1x_add(acc, all[(size_t)r * ws.size() + w]);
-        ws[w] = acc;
-    }
-    g_exchange_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-}
 // point range of this rank for an n-point MSM (contiguous shards; the last rank takes the remainder)
 static void shard_range(const Context& ctx, size_t n, size_t& lo, size_t& len) {
     if (ctx.world <= 1 || !ctx.allgather) {
@@ -504,23 +495,28 @@ static void check_cfg(const MsmConfig& cfg, size_t n) {
     if (cfg.W > (uint32_t)MAX_W) throw std::runtime_error("msm: too many windows");
     if (n >= ((size_t)1 << 31) || (cfg.merged && cfg.table_n * cfg.W >= ((size_t)1 << 31))) throw std::invalid_argument("msm: index space must be < 2^31");
 }
-// `ncols` MSMs over the same bases: per-column bucket accumulation, ONE reduction for all columns, one exchange across ranks.
-// `bases_origin`: index of the point that bases[0] corresponds to (non-zero when `bases` is a per-shard window table)
-// `col_bases` (optional): one base pointer per column, for batches that mix the coefficient and the Lagrange basis.
-static void msm_batch_core(Context& ctx, const G1Affine* bases, const Fr* const* cols, size_t ncols, size_t n, const MsmConfig& cfg, G1Affine* out,
-                           size_t bases_origin, bool shard_points, const G1Affine* const* col_bases = nullptr) {
+// `ncols` MSMs with one configuration: per-column bucket accumulation, ONE bucket reduction for all columns. Column j reads
+// the bases at col_bases[j] (the two SRS bases can be mixed in a batch); with col_partial[j] set, only this rank's point
+// range of column j is accumulated. sums_out gets cfg.groups entries per column: the (partial) window sums, XYZZ.
+static void msm_batch_core(Context& ctx, const G1Affine* const* col_bases, const Fr* const* cols, const uint8_t* col_partial, size_t ncols, size_t n,
+                           const MsmConfig& cfg, std::vector<G1X>& sums_out) {
     check_cfg(cfg, n);
     cudaStream_t s = ctx.stream;
-    size_t lo = 0, len = n;
-    if (shard_points) shard_range(ctx, n, lo, len);
+    size_t shard_lo = 0, shard_len = n;
+    shard_range(ctx, n, shard_lo, shard_len);
     const uint32_t nb = cfg.groups * cfg.B;
+    sums_out.clear();
     // bound the scratch: at most 32 columns (≈2 GiB of bucket sums at c = 20) per reduction round
     const size_t round = 32;
     for (size_t c0 = 0; c0 < ncols; c0 += round) {
         const size_t nc = std::min(round, ncols - c0);
         DevBuf<G1X> bucket_sums((size_t)nc * nb, s);
         CUDA_CHECK(cudaMemsetAsync(bucket_sums.get(), 0, (size_t)nc * nb * sizeof(G1X), s));
-        if (len > 0) {
+        auto lo_of = [&](size_t j) { return col_partial && col_partial[j] ? shard_lo : (size_t)0; };
+        auto len_of = [&](size_t j) { return col_partial && col_partial[j] ? shard_len : n; };
+        size_t max_len = 0;
+        for (size_t j = 0; j < nc; ++j) max_len = std::max(max_len, len_of(c0 + j));
+        if (max_len > 0) {
             // several columns in flight: slot 0 on the context stream, the others on auxiliary streams
             const int nslots = ctx.aux_streams[0] ? (int)std::min<size_t>(nc, MSM_SLOTS) : 1;
             MsmSlot slots[MSM_SLOTS];
@@ -528,18 +524,19 @@ static void msm_batch_core(Context& ctx, const G1Affine* bases, const Fr* const*
                 slots[q].st = q == 0 ? s : ctx.aux_streams[q - 1];
                 slots[q].ev = ctx.msm_events[q];
                 slots[q].total_host = ctx.pinned_u32 + q;
-                slots[q].alloc(ctx, nb, len * cfg.W);
+                slots[q].alloc(ctx, nb, max_len * cfg.W);
             }
             if (nslots > 1) {  // the aux streams may touch the buffers only after everything queued so far on the main stream
                 CUDA_CHECK(cudaEventRecord(ctx.msm_fork, s));
                 for (int q = 1; q < nslots; ++q) CUDA_CHECK(cudaStreamWaitEvent(ctx.aux_streams[q - 1], ctx.msm_fork, 0));
             }
-            for (size_t j = 0; j < (size_t)nslots && j < nc; ++j) msm_issue_count(slots[j], cols[c0 + j] + lo, len, cfg);
+            auto count = [&](MsmSlot& sl, size_t j) { msm_issue_count(sl, cols[j] + lo_of(j), len_of(j), cfg); };
+            for (size_t j = 0; j < (size_t)nslots && j < nc; ++j) count(slots[j], c0 + j);
             for (size_t j = 0; j < nc; ++j) {
                 MsmSlot& sl = slots[j % nslots];
-                const G1Affine* b = (col_bases ? col_bases[c0 + j] : bases) + (lo - bases_origin);
-                msm_issue_accumulate(sl, b, cols[c0 + j] + lo, len, cfg, bucket_sums.get() + j * nb);
-                if (j + nslots < nc) msm_issue_count(sl, cols[c0 + j + nslots] + lo, len, cfg);
+                const size_t col = c0 + j;
+                msm_issue_accumulate(sl, col_bases[col] + lo_of(col), cols[col] + lo_of(col), len_of(col), cfg, bucket_sums.get() + j * nb);
+                if (j + nslots < nc) count(sl, col + nslots);
             }
             for (int q = 1; q < nslots; ++q) {  // main stream (reduce, frees) continues after the aux streams have drained
                 CUDA_CHECK(cudaEventRecord(ctx.msm_join[q - 1], ctx.aux_streams[q - 1]));
@@ -549,69 +546,82 @@ static void msm_batch_core(Context& ctx, const G1Affine* bases, const Fr* const*
         }
         std::vector<G1X> ws;
         msm_reduce_groups(ctx, bucket_sums.get(), (uint32_t)(nc * cfg.groups), cfg.B, ws);
-        if (shard_points) combine_across_ranks(ctx, ws);
-        for (size_t j = 0; j < nc; ++j)
-            out[c0 + j] = cfg.merged ? g1x_to_affine(ws[j]) : g1x_to_affine(msm_fold_windows(ws.data() + j * cfg.W, cfg.W, cfg.c));
+        sums_out.insert(sums_out.end(), ws.begin(), ws.end());
+    }
+}
+// window sums of one column -> canonical affine result
+static G1Affine msm_finish(const MsmConfig& cfg, const G1X* sums) {
+    return cfg.merged ? g1x_to_affine(sums[0]) : g1x_to_affine(msm_fold_windows(sums, cfg.W, cfg.c));
+}
+
+// Multi-GPU split of a batch (both levels of the north star). With `world` ranks and ncols = q·world + rem:
+// the first q·world columns are dealt out by COLUMN — rank r commits columns r, r+world, ... over the full point range —
+// and the remaining rem (< world) columns are split by POINT RANGE, every rank accumulating its contiguous shard. All of
+// a rank's work goes through ONE accumulate batch and one bucket reduction; one all-gather (host callback) then carries
+// the q finished sums and the rem partial window sums of every rank, and the partial ones are added on the host.
+static void msm_batch_distribute(Context& ctx, const G1Affine* const* col_bases, const Fr* const* cols, size_t ncols, size_t n, const MsmConfig& cfg,
+                                 G1Affine* out) {
+    const bool dist = ctx.world > 1 && ctx.allgather;
+    const size_t G = cfg.groups;
+    std::vector<G1X> sums;
+    if (!dist) {
+        msm_batch_core(ctx, col_bases, cols, nullptr, ncols, n, cfg, sums);
+        for (size_t j = 0; j < ncols; ++j) out[j] = msm_finish(cfg, sums.data() + j * G);
+        return;
+    }
+    const size_t world = ctx.world, q = ncols / world, rem = ncols % world, dealt = q * world;
+    std::vector<const G1Affine*> my_bases;
+    std::vector<const Fr*> my_cols;
+    std::vector<uint8_t> partial;
+    for (size_t j = ctx.rank; j < dealt; j += world) my_bases.push_back(col_bases[j]), my_cols.push_back(cols[j]), partial.push_back(0);
+    for (size_t j = dealt; j < ncols; ++j) my_bases.push_back(col_bases[j]), my_cols.push_back(cols[j]), partial.push_back(1);
+    msm_batch_core(ctx, my_bases.data(), my_cols.data(), partial.data(), my_cols.size(), n, cfg, sums);
+    const size_t per = (q + rem) * G;  // entries per rank, the same on every rank
+    std::vector<G1X> all(per * world);
+    const auto t0 = std::chrono::steady_clock::now();
+    if (ctx.allgather(ctx.allgather_user, sums.data(), per * sizeof(G1X), all.data()) != 0) throw std::runtime_error("msm: all-gather callback failed");
+    g_exchange_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    for (size_t j = 0; j < dealt; ++j) out[j] = msm_finish(cfg, all.data() + (j % world) * per + (j / world) * G);
+    std::vector<G1X> acc(G);
+    for (size_t j = dealt; j < ncols; ++j) {
+        for (size_t g = 0; g < G; ++g) {
+            acc[g] = g1x_identity();
+            for (size_t r = 0; r < world; ++r) acc[g] = g1x_add(acc[g], all[r * per + (q + (j - dealt)) * G + g]);
+        }
+        out[j] = msm_finish(cfg, acc.data());
     }
 }
 
 // arbitrary bases (best_multiexp): windows kept separate, folded on the host
 G1Affine msm_run(Context& ctx, const G1Affine* bases, const Fr* scalars, size_t n) {
     G1Affine r;
-    msm_batch_core(ctx, bases, &scalars, 1, n, msm_config(n), &r, 0, true);
+    msm_batch_distribute(ctx, &bases, &scalars, 1, n, msm_config(n), &r);
     return r;
 }
 
-// SRS bases: uses the precomputed window table when it exists (one bucket set, no fold).
-// Multi-GPU (both levels of the north star): a batch with at least `world` columns is dealt out by
-// COLUMN — rank r commits columns r, r+world, ... over the full point range and the 64-byte results are all-gathered —
-// while smaller batches (the random polynomial, h pieces, SHPLONK quotients) are split by POINT RANGE with the partial
-// bucket sums exchanged.
-// `basis[j]` selects g (0) or g_lagrange (1) for column j
-static void msm_batch_srs_local(Context& ctx, const int* basis, const Fr* const* cols, size_t ncols, size_t n, G1Affine* out, bool shard_points) {
+// SRS bases: the precomputed window tables when they exist (one bucket set, no fold). `basis[j]` selects g (0) or
+// g_lagrange (1) for column j.
+void msm_batch_srs_mixed(Context& ctx, const int* basis, const Fr* const* cols, size_t ncols, size_t n, G1Affine* out) {
     if (ncols == 0) return;
     const Srs& srs = *ctx.srs;
     bool uniform = true;
     for (size_t j = 1; j < ncols; ++j) uniform = uniform && basis[j] == basis[0];
-    const bool tables = srs.g_tab.size() != 0 && srs.gl_tab.size() != 0 && n * 8 >= srs.n;
-    if (!uniform && !tables) {  // without both window tables the two bases use different configurations: one call per run
+    auto table = [&](int b) -> const DevBuf<G1Affine>& { return b == 0 ? srs.g_tab : srs.gl_tab; };
+    auto has_table = [&](int b) { return table(b).size() != 0 && n * 8 >= srs.n; };
+    if (!uniform && !(has_table(0) && has_table(1))) {  // the two bases would use different configurations: one call per run
         for (size_t j0 = 0; j0 < ncols;) {
             size_t j1 = j0 + 1;
             while (j1 < ncols && basis[j1] == basis[j0]) ++j1;
-            msm_batch_srs_local(ctx, basis + j0, cols + j0, j1 - j0, n, out + j0, shard_points);
+            msm_batch_srs_mixed(ctx, basis + j0, cols + j0, j1 - j0, n, out + j0);
             j0 = j1;
         }
         return;
     }
-    const DevBuf<G1Affine>& tab = basis[0] == 0 ? srs.g_tab : srs.gl_tab;
-    if (uniform && (tab.size() == 0 || n * 8 < srs.n)) {
-        msm_batch_core(ctx, basis[0] == 0 ? srs.g.get() : srs.g_lagrange.get(), cols, ncols, n, msm_config(n), out, 0, shard_points);
-        return;
-    }
+    const bool tabled = has_table(basis[0]);
     std::vector<const G1Affine*> col_bases(ncols);
-    for (size_t j = 0; j < ncols; ++j) col_bases[j] = basis[j] == 0 ? srs.g_tab.get() : srs.gl_tab.get();
-    msm_batch_core(ctx, tab.get(), cols, ncols, n, msm_config_merged(srs.tab_c, srs.n), out, 0, shard_points, uniform ? nullptr : col_bases.data());
-}
-void msm_batch_srs_mixed(Context& ctx, const int* basis, const Fr* const* cols, size_t ncols, size_t n, G1Affine* out) {
-    const bool dist = ctx.world > 1 && ctx.allgather;
-    if (!dist || ncols < (size_t)ctx.world) {
-        msm_batch_srs_local(ctx, basis, cols, ncols, n, out, dist);
-        return;
-    }
-    const size_t world = ctx.world, per = (ncols + world - 1) / world;
-    std::vector<const Fr*> mine;
-    std::vector<int> mine_basis;
-    for (size_t j = ctx.rank; j < ncols; j += world) {
-        mine.push_back(cols[j]);
-        mine_basis.push_back(basis[j]);
-    }
-    std::vector<G1Affine> send(per), recv(per * world);
-    memset(send.data(), 0, per * sizeof(G1Affine));
-    if (!mine.empty()) msm_batch_srs_local(ctx, mine_basis.data(), mine.data(), mine.size(), n, send.data(), false);
-    const auto t0 = std::chrono::steady_clock::now();
-    if (ctx.allgather(ctx.allgather_user, send.data(), per * sizeof(G1Affine), recv.data()) != 0) throw std::runtime_error("msm: all-gather callback failed");
-    g_exchange_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    for (size_t j = 0; j < ncols; ++j) out[j] = recv[(j % world) * per + j / world];
+    for (size_t j = 0; j < ncols; ++j)
+        col_bases[j] = tabled ? table(basis[j]).get() : (basis[j] == 0 ? srs.g.get() : srs.g_lagrange.get());
+    msm_batch_distribute(ctx, col_bases.data(), cols, ncols, n, tabled ? msm_config_merged(srs.tab_c, srs.n) : msm_config(n), out);
 }
 void msm_batch_srs(Context& ctx, int basis, const Fr* const* cols, size_t ncols, size_t n, G1Affine* out) {
     std::vector<int> b(ncols, basis);

@@ -65,7 +65,10 @@ def test_tables_and_generic_paths_agree(ctx):
 
 
 def test_column_dealt_batch(ctx):
-    """Batches with >= world columns are dealt out by column: each rank commits its own columns over the full range."""
+    """A batch of q·world + rem columns: the first q·world are dealt out by column (each rank commits its own over the full
+    point range), the last rem are split by point range and every rank contributes a partial sum."""
+    import ctypes
+
     k, world = 12, 2
     n = 1 << k
     ctx.srs_setup(k)
@@ -84,8 +87,14 @@ def test_column_dealt_batch(ctx):
             got[rank] = ctx.msm_batch_dev(ptrs, n, 1)
     finally:
         ctx.set_allgather(0, 1, None)
-    for j in range(5):
+    for j in range(4):
         assert np.array_equal(got[j % world][j], want[j]), j          # the owner produced the right commitment
         assert not got[1 - j % world][j].any()                        # the other rank left it to the exchange
+    # the fifth column: each rank alone yields the sum over its half of the points; the halves add up to the commitment
+    parts = np.ascontiguousarray(np.stack([got[0][4], got[1][4]]))
+    assert parts[0].any() and parts[1].any() and not np.array_equal(parts[0], want[4])
+    total = np.zeros(8, dtype=np.uint64)
+    assert b200zk.lib().b200zk_g1_sum_host(parts.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(2), total.ctypes.data_as(ctypes.c_void_p)) == 0
+    assert np.array_equal(total, want[4])
     for p in ptrs:
         ctx.dev_free(p)

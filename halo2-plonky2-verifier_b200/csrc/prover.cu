@@ -627,6 +627,11 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
         for (uint32_t set = 0; set < NS; ++set) cols.push_back(z_polys.get() + (size_t)set * n), basis.push_back(1);
         for (uint32_t l = 0; l < L; ++l) cols.push_back(lk_z_poly.get() + (size_t)l * n), basis.push_back(1);
         cols.push_back(random_poly.get()), basis.push_back(0);
+        if (shard.on() && NS >= (uint32_t)ctx.world) {
+            // z columns beyond the dealt part of the batch are committed by point range on EVERY rank: hand them out first
+            const size_t dealt = cols.size() / ctx.world * ctx.world;
+            for (size_t set = dealt; set < NS; ++set) shard.broadcast(z_polys.get() + set * n, n, shard.owner(set));
+        }
         std::vector<G1Affine> cms(cols.size());
         msm_batch_srs_mixed(ctx, basis.data(), cols.data(), cols.size(), n, cms.data());
         lap(tm ? &tm->msm : nullptr);

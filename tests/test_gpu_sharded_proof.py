@@ -1,6 +1,8 @@
-"""Row (e) on real hardware: one proof computed by 2 ranks (MSM point-range shards + NCCL broadcast of per-column NTT
-results + all-gather of h(X) row ranges) must be byte-identical to the single-GPU proof and to the oracle's.
-Needs >= 2 GPUs (skipped otherwise); launched through torchrun like bench.py."""
+"""Row (e) on real hardware: one proof computed by 2 (and, where the box has them, 4) ranks — commit batches dealt by
+column with the remainder split by point range, per-column NTTs, h(X) row slices, grand products by set — must be
+byte-identical to the single-GPU proof and to the oracle's. Needs >= 2 GPUs (skipped otherwise); launched through torchrun
+like bench.py. The 4-rank shapes put permutation-product columns into the point-range remainder of their commit batch
+(6 sets + the random polynomial on 4 ranks), which 2 ranks can never do."""
 import os
 import socket
 import subprocess
@@ -20,7 +22,7 @@ WORKER = textwrap.dedent("""
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
-    for (k, A, L, F) in [(10, 4, 1, 2), (12, 5, 3, 1), (11, 3, 0, 1)]:
+    for (k, A, L, F) in [(10, 4, 1, 2), (12, 5, 3, 1), (11, 3, 0, 1), (11, 10, 0, 1), (10, 9, 1, 2)]:
         fixed, advice, copies = b200zk.synth_circuit(k, A, L, F, seed=k)
         ctx = b200zk.Context(rank)
         ctx.srs_setup(k)
@@ -41,17 +43,18 @@ WORKER = textwrap.dedent("""
 """) % (ROOT, ROOT)
 
 
-def test_two_rank_proof_is_identical(tmp_path):
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_proof_is_identical(tmp_path, world):
     import torch
 
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     with socket.socket() as sock:
         sock.bind(("127.0.0.1", 0))
         port = sock.getsockname()[1]
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("sharded ok") == 2, r.stdout  # (lines of the two ranks may interleave)
+    assert r.stdout.count("sharded ok") == world, r.stdout  # (lines of the ranks may interleave)

@@ -62,14 +62,15 @@ struct Nccl {
     }
 };
 
-// ownership of column-wise work in the sharded prover: item i belongs to rank i mod world
+// ownership of column-wise work in the sharded prover: item i of a family belongs to rank (i + off) mod world. Each column
+// family uses its own offset so that the ranks taking the odd column of 17 advice / 9 product / 9 lookup columns differ.
 struct Sharder {
     Context& ctx;
     bool enabled = true;  // false: this call works on the local GPU alone even inside a multi-rank job
     explicit Sharder(Context& c) : ctx(c) {}
     bool on() const { return enabled && ctx.world > 1 && ctx.allgather; }
-    int owner(size_t i) const { return on() ? (int)(i % ctx.world) : 0; }
-    bool mine(size_t i) const { return !on() || owner(i) == ctx.rank; }
+    int owner(size_t i, size_t off = 0) const { return on() ? (int)((i + off) % ctx.world) : 0; }
+    bool mine(size_t i, size_t off = 0) const { return !on() || owner(i, off) == ctx.rank; }
     Nccl& nccl() {
         if (!ctx.nccl) {
             auto n = std::make_shared<Nccl>();
@@ -89,19 +90,22 @@ struct Sharder {
         if (!on()) return;
         nccl().check(nccl().Broadcast(buf, buf, count * sizeof(Fr), /*ncclUint8*/ 1, root, nccl().comm, ctx.stream), "Broadcast");
     }
-    // Columns base[c·len .. (c+1)·len), c < ncols, each complete on rank c mod world only: afterwards complete everywhere.
+    // Columns base[c·len .. (c+1)·len), c < ncols, each complete on rank owner(c, off) only: afterwards complete everywhere.
     // One all-gather over an owner-major staging buffer instead of ncols broadcasts (NVSwitch all-gather bandwidth, one
-    // launch): stage[r][j] = column r + j·world.
-    void allgather_columns(Fr* base, size_t ncols, size_t len) {
+    // launch): stage[r][j] = the j-th column owned by rank r = column first(r) + j·world.
+    void allgather_columns(Fr* base, size_t ncols, size_t len, size_t off = 0) {
         if (!on() || ncols == 0) return;
         const size_t world = ctx.world, per = (ncols + world - 1) / world;
+        auto first = [&](size_t r) { return (r + world - off % world) % world; };  // smallest column index owned by rank r
         DevBuf<Fr> stage(world * per * len, ctx.stream);
-        for (size_t c = ctx.rank; c < ncols; c += world)
-            CUDA_CHECK(cudaMemcpyAsync(stage.get() + ((size_t)ctx.rank * per + c / world) * len, base + c * len, len * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx.stream));
+        for (size_t c = first(ctx.rank), j = 0; c < ncols; c += world, ++j)
+            CUDA_CHECK(cudaMemcpyAsync(stage.get() + ((size_t)ctx.rank * per + j) * len, base + c * len, len * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx.stream));
         all_gather_inplace(stage.get(), per * len);
-        for (size_t c = 0; c < ncols; ++c)
-            if (c % world != (size_t)ctx.rank)
-                CUDA_CHECK(cudaMemcpyAsync(base + c * len, stage.get() + ((c % world) * per + c / world) * len, len * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx.stream));
+        for (size_t r = 0; r < world; ++r) {
+            if (r == (size_t)ctx.rank) continue;
+            for (size_t c = first(r), j = 0; c < ncols; c += world, ++j)
+                CUDA_CHECK(cudaMemcpyAsync(base + c * len, stage.get() + (r * per + j) * len, len * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx.stream));
+        }
     }
     // Row-slice exchange for the h(X) stage: column c (length en, complete on owner(c) only) is needed by rank d only on
     // the extended rows d evaluates plus the rotation halo — rows [d·R − before, (d+1)·R + after) mod en, R = en / world.

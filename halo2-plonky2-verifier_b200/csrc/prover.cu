@@ -297,6 +297,8 @@ static void eval_many_dist(Context& ctx, Sharder& shard, const std::vector<const
 // ---- create_proof ---------------------------------------------------------------------------------------------------------
 // rotation reach of the h(X) kernels in extended rows: -4·(blinding_factors+1) = -28 (z of the previous set) ... +12 (gate rotation 3)
 static constexpr size_t HALO_BEFORE = 32, HALO_AFTER = 16;
+// ownership offsets of the column families that are only transformed (not built) by their owner
+static constexpr size_t OFF_ADVICE_NTT = 1, OFF_LOOKUP_COSETS = 2;
 // Row H: evaluation::Evaluator::evaluate_h followed by divide_by_vanishing_poly (the t_inv scaling is fused into the last
 // kernel), on the extended domain. Inputs: the advice and permutation-product cosets (NA resp. NS columns of 4n), and per
 // lookup the coefficient forms of Z, a', s' (their cosets are made here, three at a time, so they never all coexist).
@@ -340,9 +342,9 @@ static void evaluate_h_dev(Context& ctx, Sharder& shard, const ProvingKeyDev& pk
         for (uint32_t l = 0; l < L; ++l) {
             const Fr* srcs[3] = {lk_z_poly + (size_t)l * n, perm_in_poly + (size_t)l * n, perm_tab_poly + (size_t)l * n};
             for (uint32_t j = 0; j < 3; ++j)
-                if (shard.mine(3 * l + j)) dev_coeff_to_extended(ctx, sh.k, srcs[j], lc.get() + (size_t)j * en);
+                if (shard.mine(3 * l + j, OFF_LOOKUP_COSETS)) dev_coeff_to_extended(ctx, sh.k, srcs[j], lc.get() + (size_t)j * en);
             Fr* cs[3] = {lc.get(), lc.get() + en, lc.get() + 2 * en};
-            shard.exchange_row_slices(cs, 3, [&](size_t j) { return shard.owner(3 * l + j); }, en, HALO_BEFORE, HALO_AFTER);
+            shard.exchange_row_slices(cs, 3, [&](size_t j) { return shard.owner(3 * l + j, OFF_LOOKUP_COSETS); }, en, HALO_BEFORE, HALO_AFTER);
             lap(tm ? &tm->ntt : nullptr);
             LookupCosets Lk{lc.get(), lc.get() + en, lc.get() + 2 * en, Q.advice[A + l], Q.fixed[sh.table_col()]};
             h_lookup(Q, Lk, h, l + 1 == L, s);
@@ -662,14 +664,14 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
         for (uint32_t c = 0; c < NA; ++c) dev_coeff_to_extended(ctx, sh.k, advice_polys.get() + (size_t)c * n, advice_cosets.get() + (size_t)c * en);
     } else {  // column c is transformed by rank c mod world and broadcast over NCCL
         for (uint32_t c = 0; c < NA; ++c)
-            if (shard.mine(c)) {
+            if (shard.mine(c, OFF_ADVICE_NTT)) {
                 dev_lagrange_to_coeff(ctx, sh.k, advice_polys.get() + (size_t)c * n);
                 dev_coeff_to_extended(ctx, sh.k, advice_polys.get() + (size_t)c * n, advice_cosets.get() + (size_t)c * en);
             }
-        shard.allgather_columns(advice_polys.get(), NA, n);
+        shard.allgather_columns(advice_polys.get(), NA, n, OFF_ADVICE_NTT);
         std::vector<Fr*> cs(NA);
         for (uint32_t c = 0; c < NA; ++c) cs[c] = advice_cosets.get() + (size_t)c * en;
-        shard.exchange_row_slices(cs.data(), NA, [&](size_t c) { return shard.owner(c); }, en, HALO_BEFORE, HALO_AFTER);
+        shard.exchange_row_slices(cs.data(), NA, [&](size_t c) { return shard.owner(c, OFF_ADVICE_NTT); }, en, HALO_BEFORE, HALO_AFTER);
     }
     lap(tm ? &tm->ntt : nullptr);
     DevBuf<Fr> h(en, s);
@@ -798,6 +800,21 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
     CUDA_CHECK(cudaMemsetAsync(h_x.get(), 0, n * sizeof(Fr), s));
     std::vector<std::vector<std::vector<Fr>>> low(sets.size());
     {
+        // Sharded: the rotation sets are independent until they are summed into h(X), so they are dealt to the ranks by
+        // cost (longest first onto the least loaded rank: one axpy per polynomial, a division ≈ 6 axpys per point); each rank
+        // sums its sets into a partial h(X), the partials are all-gathered and added.
+        std::vector<int> set_owner(sets.size(), 0);
+        if (shard.on()) {
+            std::vector<size_t> order(sets.size()), load(ctx.world, 0);
+            for (size_t i = 0; i < sets.size(); ++i) order[i] = i;
+            auto cost = [&](size_t i) { return sets[i].polys.size() + 6 * sets[i].points.size(); };
+            std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return cost(a) > cost(b); });
+            for (size_t i : order) {
+                const size_t r = std::min_element(load.begin(), load.end()) - load.begin();
+                set_owner[i] = (int)r;
+                load[r] += cost(i);
+            }
+        }
         Fr vp = one;
         for (size_t i = 0; i < sets.size(); ++i) {
             const RotationSet& rs = sets[i];
@@ -812,15 +829,26 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
                 for (size_t t = 0; t < low[i][j].size(); ++t) r_comb[t] = f_add(r_comb[t], f_mul(low[i][j][t], yp));
                 yp = f_mul(yp, ych);
             }
-            fr_lincomb(buf_a.get(), ps, cs, n, false, s);
-            fr_sub_low(buf_a.get(), r_comb.data(), (uint32_t)r_comb.size(), s);
-            Fr *src = buf_a.get(), *dst = buf_b.get();
-            for (auto& pt : rs.points) {
-                fr_kate_division(ctx, src, dst, n, pt);
-                std::swap(src, dst);
+            if (!shard.on() || set_owner[i] == ctx.rank) {
+                fr_lincomb(buf_a.get(), ps, cs, n, false, s);
+                fr_sub_low(buf_a.get(), r_comb.data(), (uint32_t)r_comb.size(), s);
+                Fr *src = buf_a.get(), *dst = buf_b.get();
+                for (auto& pt : rs.points) {
+                    fr_kate_division(ctx, src, dst, n, pt);
+                    std::swap(src, dst);
+                }
+                fr_lincomb(h_x.get(), {src}, {vp}, n, true, s);
             }
-            fr_lincomb(h_x.get(), {src}, {vp}, n, true, s);
             vp = f_mul(vp, vch);
+        }
+        if (shard.on()) {
+            DevBuf<Fr> parts((size_t)ctx.world * n, s);
+            CUDA_CHECK(cudaMemcpyAsync(parts.get() + (size_t)ctx.rank * n, h_x.get(), n * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
+            shard.all_gather_inplace(parts.get(), n);
+            std::vector<const Fr*> ps(ctx.world);
+            for (int r = 0; r < ctx.world; ++r) ps[r] = parts.get() + (size_t)r * n;
+            fr_lincomb(h_x.get(), ps, std::vector<Fr>(ctx.world, one), n, false, s);
+            CUDA_CHECK(cudaStreamSynchronize(s));
         }
     }
     lap(tm ? &tm->shplonk : nullptr);
@@ -855,7 +883,14 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
         const Fr zt_eval = vanishing_eval(super, uch);
         ps.push_back(h_x.get());
         cs.push_back(f_neg(zt_eval));
-        fr_lincomb(buf_a.get(), ps, cs, n, false, s);
+        if (shard.on() && n % ctx.world == 0) {  // the big linear combination by coefficient range, then an in-place all-gather
+            const size_t len = n / ctx.world, lo = len * ctx.rank;
+            for (auto& ptr : ps) ptr += lo;
+            fr_lincomb(buf_a.get() + lo, ps, cs, len, false, s);
+            shard.all_gather_inplace(buf_a.get(), len);
+        } else {
+            fr_lincomb(buf_a.get(), ps, cs, n, false, s);
+        }
         fr_sub_low(buf_a.get(), &const_term, 1, s);
         fr_kate_division(ctx, buf_a.get(), buf_b.get(), n, uch);
         fr_scale(buf_b.get(), f_inv(z_diffs[0]), n, s);

@@ -298,7 +298,18 @@ static void eval_many_dist(Context& ctx, Sharder& shard, const std::vector<const
 // rotation reach of the h(X) kernels in extended rows: -4·(blinding_factors+1) = -28 (z of the previous set) ... +12 (gate rotation 3)
 static constexpr size_t HALO_BEFORE = 32, HALO_AFTER = 16;
 // ownership offsets of the column families that are only transformed (not built) by their owner
-static constexpr size_t OFF_ADVICE_NTT = 1, OFF_LOOKUP_COSETS = 2;
+static constexpr size_t OFF_ADVICE_NTT = 1, OFF_LOOKUP_COSETS = 2, OFF_PERM_IN = 0, OFF_PERM_TAB = 3, OFF_LOOKUP_Z = 6;
+// lagrange_to_coeff of `count` columns that every rank holds: by column across the ranks, then one all-gather
+static void lagrange_to_coeff_dist(Context& ctx, Sharder& shard, uint32_t k, Fr* base, uint32_t count, size_t n, size_t off) {
+    if (count == 0) return;
+    if (!shard.on()) {
+        dev_lagrange_to_coeff(ctx, k, base, count, n);
+        return;
+    }
+    for (uint32_t c = 0; c < count; ++c)
+        if (shard.mine(c, off)) dev_lagrange_to_coeff(ctx, k, base + (size_t)c * n);
+    shard.allgather_columns(base, count, n, off);
+}
 // Row H: evaluation::Evaluator::evaluate_h followed by divide_by_vanishing_poly (the t_inv scaling is fused into the last
 // kernel), on the extended domain. Inputs: the advice and permutation-product cosets (NA resp. NS columns of 4n), and per
 // lookup the coefficient forms of Z, a', s' (their cosets are made here, three at a time, so they never all coexist).
@@ -521,8 +532,8 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
         CUDA_CHECK(cudaMemcpyAsync(perm_in_poly.get(), perm_in.get(), (size_t)L * n * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
         CUDA_CHECK(cudaMemcpyAsync(perm_tab_poly.get(), perm_tab.get(), (size_t)L * n * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
         if (L) {
-            dev_lagrange_to_coeff(ctx, sh.k, perm_in_poly.get(), L, n);
-            dev_lagrange_to_coeff(ctx, sh.k, perm_tab_poly.get(), L, n);
+            lagrange_to_coeff_dist(ctx, shard, sh.k, perm_in_poly.get(), L, n, OFF_PERM_IN);
+            lagrange_to_coeff_dist(ctx, shard, sh.k, perm_tab_poly.get(), L, n, OFF_PERM_TAB);
         }
         lap(tm ? &tm->ntt : nullptr);
         for (const G1Affine& cm : cms) tr.write_point(cm);
@@ -653,7 +664,7 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
         for (uint32_t set = 0; set < NS; ++set) cs[set] = z_cosets.get() + (size_t)set * en;
         shard.exchange_row_slices(cs.data(), NS, [&](size_t c) { return shard.owner(c); }, en, HALO_BEFORE, HALO_AFTER);
     }
-    if (L) dev_lagrange_to_coeff(ctx, sh.k, lk_z_poly.get(), L, n);
+    lagrange_to_coeff_dist(ctx, shard, sh.k, lk_z_poly.get(), L, n, OFF_LOOKUP_Z);
     lap(tm ? &tm->ntt : nullptr);
     const Fr y = tr.squeeze_challenge();
     // step 8/9: advice polys + cosets, h(X) (D.8)

@@ -318,16 +318,61 @@ __global__ void __launch_bounds__(128) msm_reduce_sum_kernel(SumLevels lv, uint3
     }
     if (threadIdx.x == 0) g1x_store(out + ((size_t)level * W + w) * slices + slice, sh[0]);
 }
-// one thread per window: Horner over the levels. S[w] = the single entry of the last run list.
+// Tail of the recursion: F = Σ_b (b+1)·X[b] and S = Σ_b X[b] of one list of len <= TAIL_MAX entries (a power of two) per
+// block. Thread t takes E = len/256 consecutive entries (run_t, tot_t as above); with suff_t = Σ_{t'>=t} run_t' from a
+// block-wide suffix scan, F = Σ_t tot_t + E·Σ_{t>=1} suff_t. About 26 dependent additions instead of four more launches of
+// 16 each: the deep levels of the reduction are pure latency.
+constexpr uint32_t TAIL_MAX = 1024, TAIL_THREADS = 256;
+__global__ void __launch_bounds__(TAIL_THREADS) msm_reduce_tail_kernel(const G1X* X, uint32_t len, G1X* F_out, G1X* S_out) {
+    extern __shared__ uint4 tail_smem[];
+    G1X* cur = reinterpret_cast<G1X*>(tail_smem);
+    G1X* nxt = cur + TAIL_THREADS;
+    const uint32_t g = blockIdx.x, t = threadIdx.x;
+    const uint32_t E = len > TAIL_THREADS ? len / TAIL_THREADS : 1, active = len / E;
+    G1X run = g1x_identity(), tot = g1x_identity();
+    if (t < active) {
+        const G1X* b = X + (size_t)g * len + (size_t)t * E;
+        for (int i = (int)E - 1; i >= 0; --i) {
+            run = g1x_add(run, g1x_load(b + i));
+            tot = g1x_add(tot, run);
+        }
+    }
+    cur[t] = run;
+    __syncthreads();
+    for (uint32_t d = 1; d < TAIL_THREADS; d <<= 1) {  // inclusive suffix scan (Hillis–Steele)
+        G1X v = cur[t];
+        if (t + d < TAIL_THREADS) v = g1x_add(v, cur[t + d]);
+        nxt[t] = v;
+        G1X* tmp = cur;
+        cur = nxt;
+        nxt = tmp;
+        __syncthreads();
+    }
+    G1X v = tot;
+    if (t >= 1) {
+        G1X e = cur[t];
+        for (uint32_t k = 1; k < E; k <<= 1) e = g1x_dbl(e);
+        v = g1x_add(v, e);
+    }
+    if (t == 0) g1x_store(S_out + g, cur[0]);
+    nxt[t] = v;
+    __syncthreads();
+    for (uint32_t h = TAIL_THREADS / 2; h > 0; h >>= 1) {
+        if (t < h) nxt[t] = g1x_add(nxt[t], nxt[t + h]);
+        __syncthreads();
+    }
+    if (t == 0) g1x_store(F_out + g, nxt[0]);
+}
+// one thread per window: Horner over the levels, starting from the tail's F and S
 struct HornerLevels {
     uint32_t log_m[16];
     uint32_t levels;
 };
-__global__ void msm_reduce_horner_kernel(const G1X* T, const G1X* S, HornerLevels hl, uint32_t W, G1X* window_sums) {
+__global__ void msm_reduce_horner_kernel(const G1X* T, const G1X* F_tail, const G1X* S, HornerLevels hl, uint32_t W, G1X* window_sums) {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= W) return;
-    const G1X s = g1x_load(S + w), neg_s = g1x_neg(s);
-    G1X a = s;
+    const G1X neg_s = g1x_neg(g1x_load(S + w));
+    G1X a = g1x_load(F_tail + w);
     for (int l = (int)hl.levels - 1; l >= 0; --l) {
         a = g1x_add(a, neg_s);
         for (uint32_t d = 0; d < hl.log_m[l]; ++d) a = g1x_dbl(a);
@@ -432,9 +477,8 @@ static void msm_reduce_groups(Context& ctx, const G1X* bucket_sums, uint32_t G, 
         HornerLevels hl{};
         const G1X* X = bucket_sums;
         uint32_t len = B, level = 0;
-        while (len > 1) {
-            const uint32_t lm = len >= (1u << RED_LOG_M) ? RED_LOG_M : (uint32_t)__builtin_ctz(len);
-            const uint32_t m = 1u << lm, out_len = len >> lm, total_chunks = G * out_len;
+        while (len > TAIL_MAX) {
+            const uint32_t lm = RED_LOG_M, m = 1u << lm, out_len = len >> lm, total_chunks = G * out_len;
             tots.emplace_back((size_t)total_chunks, s);
             runs.emplace_back((size_t)total_chunks, s);
             msm_reduce_chunks_kernel<<<(total_chunks + 127) / 128, 128, 0, s>>>(X, total_chunks, m, tots.back().get(), runs.back().get());
@@ -447,8 +491,18 @@ static void msm_reduce_groups(Context& ctx, const G1X* bucket_sums, uint32_t G, 
             ++level;
         }
         hl.levels = level;
-        if (level == 0) {  // one bucket per set: F = bucket[0]
-            CUDA_CHECK(cudaMemcpyAsync(wsums.get(), bucket_sums, G * sizeof(G1X), cudaMemcpyDeviceToDevice, s));
+        // the remaining list (<= TAIL_MAX entries per set) in one launch
+        static bool tail_attr_set = false;
+        const size_t tail_smem = 2 * TAIL_THREADS * sizeof(G1X);
+        if (!tail_attr_set) {
+            CUDA_CHECK(cudaFuncSetAttribute(msm_reduce_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
+            tail_attr_set = true;
+        }
+        DevBuf<G1X> tail_f(G, s), tail_s(G, s);
+        msm_reduce_tail_kernel<<<G, TAIL_THREADS, tail_smem, s>>>(X, len, tail_f.get(), tail_s.get());
+        ++g_launch_count;
+        if (level == 0) {
+            CUDA_CHECK(cudaMemcpyAsync(wsums.get(), tail_f.get(), G * sizeof(G1X), cudaMemcpyDeviceToDevice, s));
         } else {
             DevBuf<G1X> T((size_t)level * G, s);
             uint32_t max_len = 0;
@@ -468,7 +522,7 @@ static void msm_reduce_groups(Context& ctx, const G1X* bucket_sums, uint32_t G, 
                 msm_reduce_sum_kernel<<<dim3(G, level, 1), 128, 0, s>>>(sl2, G, 1, T.get());
                 g_launch_count += 2;
             }
-            msm_reduce_horner_kernel<<<(G + 31) / 32, 32, 0, s>>>(T.get(), X, hl, G, wsums.get());
+            msm_reduce_horner_kernel<<<(G + 31) / 32, 32, 0, s>>>(T.get(), tail_f.get(), tail_s.get(), hl, G, wsums.get());
             ++g_launch_count;
         }
         CUDA_CHECK(cudaGetLastError());

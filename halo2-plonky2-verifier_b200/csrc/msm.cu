@@ -498,30 +498,39 @@ static void msm_reduce_groups(Context& ctx, const G1X* bucket_sums, uint32_t G, 
             CUDA_CHECK(cudaFuncSetAttribute(msm_reduce_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
             tail_attr_set = true;
         }
-        DevBuf<G1X> tail_f(G, s), tail_s(G, s);
+        // the level sums T_l only need the `tot` lists: they run on an auxiliary stream beside the tail launch
+        cudaStream_t side = ctx.aux_streams[0] && level ? ctx.aux_streams[0] : s;
+        DevBuf<G1X> tail_f(G, s), tail_s(G, s), T((size_t)std::max<uint32_t>(level, 1) * G, s);
+        uint32_t max_len = 0;
+        for (uint32_t l = 0; l < level; ++l) max_len = std::max(max_len, sl.len[l]);
+        const uint32_t slices = (max_len + SUM_SLICE - 1) / SUM_SLICE;
+        DevBuf<G1X> part(slices > 1 ? (size_t)level * G * slices : 0, s);  // slices beyond a short list sum to the identity
+        if (side != s) {
+            CUDA_CHECK(cudaEventRecord(ctx.msm_fork, s));
+            CUDA_CHECK(cudaStreamWaitEvent(side, ctx.msm_fork, 0));
+        }
+        if (level && slices <= 1) {
+            msm_reduce_sum_kernel<<<dim3(G, level, 1), 128, 0, side>>>(sl, G, 1, T.get());
+            ++g_launch_count;
+        } else if (level) {
+            msm_reduce_sum_kernel<<<dim3(G, level, slices), 128, 0, side>>>(sl, G, slices, part.get());
+            SumLevels sl2{};
+            for (uint32_t l = 0; l < level; ++l) {
+                sl2.tot[l] = part.get() + (size_t)l * G * slices;
+                sl2.len[l] = slices;
+            }
+            msm_reduce_sum_kernel<<<dim3(G, level, 1), 128, 0, side>>>(sl2, G, 1, T.get());
+            g_launch_count += 2;
+        }
         msm_reduce_tail_kernel<<<G, TAIL_THREADS, tail_smem, s>>>(X, len, tail_f.get(), tail_s.get());
         ++g_launch_count;
+        if (side != s) {
+            CUDA_CHECK(cudaEventRecord(ctx.msm_join[0], side));
+            CUDA_CHECK(cudaStreamWaitEvent(s, ctx.msm_join[0], 0));
+        }
         if (level == 0) {
             CUDA_CHECK(cudaMemcpyAsync(wsums.get(), tail_f.get(), G * sizeof(G1X), cudaMemcpyDeviceToDevice, s));
         } else {
-            DevBuf<G1X> T((size_t)level * G, s);
-            uint32_t max_len = 0;
-            for (uint32_t l = 0; l < level; ++l) max_len = std::max(max_len, sl.len[l]);
-            const uint32_t slices = (max_len + SUM_SLICE - 1) / SUM_SLICE;
-            if (slices <= 1) {
-                msm_reduce_sum_kernel<<<dim3(G, level, 1), 128, 0, s>>>(sl, G, 1, T.get());
-                ++g_launch_count;
-            } else {
-                DevBuf<G1X> part((size_t)level * G * slices, s);  // slices beyond a short list sum to the identity
-                msm_reduce_sum_kernel<<<dim3(G, level, slices), 128, 0, s>>>(sl, G, slices, part.get());
-                SumLevels sl2{};
-                for (uint32_t l = 0; l < level; ++l) {
-                    sl2.tot[l] = part.get() + (size_t)l * G * slices;
-                    sl2.len[l] = slices;
-                }
-                msm_reduce_sum_kernel<<<dim3(G, level, 1), 128, 0, s>>>(sl2, G, 1, T.get());
-                g_launch_count += 2;
-            }
             msm_reduce_horner_kernel<<<(G + 31) / 32, 32, 0, s>>>(T.get(), tail_f.get(), tail_s.get(), hl, G, wsums.get());
             ++g_launch_count;
         }

@@ -349,16 +349,26 @@ static void evaluate_h_dev(Context& ctx, Sharder& shard, const ProvingKeyDev& pk
     h_permutation(Q, h, L == 0, s);
     lap(tm ? &tm->quotient : nullptr);
     if (L) {
-        DevBuf<Fr> lc(3 * en, s);
-        for (uint32_t l = 0; l < L; ++l) {
-            const Fr* srcs[3] = {lk_z_poly + (size_t)l * n, perm_in_poly + (size_t)l * n, perm_tab_poly + (size_t)l * n};
-            for (uint32_t j = 0; j < 3; ++j)
-                if (shard.mine(3 * l + j, OFF_LOOKUP_COSETS)) dev_coeff_to_extended(ctx, sh.k, srcs[j], lc.get() + (size_t)j * en);
-            Fr* cs[3] = {lc.get(), lc.get() + en, lc.get() + 2 * en};
-            shard.exchange_row_slices(cs, 3, [&](size_t j) { return shard.owner(3 * l + j, OFF_LOOKUP_COSETS); }, en, HALO_BEFORE, HALO_AFTER);
+        // the cosets of Z, a', s' are made for two lookups at a time (six columns: enough to occupy six ranks at once) and
+        // never all coexist
+        const uint32_t GL = L >= 2 ? 2 : 1;
+        DevBuf<Fr> lc((size_t)3 * GL * en, s);
+        for (uint32_t l0 = 0; l0 < L; l0 += GL) {
+            const uint32_t g = std::min(GL, L - l0);
+            Fr* cs[6];
+            for (uint32_t q = 0; q < 3 * g; ++q) {
+                const uint32_t l = l0 + q / 3;
+                const Fr* src = (q % 3 == 0 ? lk_z_poly : q % 3 == 1 ? perm_in_poly : perm_tab_poly) + (size_t)l * n;
+                cs[q] = lc.get() + (size_t)q * en;
+                if (shard.mine(3 * l0 + q, OFF_LOOKUP_COSETS)) dev_coeff_to_extended(ctx, sh.k, src, cs[q]);
+            }
+            shard.exchange_row_slices(cs, 3 * g, [&](size_t q) { return shard.owner(3 * l0 + q, OFF_LOOKUP_COSETS); }, en, HALO_BEFORE, HALO_AFTER);
             lap(tm ? &tm->ntt : nullptr);
-            LookupCosets Lk{lc.get(), lc.get() + en, lc.get() + 2 * en, Q.advice[A + l], Q.fixed[sh.table_col()]};
-            h_lookup(Q, Lk, h, l + 1 == L, s);
+            for (uint32_t i = 0; i < g; ++i) {
+                const uint32_t l = l0 + i;
+                LookupCosets Lk{cs[3 * i], cs[3 * i + 1], cs[3 * i + 2], Q.advice[A + l], Q.fixed[sh.table_col()]};
+                h_lookup(Q, Lk, h, l + 1 == L, s);
+            }
             lap(tm ? &tm->quotient : nullptr);
         }
     }

@@ -23,6 +23,25 @@ def test_library_exports_every_declared_symbol():
     assert not missing, missing
 
 
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 (no C++ or torch types), and a C translation unit that
+    references every declared entry point must link against the shared library."""
+    import shutil
+    import subprocess
+
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    header = os.path.join(ROOT, "include", "b200zk.h")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", header])
+    names = sorted(set(re.findall(r"B200ZK_API[^;(]*?\b(b200zk_\w+)\s*\(", open(header).read())))
+    src = tmp_path / "link_all.c"
+    src.write_text('#include "b200zk.h"\n#include <stdio.h>\nint main(void) {\n  void* p[] = {%s};\n  printf("%%d\\n", (int)(sizeof p / sizeof p[0]));\n  return 0;\n}\n'
+                   % ", ".join("(void*)" + n for n in names))
+    libdir = os.path.join(ROOT, "halo2-plonky2-verifier_b200")
+    exe = tmp_path / "link_all"
+    subprocess.check_call(["gcc", "-std=gnu99", "-I", os.path.join(ROOT, "include"), str(src), "-L", libdir, "-lb200zk", "-Wl,-rpath," + libdir, "-o", str(exe)])
+
+
 def test_no_cpu_fallback():
     import torch
 

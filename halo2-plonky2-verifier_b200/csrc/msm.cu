@@ -581,7 +581,8 @@ static void msm_batch_core(Context& ctx, const G1Affine* const* col_bases, const
         for (size_t j = 0; j < nc; ++j) max_len = std::max(max_len, len_of(c0 + j));
         if (max_len > 0) {
             // several columns in flight: slot 0 on the context stream, the others on auxiliary streams
-            const int nslots = ctx.aux_streams[0] ? (int)std::min<size_t>(nc, MSM_SLOTS) : 1;
+            // (under the event profiler one column at a time: concurrent streams would inflate each other's bracketed durations)
+            const int nslots = ctx.aux_streams[0] && !g_prof_enabled ? (int)std::min<size_t>(nc, MSM_SLOTS) : 1;
             MsmSlot slots[MSM_SLOTS];
             for (int q = 0; q < nslots; ++q) {
                 slots[q].st = q == 0 ? s : ctx.aux_streams[q - 1];

@@ -7,18 +7,20 @@
 //                 set per window and a short host-side fold.
 //   1. digits   : scalars leave Montgomery form; each is cut into W signed c-bit digits dₗ ∈ [-2^(c-1), 2^(c-1)];
 //                 zero digits create no work (advice-like scalars are mostly < 2^84, lookup columns < 2^(k-1)).
-//   2. sort     : counting sort by bucket: histogram with atomics, exclusive scan, scatter. Order inside a bucket is
-//                 irrelevant to the group sum, so the result stays deterministic.
+//   2. sort     : counting sort by bucket: histogram with warp-aggregated atomics, exclusive scan, scatter. Order inside
+//                 a bucket is irrelevant to the group sum, so the result stays deterministic.
 //   3. accumulate: the sorted entry list is cut into equal chunks of T entries, one thread each (perfect balance
 //                 whatever the bucket histogram: hot buckets simply span many chunks). A thread walks its chunk
 //                 with one XYZZ accumulator and mixed additions (8M+2S); runs that begin inside the chunk are
-//                 stored to their bucket, the run that began earlier goes to a "head" list, which is itself
-//                 segment-summed by the same scheme with chunk T2 until one thread covers it.
-//   4. reduce   : Σ b·B_b via recursive chunked running sums (2 additions per bucket, Horner in the chunk size), done
-//                 ONCE for all columns of a commit batch — its deep levels are latency bound.
+//                 stored to their bucket, the run that began earlier goes to a "head" list, which is segment-summed
+//                 one partial per lane with a shuffle scan (fan-in 32 per level) until one warp covers it.
+//   4. reduce   : Σ b·B_b via recursive chunked running sums (2 additions per bucket, Horner in the chunk size) down to
+//                 1024 entries per set, then one tail launch (block-wide suffix scan); done ONCE for all columns of a
+//                 commit batch — its deep levels are latency bound.
 // Up to four columns of a batch are in flight on separate streams so that the latency-bound phases of one column
 // (atomics, scans, the entry-count read-back, short combine levels) hide under another column's accumulate.
-// Multi-GPU: batches are dealt by column, small batches split by point range (see msm_batch_srs).
+// A batch may mix the two SRS bases (a base pointer per column). Multi-GPU: q·world columns are dealt by column, the
+// remainder is split by point range (see msm_batch_distribute).
 // Bound: the FMA-heavy (IMAD) pipe — 80 % busy in msm_accumulate_kernel (profiles/ncu_summary_r01.md) — not HBM.
 #include <algorithm>
 #include <chrono>

@@ -3,6 +3,7 @@
 
 #include "prover.cuh"
 #include "collectives.cuh"
+#include "upload.cuh"
 
 using namespace b200zk;
 
@@ -456,6 +457,7 @@ int b200zk_msm_batch(b200zk_ctx* ctx, int basis, const b200zk_fr* const* cols, s
     // groups of up to 8 columns share one staging buffer; within a group the uploads queue on the stream ahead of the MSM
     const size_t group = 8;
     DevBuf<Fr> d(std::min(group, ncols) * n, c.stream);
+    StagedUpload stager(c);
     std::vector<G1Affine> r(ncols);
     for (size_t g0 = 0; g0 < ncols; g0 += group) {
         const size_t g = std::min(group, ncols - g0);
@@ -463,7 +465,12 @@ int b200zk_msm_batch(b200zk_ctx* ctx, int basis, const b200zk_fr* const* cols, s
         for (size_t i = 0; i < g; ++i) {
             if (!cols[g0 + i]) throw std::invalid_argument("msm_batch: null column");
             ptrs[i] = d.get() + i * n;
-            CUDA_CHECK(cudaMemcpyAsync(d.get() + i * n, cols[g0 + i], 32 * n, cudaMemcpyHostToDevice, c.stream));
+            if (n * 32 >= ((size_t)8 << 20) && host_pointer_is_pageable(cols[g0 + i])) {  // pageable column: pinned staging (upload.cuh)
+                stager.start(d.get() + i * n, cols[g0 + i], 32 * n, c.stream);
+                stager.join();
+            } else {
+                CUDA_CHECK(cudaMemcpyAsync(d.get() + i * n, cols[g0 + i], 32 * n, cudaMemcpyHostToDevice, c.stream));
+            }
         }
         msm_batch_srs(c, basis, ptrs.data(), g, n, r.data() + g0);
     }

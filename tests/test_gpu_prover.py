@@ -180,3 +180,15 @@ def test_msm_batch_host_columns(ctx):
             assert np.array_equal(got[i], ctx.msm(c, basis)), (basis, i)
     assert not got[3].any()  # identity = (0, 0)
     assert ctx.msm_batch([], 0).shape == (0, 8)
+
+
+def test_msm_batch_large_pageable_columns(ctx):
+    """Columns of 8 MiB and more in pageable memory take the pinned-staging upload path of b200zk_msm_batch."""
+    k = 18
+    ctx.srs_setup(k)
+    n = 1 << k
+    rng = np.random.default_rng(6)
+    cols = [O.random_fr(rng, n) for _ in range(3)]
+    got = ctx.msm_batch(cols, 1)
+    for i, c in enumerate(cols):
+        assert np.array_equal(got[i], ctx.msm(c, 1)), i

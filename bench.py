@@ -3,19 +3,23 @@
 k=20 (shape S20-bn: 14 gate + 3 lookup + 1 constant columns, 41 MSMs of 2^20, 35 iNTTs, 35 coset NTTs),
 KZG-BN254 / SHPLONK / Blake2b transcript, plus the MSM Mpts/s and NTT GB/s lines the metric names.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--k 20]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--k 20] [--A 14 --L 3 --F 1]
 
-One JSON line on stdout (rank 0). A "step" = one create_proof over one synthetic witness.
+One JSON line on stdout (rank 0). A "step" = one create_proof over one synthetic witness (workload/synth.cpp).
   value  : seconds per proof with the witness already resident in HBM (b200zk_create_proof_dev), CUDA events on the
            library's stream, max over ranks.
-  e2e    : the same through the reference-facing call with HOST buffers (b200zk_create_proof): pinned host witness ->
-           device inside the timed region, proof bytes back on the host.
-  --impl reference : the CPU restatement of halo2's prover (oracle/, all host threads) on a bounded sample of the same
-           workload (same shape at k=17 = 1/8 of the rows), scaled linearly to k=20 — the real Rust prover cannot be built
-           here (no Rust toolchain, un-vendored dependencies).
-N > 1 (torchrun): ONE proof is computed by all ranks together (strong scaling). Every MSM is sharded by contiguous point
-range over the ranks and the per-rank partial bucket sums (128 B per column) are all-gathered over NCCL; the remaining
-stages run replicated in lockstep (same witness, same transcript on every rank). value = seconds per proof.
+  e2e    : the same through the reference-facing call with HOST buffers (b200zk_create_proof) from PAGEABLE host memory —
+           what halo2's create_proof holds (a Rust Vec<Fr>) — host-to-device copies inside the timed region, proof bytes
+           back on the host. `e2e.pinned` is the same call from page-locked memory.
+  roofline : the dominant kernel (msm_accumulate_kernel) against the roof that binds it, the INT32 multiply-add pipe
+           (north_star: "ncu integer-pipe utilisation against the B200's INT32 peak"); the HBM view the contract names
+           (96 bytes per point) is carried under roofline.hbm.
+  --impl reference : the CPU restatement of halo2's prover (oracle/, all host threads) on the SAME configuration: the same
+           circuit at the same k, at most two measured steps (≈ 50 s each at k=20 on 16 threads) and no warm-up, so that the
+           run ends within minutes; `steps` in its line is the number of steps actually timed. The real Rust prover cannot
+           be built here (no Rust toolchain, un-vendored dependencies).
+N > 1 (torchrun): ONE proof is computed by all ranks together (strong scaling): commit batches dealt by column with the
+remainder split by point range, NTTs by column, h(X) by row slice; the partial sums travel over NCCL inside the library.
 """
 import argparse
 import json
@@ -28,11 +32,12 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 SHAPE = dict(A=14, L=3, F=1)  # S20-bn / its k-scaled versions
 emit = None
-IMAD_PEAK_TOPS = 18.0  # measured by tools/microbench.cu on this pool's B200 (profiles/microbench_r01.json)
+# multiply-add instructions on the FMA-heavy pipe per Montgomery product / square (cuobjdump of build/*.o)
+IMAD_PER_MUL, IMAD_PER_SQR = 138, 108
+MADD_MUL, MADD_SQR = 8, 2  # XYZZ mixed addition (madd-2008-s): 8 products + 2 squares
 
 
 def parse():
@@ -45,7 +50,8 @@ def parse():
     p.add_argument("--A", type=int, default=SHAPE["A"], help="gate advice columns (default: S20-bn)")
     p.add_argument("--L", type=int, default=SHAPE["L"], help="lookup advice columns")
     p.add_argument("--F", type=int, default=SHAPE["F"], help="constant columns")
-    p.add_argument("--sample-k", type=int, default=17, help="k of the bounded CPU sample")
+    p.add_argument("--sample-k", type=int, default=17, help="k of the bounded CPU sample in the GPU arm's cpu_baseline")
+    p.add_argument("--ref-max-steps", type=int, default=2, help="reference arm: measured steps are capped at this")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-extras", action="store_true", help="skip the MSM / NTT side lines")
     return p.parse_args()
@@ -87,6 +93,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        self.thread.join(timeout=5)
         sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -94,16 +101,16 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_sample(k, threads=None):
-    """Oracle (restated halo2 CPU prover, std::thread on all host cores) on the same shape at k: returns seconds."""
-    import numpy as np  # noqa: F401
-
-    import b200zk
+def cpu_prover(k, threads=None):
+    """Oracle (restated halo2 CPU prover, std::thread on all host cores) for the bench shape at k. The circuit comes from the
+    workload library, so this path maps neither libb200zk nor torch. Returns (step() -> (seconds, proof), cores, pk)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
+    import workload
 
     if threads:
         O.lib().oracle_set_threads(threads)
-    fixed, advice, copies = b200zk.synth_circuit(k, SHAPE["A"], SHAPE["L"], SHAPE["F"], seed=0)
+    fixed, advice, copies = workload.synth_circuit(k, SHAPE["A"], SHAPE["L"], SHAPE["F"], seed=0)
     params = O.Params.setup(k)
     pk = O.ProvingKey(params, k, SHAPE["A"], SHAPE["L"], SHAPE["F"], fixed, copies)
 
@@ -115,31 +122,44 @@ def cpu_sample(k, threads=None):
 
 
 def run_reference(args, rank):
-    """--impl reference: the reference's CPU implementation of the path (oracle port) on the box's host cores."""
+    """--impl reference: the reference's CPU implementation of the path (oracle port) on the box's host cores, on the
+    configuration the GPU arm runs (same circuit, same k). Rank 0 alone works."""
     if rank != 0:
         return
-    step, cores, pk = cpu_sample(args.sample_k)
-    for _ in range(args.warmup):
-        step()
+    t_setup = time.time()
+    step, cores, pk = cpu_prover(args.k)
+    t_setup = time.time() - t_setup
+    steps = max(1, min(args.steps, args.ref_max_steps))
     t = []
-    for _ in range(args.steps):
+    for _ in range(steps):
         s, proof = step()
         t.append(s)
-    assert pk.verify(proof)[0]
-    scale = float(1 << (args.k - args.sample_k))
-    sample_s = sum(t) / len(t)
-    value = sample_s * scale
+    ok, err = pk.verify(proof)
+    if not ok:
+        raise SystemExit(f"bench.py: the oracle rejected its own proof: {err}")
+    value = sum(t) / len(t)
     line = {
-        "impl": "reference", "metric": "create_proof_s", "value": value, "unit": "s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "impl": "reference", "metric": "create_proof_s", "value": value, "unit": "s", "n_gpus": args.gpus, "steps": steps, "warmup": 0,
+        "steps_requested": args.steps, "warmup_requested": args.warmup,
         "ms_per_step": value * 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (254-bit Montgomery)",
         "data": "synthetic", "config": {"workload": workload_name(args.k)},
         "cpu_baseline": {"value": value, "unit": "s", "cores": cores, "kind": "port",
-                         "sample": f"same shape at k={args.sample_k} ({sample_s:.3f} s per create_proof, mean of {args.steps}), scaled x{int(scale)} "
-                                   f"(rows) to k={args.k}; restated halo2 CPU algorithms (C++ oracle), not the rayon binary"},
+                         "sample": f"the whole configuration: create_proof at k={args.k}, {steps} measured step(s) of {[round(x, 2) for x in t]} s, no warm-up "
+                                   f"(SRS + keygen_pk on the CPU took {t_setup:.0f} s, untimed); restated halo2 CPU algorithms (C++ oracle, std::thread), "
+                                   "not the rayon binary — Rust is not available here"},
         "e2e": {"value": value, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def ncu_traffic(kernel):
+    """dram bytes per launch of `kernel` from the committed ncu capture (profiles/ncu_traffic.json), or None."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kernel]
+        return float(rec["dram_bytes_per_launch"]), rec.get("source", "profiles/ncu_traffic.json")
+    except Exception:
+        return None, "no committed ncu capture for this kernel"
 
 
 def main():
@@ -157,11 +177,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank)
-        return
+        return 0
     import numpy as np
     import torch
 
     import b200zk
+    import workload
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — libb200zk has no CPU fallback (use --impl reference for the CPU arm)")
@@ -170,30 +191,29 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
-
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     k, A, L, F = args.k, SHAPE["A"], SHAPE["L"], SHAPE["F"]
     n = 1 << k
     ctx = b200zk.Context(local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
-    if world > 1:  # MSM point-range shards + NCCL all-gather of the partial sums
+    if world > 1:  # the library builds its own NCCL communicator; the callback only carries the 128-byte bootstrap id
         ctx.set_allgather(rank, world, b200zk.torch_allgather(dist, torch.device("cuda", local_rank)))
     # ---- untimed setup: SRS on the device, synthetic circuit, keygen ----
     t0 = time.time()
     ctx.srs_setup(k)  # ParamsKZG::setup(k, ChaCha20Rng::from_seed([0;32])) like halo2-base gen_srs
     t_srs = time.time() - t0
-    fixed, advice, copies = b200zk.synth_circuit(k, A, L, F, seed=0)
+    fixed, advice, copies = workload.synth_circuit(k, A, L, F, seed=0)
     t0 = time.time()
     pk = ctx.keygen(k, A, L, F, fixed, copies)
     t_keygen = time.time() - t0
     del fixed, copies
-    pinned = torch.from_numpy(advice.view(np.int64).reshape(-1)).pin_memory()
-    host_advice = pinned.numpy().view(np.uint64)
+    pageable_advice = np.ascontiguousarray(advice).reshape(-1)  # what a Rust Vec<Fr> is: ordinary pageable memory
+    pinned = torch.from_numpy(pageable_advice.view(np.int64)).pin_memory()
+    pinned_advice = pinned.numpy().view(np.uint64)
     dev_advice = torch.empty(pinned.numel(), dtype=torch.int64, device="cuda")
     dev_advice.copy_(pinned)
     torch.cuda.synchronize()
     advice_bytes = pinned.numel() * 8
-    launches0 = b200zk.launch_count()
 
     def barrier():
         torch.cuda.synchronize()
@@ -220,7 +240,8 @@ def main():
         return ms / steps, wall / steps, out
 
     step_dev = lambda: pk.create_proof(None, 0, device_ptr=dev_advice.data_ptr())  # noqa: E731
-    step_host = lambda: pk.create_proof(host_advice, 0)  # noqa: E731
+    step_pageable = lambda: pk.create_proof(pageable_advice, 0)  # noqa: E731
+    step_pinned = lambda: pk.create_proof(pinned_advice, 0)  # noqa: E731
     for _ in range(max(args.warmup, 0)):
         step_dev()
     l_before = b200zk.launch_count()
@@ -229,28 +250,39 @@ def main():
     ms_dev, wall_dev, proof = timed(step_dev, args.steps)
     launches = (b200zk.launch_count() - l_before) // max(args.steps, 1)
     for _ in range(min(args.warmup, 2)):
-        step_host()
-    ms_host, wall_host, proof_h = timed(step_host, args.steps)
+        step_pageable()
+    ms_host, wall_host, proof_h = timed(step_pageable, args.steps)
+    step_pinned()
+    ms_pin, wall_pin, proof_p = timed(step_pinned, max(1, min(args.steps, 3)))
     clocks = sampler.stop()
-    assert proof == proof_h and len(proof) == pk.proof_size()
+    ok = proof == proof_h == proof_p and len(proof) == pk.proof_size()
     # ---- one profiled step: per-stage split + dominant-kernel durations by CUDA events on the launching stream ----
     # (two untimed steps: the stage split with the normal stream overlap, then the event profiler, under which the MSM
     # columns run one at a time so that a kernel's bracketed duration is its own and comparable with the ncu launch list)
     _, stages = pk.create_proof(None, 0, timings=True, device_ptr=dev_advice.data_ptr())
     ctx.profile_enable(True)
     pk.create_proof(None, 0, device_ptr=dev_advice.data_ptr())
+    acc_adds = ctx.profile_work("msm_accumulate")
+    ntt_bfly = ctx.profile_work("ntt_pass")
     acc_ms, acc_n = ctx.profile_get("msm_accumulate")
     ntt_ms, ntt_n = ctx.profile_get("ntt_pass")
     q_ms, q_n = ctx.profile_get("quotient")
     ctx.profile_enable(False)
-    n_msm = acc_n
     if world > 1:
         # the sharded proof must be the single-GPU proof: every rank recomputes it alone (untimed, after the last sharded
-        # call) and compares the bytes
+        # call) and compares the bytes; the verdict is agreed on by all ranks before anyone leaves
         ctx.set_allgather(0, 1, None)
         alone = pk.create_proof(None, 0, device_ptr=dev_advice.data_ptr())
-        if alone != proof:
-            raise SystemExit(f"bench.py: rank {rank}: the proof sharded over {world} GPUs differs from the single-GPU proof")
+        ok = ok and alone == proof
+        flag = torch.tensor([0 if ok else 1], device="cuda", dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        ok = flag.item() == 0
+    if not ok:
+        pk.close()
+        ctx.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        raise SystemExit(f"bench.py: rank {rank}: proofs differ (device-resident / host witness" + (f" / sharded over {world} GPUs vs one GPU)" if world > 1 else ")"))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -258,18 +290,32 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    # dominant kernel = msm_accumulate_kernel: algorithmic bytes per launch = 96·n (32 B scalar + 64 B base per point)
+    imad_peak, imad_src = 18.0, "fallback 18.0 T/s (round-1 measurement)"
+    try:
+        mb = json.load(open(os.path.join(ROOT, "profiles", "microbench_r02.json")))
+        imad_peak, imad_src = float(mb["imad_Tops"]), "measured: dependent-free IMAD issue rate, tools/microbench.cu (profiles/microbench_r02.json)"
+    except Exception:
+        pass
+    # dominant kernel = msm_accumulate_kernel. Integer roof: one XYZZ mixed addition = 8 Montgomery products + 2 squares
+    # = 8·138 + 2·108 multiply-add instructions on the FMA-heavy pipe; additions per launch counted by the library.
     acc_avg_ms = acc_ms / max(acc_n, 1)
-    alg_bytes = 96.0 * n
-    achieved = alg_bytes / (acc_avg_ms * 1e-3) / 1e9 if acc_avg_ms > 0 else 0.0
-    roofline = {"kernel": "msm_accumulate_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": 1.844e9, "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of the 2^20 uniform-scalar launch "
-                                                      "(profiles/ncu_summary_r01.md); one 64-byte base gathered per non-zero digit",
-                "peak_source": peak_src, "launches": acc_n, "avg_launch_ms": acc_avg_ms, "share_of_step": acc_ms / (ms_dev if ms_dev else 1),
+    imad_per_add = MADD_MUL * IMAD_PER_MUL + MADD_SQR * IMAD_PER_SQR
+    adds_per_launch = acc_adds / max(acc_n, 1)
+    achieved_tops = adds_per_launch * imad_per_add / (acc_avg_ms * 1e-3) / 1e12 if acc_avg_ms > 0 else 0.0
+    alg_bytes = 96.0 * n  # 32 B scalar + 64 B base per point
+    achieved_gbs = alg_bytes / (acc_avg_ms * 1e-3) / 1e9 if acc_avg_ms > 0 else 0.0
+    traffic, traffic_src = ncu_traffic("msm_accumulate_kernel")
+    roofline = {"kernel": "msm_accumulate_kernel", "bound": "int32", "achieved": achieved_tops, "peak": imad_peak, "unit": "T multiply-add/s",
+                "frac": achieved_tops / imad_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": imad_src,
+                "work": {"mixed_additions_per_launch": adds_per_launch, "multiply_adds_per_addition": imad_per_add,
+                         "basis": "XYZZ madd-2008-s = 8 products (138 IMAD-class each) + 2 squares (108 each); additions counted by the library"},
+                "hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                        "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
+                "launches": acc_n, "avg_launch_ms": acc_avg_ms, "share_of_step": acc_ms / (ms_dev if ms_dev else 1),
                 "timing": "CUDA events on the launching stream around every launch of one untimed step in which the MSM columns run one at a time "
                           "(in the timed steps up to four columns overlap on separate streams)",
-                "note": "integer-pipe bound by design (north_star: no tensor cores, IMAD carry chains): ncu shows the FMA-heavy (IMAD) pipe 80 % "
-                        "busy in this kernel (profiles/ncu_summary_r01.md); the HBM fraction is reported because the contract asks for it"}
+                "note": "integer-pipe bound by design (north_star: no tensor cores, IMAD carry chains); carry-flag forms of IMAD.WIDE issue at half "
+                        "rate on sm_100 (profiles/microbench_r02.json), which caps a 32-bit-limb multiplier near 0.5 of this peak"}
     line = {
         "metric": "create_proof_s", "value": ms_dev / 1e3, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
         "higher_is_better": False, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "u32 limbs (254-bit Montgomery integers)",
@@ -279,33 +325,41 @@ def main():
                    "rng": "StdRng::seed_from_u64(0)",
                    "srs": "ParamsKZG::setup(k, ChaCha20Rng::from_seed([0;32])) generated on device"},
         "clocks": clocks,
-        "e2e": {"value": ms_host / 1e3, "unit": "s", "h2d_bytes_per_step": advice_bytes, "d2h_bytes_per_step": len(proof) + n_msm * 16 * 128,
-                "wall_s": wall_host, "api": "b200zk_create_proof (host witness in pinned memory -> proof bytes on host)"},
+        "e2e": {"value": ms_host / 1e3, "unit": "s", "h2d_bytes_per_step": advice_bytes, "d2h_bytes_per_step": len(proof) + acc_n * 16 * 128,
+                "wall_s": wall_host, "api": "b200zk_create_proof (host witness in PAGEABLE memory, as a Rust Vec<Fr> is -> proof bytes on host)",
+                "pinned": {"value": ms_pin / 1e3, "wall_s": wall_pin, "note": "the same call from page-locked host memory"}},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "stages_ms": {k_: round(v * 1e3, 2) for k_, v in stages.items()},
         "setup_s": {"srs_device": round(t_srs, 2), "keygen_pk": round(t_keygen, 2)},
         "proof_bytes": len(proof),
+        "kernels_in_profiled_step": {"msm_accumulate": {"ms": acc_ms, "launches": acc_n, "mixed_additions": acc_adds},
+                                     "ntt_pass": {"ms": ntt_ms, "launches": ntt_n, "butterflies": ntt_bfly,
+                                                  "Gbutterfly_s": ntt_bfly / (ntt_ms * 1e-3) / 1e9 if ntt_ms else None},
+                                     "quotient": {"ms": q_ms, "launches": q_n}},
     }
     if rank == 0 and world == 1 and not args.no_extras:  # single-GPU side lines (a sharded context would wait for its peers)
-        line.update(side_lines(ctx, stream, torch, np, k, acc_ms, acc_n, ntt_ms, ntt_n, q_ms, q_n))
+        line.update(side_lines(ctx, stream, torch, np, k))
+    pk.close()
+    ctx.close()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:  # the contract asks for it at N=1 only
-        step, cores, opk = cpu_sample(args.sample_k)
-        t0 = time.time()
+        step, cores, opk = cpu_prover(args.sample_k)
+        step()  # warm-up (page faults, thread pool)
         secs, oproof = step()
         scale = float(1 << (k - args.sample_k))
         line["cpu_baseline"] = {"value": secs * scale, "unit": "s", "cores": cores, "kind": "port",
-                                "sample": f"oracle create_proof on the same shape at k={args.sample_k}: {secs:.3f} s, scaled x{int(scale)} (rows) to k={k}; "
+                                "sample": f"bounded sample: oracle create_proof on the same shape at k={args.sample_k} ({secs:.3f} s after one warm-up run), scaled "
+                                          f"x{int(scale)} (rows) to k={k}; the reference arm (bench.py --impl reference) times the whole k={k} configuration; "
                                           "restated halo2 CPU algorithms (C++ oracle, std::thread), not the rayon binary"}
     if rank == 0:
         emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
-    os._exit(0)
+    return 0
 
 
-def side_lines(ctx, stream, torch, np, k, acc_ms, acc_n, ntt_ms, ntt_n, q_ms, q_n):
+def side_lines(ctx, stream, torch, np, k):
     """MSM Mpts/s and NTT GB/s (the other two parts of BASELINE.json's metric) at the workload's size, device-resident."""
     n = 1 << k
     rng = np.random.default_rng(0)
@@ -339,16 +393,15 @@ def side_lines(ctx, stream, torch, np, k, acc_ms, acc_n, ntt_ms, ntt_n, q_ms, q_
     ntt_batch_ms = ev(lambda: ctx.ntt_dev(buf.data_ptr(), k, omega, 4, n), 5)
     ext = torch.empty(4 * n * 4, dtype=torch.int64, device="cuda")
     coset_ms = ev(lambda: ctx.coeff_to_extended_dev(k, buf.data_ptr(), ext.data_ptr()), 5)
-    return {
+    out = {
         "msm": {"n": n, "scalars": "uniform Fr", "ms": msm_ms, "Mpts_s": n / msm_ms / 1e3},
         "ntt": {"n": n, "batch": 4, "ms": ntt_batch_ms, "GBps_64nB": 64.0 * n * 4 / (ntt_batch_ms * 1e-3) / 1e9,
                 "Gbutterfly_s": 4 * (n // 2) * k / (ntt_batch_ms * 1e-3) / 1e9},
         "coset_ntt": {"n": n, "ms": coset_ms, "GBps_160n": 160.0 * n / (coset_ms * 1e-3) / 1e9},
-        "int_pipe": {"peak_Tops": IMAD_PEAK_TOPS, "peak_source": "tools/microbench.cu IMAD issue rate on this pool's B200 (profiles/microbench_r01.json)",
-                     "kernel_ms_in_profiled_step": {"msm_accumulate": acc_ms, "ntt_pass": ntt_ms, "quotient": q_ms},
-                     "launches": {"msm_accumulate": acc_n, "ntt_pass": ntt_n, "quotient": q_n}},
     }
+    del buf, ext
+    return out
 
 
 if __name__ == "__main__":
-    main()
+    sys.exit(main())

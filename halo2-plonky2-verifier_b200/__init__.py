@@ -48,7 +48,6 @@ def lib():
         _lib.b200zk_launch_count.restype = ctypes.c_ulonglong
         _lib.b200zk_proof_size.restype = ctypes.c_size_t
         _lib.b200zk_num_sets.restype = ctypes.c_uint32
-        _lib.b200zk_synth_max_copies.restype = ctypes.c_size_t
         _lib.b200zk_srs_file_size.restype = ctypes.c_size_t
     return _lib
 
@@ -148,6 +147,12 @@ class Context:
 
     def profile_enable(self, on=True):
         self._check(lib().b200zk_profile_enable(self._h, int(bool(on))))
+
+    def profile_work(self, name):
+        """Algorithmic work of the recorded spans (mixed additions / butterflies / rows); call before profile_get."""
+        units = ctypes.c_double(0)
+        self._check(lib().b200zk_profile_work(self._h, self.PROF_IDS[name], ctypes.byref(units)))
+        return units.value
 
     def profile_get(self, name):
         ms = ctypes.c_double(0)
@@ -450,15 +455,16 @@ class ProvingKey:
 
 
 def synth_circuit(k, A, L, F, seed=0):
-    """Host-only generator of a satisfying circuit of the halo2-base shape (see csrc/synth.cu): returns
-    (fixed [F+1+A, n, 4], advice [A+L, n, 4], copies [m, 4])."""
-    n = 1 << k
-    fixed = np.empty((F + 1 + A, n, 4), dtype=np.uint64)
-    advice = np.empty((A + L, n, 4), dtype=np.uint64)
-    maxc = int(lib().b200zk_synth_max_copies(k, A, L, F))
-    copies = np.empty((maxc, 4), dtype=np.uint32)
-    nc = ctypes.c_size_t(0)
-    rc = lib().b200zk_synth_circuit(k, A, L, F, ctypes.c_uint64(seed), _p(fixed), _p(advice), _p(copies), ctypes.byref(nc))
-    if rc != OK:
-        raise B200zkError(rc, "synth_circuit failed")
-    return fixed, advice, copies[: nc.value].copy()
+    """Synthetic circuit of the halo2-base shape: forwards to the workload generator (workload/synth.cpp), which is its own
+    small host library — the product library carries no test-input code."""
+    import sys
+
+    root = os.path.dirname(_HERE)
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import workload
+
+    try:
+        return workload.synth_circuit(k, A, L, F, seed)
+    except ValueError as e:
+        raise B200zkError(EINVAL, str(e))

@@ -81,6 +81,13 @@ int b200zk_create(int device, b200zk_ctx** out) {
     }
     ctx->c.arena.stream = ctx->c.stream;
     arena_register(ctx->c.stream, &ctx->c.arena);
+    try {  // kernel attributes are per device: every context sets them for its own
+        ntt_init_device();
+        msm_init_device();
+    } catch (const std::exception&) {
+        b200zk_destroy(ctx);
+        return B200ZK_ECUDA;
+    }
     *out = ctx;
     return B200ZK_OK;
 }
@@ -132,6 +139,7 @@ unsigned long long b200zk_launch_count(void) { return g_launch_count; }
 int b200zk_profile_enable(b200zk_ctx* ctx, int on) {
     API_BEGIN(ctx)
     CUDA_CHECK(cudaStreamSynchronize(ctx->c.stream));
+    std::lock_guard<std::mutex> plk(g_prof_mu);
     for (auto& sp : g_prof_spans) {
         cudaEventDestroy(sp.a);
         cudaEventDestroy(sp.b);
@@ -146,6 +154,7 @@ int b200zk_profile_get(b200zk_ctx* ctx, int id, double* total_ms, unsigned long 
     CUDA_CHECK(cudaStreamSynchronize(ctx->c.stream));
     double tot = 0;
     unsigned long long cnt = 0;
+    std::lock_guard<std::mutex> plk(g_prof_mu);
     for (auto& sp : g_prof_spans) {
         if (sp.id != id) continue;
         float ms = 0;
@@ -155,6 +164,16 @@ int b200zk_profile_get(b200zk_ctx* ctx, int id, double* total_ms, unsigned long 
     }
     *total_ms = tot;
     *launches = cnt;
+    API_END(ctx)
+}
+int b200zk_profile_work(b200zk_ctx* ctx, int id, double* units) {
+    API_BEGIN(ctx)
+    if (!units) throw std::invalid_argument("profile_work: null argument");
+    double tot = 0;
+    std::lock_guard<std::mutex> plk(g_prof_mu);
+    for (auto& sp : g_prof_spans)
+        if (sp.id == id) tot += sp.work;
+    *units = tot;
     API_END(ctx)
 }
 int b200zk_set_allgather(b200zk_ctx* ctx, int rank, int world, b200zk_allgather_fn fn, void* user) {
@@ -673,7 +692,9 @@ int b200zk_host_selftest(uint64_t seed, size_t iters) {
     };
     for (size_t it = 0; it < iters; ++it) {
         const Fr a = rnd(), b = rnd(), c = rnd();
-        if (!f_eq(f_mul_chains(a, b), f_mul_host64(a, b))) return -10;                       // both multipliers agree
+        if (!f_eq(f_mul_chains(a, b), f_mul_host64(a, b))) return -10;                       // the multipliers agree
+        if (!f_eq(f_mul_comba(a, b), f_mul_host64(a, b))) return -16;
+        if (!f_eq(f_sqr_comba(a), f_mul_host64(a, a))) return -17;
         if (!f_eq(f_mul(a, f_add(b, c)), f_add(f_mul(a, b), f_mul(a, c)))) return -11;       // distributivity
         if (!f_eq(f_sub(f_add(a, b), b), a)) return -12;
         if (!f_is_zero(a) && !f_eq(f_mul(a, f_inv(a)), f_one<FrCfg>())) return -13;
@@ -684,6 +705,7 @@ int b200zk_host_selftest(uint64_t seed, size_t iters) {
         x.l[7] &= 0x0fffffffu;
         y.l[7] &= 0x0fffffffu;
         if (!f_eq(f_mul_chains(x, y), f_mul_host64(x, y))) return -15;
+        if (!f_eq(f_mul_comba(x, y), f_mul_host64(x, y)) || !f_eq(f_sqr_comba(x), f_mul_host64(x, x))) return -18;
     }
     // group laws on the generator: (2G + G) + G == 2·(2G), 5G - 5G == 0, mixed add == full add
     G1Affine gen;
@@ -767,7 +789,9 @@ int b200zk_permute_expression_pair(b200zk_ctx* ctx, uint32_t k, const b200zk_fr*
     DevBuf<Fr> din(n, s), dtab(n, s), da(n, s), ds(n, s);
     CUDA_CHECK(cudaMemcpyAsync(din.get(), input, 32 * n, cudaMemcpyHostToDevice, s));
     CUDA_CHECK(cudaMemcpyAsync(dtab.get(), table, 32 * n, cudaMemcpyHostToDevice, s));
-    if (!lookup_permute(ctx->c, din.get(), dtab.get(), da.get(), ds.get(), n, u)) throw SynthesisError("ConstraintSystemFailure: lookup input not in table");
+    const int st = lookup_permute(ctx->c, din.get(), dtab.get(), da.get(), ds.get(), n, u);
+    if (st & LOOKUP_UNSUPPORTED) throw std::invalid_argument("permute_expression_pair: unsupported table — every input and table value must be < 2^k (range-style tables)");
+    if (st & LOOKUP_NOT_IN_TABLE) throw SynthesisError("ConstraintSystemFailure: lookup input not in table");
     CUDA_CHECK(cudaMemcpyAsync(a_out, da.get(), 32 * u, cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaMemcpyAsync(s_out, ds.get(), 32 * u, cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));

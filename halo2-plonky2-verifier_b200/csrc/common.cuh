@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <stdexcept>
@@ -202,7 +203,7 @@ struct NttPlan {
 };
 void build_twiddle_table(Fr* table, const Fr& omega, uint32_t log_n, cudaStream_t stream);
 int ntt_num_passes(uint32_t log_n);
-extern unsigned long long g_launch_count;  // kernels launched by this library (bench "gpu_launches")
+extern std::atomic<unsigned long long> g_launch_count;  // kernels launched by this library (bench "gpu_launches")
 
 // Optional per-kernel-family timing with CUDA events on the launching stream (bench.py roofline section).
 // Disabled by default: when off, prof_begin/prof_end are a branch on a global flag.
@@ -210,21 +211,30 @@ enum ProfId { PROF_MSM_ACCUMULATE = 0, PROF_MSM_OTHER, PROF_NTT_PASS, PROF_QUOTI
 struct ProfSpan {
     int id;
     cudaEvent_t a, b;
+    double work;  // units of algorithmic work of the launch: mixed additions (MSM), butterflies (NTT), extended rows (h)
 };
 extern bool g_prof_enabled;
 extern std::vector<ProfSpan> g_prof_spans;
-inline void prof_begin(int id, cudaStream_t s) {
-    if (!g_prof_enabled) return;
+extern std::mutex g_prof_mu;  // contexts on several devices may record spans from different threads
+void ntt_init_device();
+void msm_init_device();
+// returns a handle for prof_end (-1 when profiling is off)
+inline int prof_begin(int id, cudaStream_t s, double work = 0) {
+    if (!g_prof_enabled) return -1;
     ProfSpan sp;
     sp.id = id;
+    sp.work = work;
     cudaEventCreate(&sp.a);
     cudaEventCreate(&sp.b);
     cudaEventRecord(sp.a, s);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     g_prof_spans.push_back(sp);
+    return (int)g_prof_spans.size() - 1;
 }
-inline void prof_end(cudaStream_t s) {
-    if (!g_prof_enabled) return;
-    cudaEventRecord(g_prof_spans.back().b, s);
+inline void prof_end(int handle, cudaStream_t s) {
+    if (handle < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEventRecord(g_prof_spans[handle].b, s);
 }
 
 }  // namespace b200zk

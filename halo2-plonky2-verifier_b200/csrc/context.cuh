@@ -105,6 +105,7 @@ struct Context {
     int rank = 0, world = 1;
     AllGatherFn allgather = nullptr;
     void* allgather_user = nullptr;
+    double exchange_seconds = 0;  // host time spent in the cross-rank exchange of partial MSM sums (reported under "other")
     bool msm_tables_enabled = true;
     std::shared_ptr<struct Nccl> nccl;  // collectives.cuh, created on first use when world > 1
 

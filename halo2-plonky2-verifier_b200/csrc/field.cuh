@@ -10,6 +10,9 @@
 // two independent mad.lo.cc/madc.hi.cc chains of four wide multiply-adds that ptxas fuses into
 // IMAD.WIDE.U32(.X) carry chains: 16 wide IMADs + 1 IMAD per limb of b, 136 per product. Retiring one limb per
 // row swaps the roles of E and O; the one-limb merge carry is fed into the next row's first chain.
+// Device square: product scanning with 36 instead of 64 partial products (f_sqr_comba). Three other multipliers were
+// measured and are kept as tested alternatives: product scanning with predicate carries (f_mul_comba), 29-bit unsaturated
+// limbs (f_mul_u29) — both slower than the carry chains on B200, see the comments at their definitions.
 // The host bodies of the same row primitives (explicit carry variable) are what the CPU tests exercise and
 // what the host side of the prover uses for its handful of scalar operations.
 #pragma once
@@ -325,6 +328,103 @@ HD Field<C> f_mul_chains(const Field<C>& a, const Field<C>& b) {
     uint32_t c = add8(t.l, E + 1, O);
     return f_reduce_once<C>(t, c);
 }
+// ---- product scanning (Comba) with predicate carries ------------------------------------------------------------------------
+// Every partial product is added into a three-word column accumulator (t0,t1,t2) with an IMAD.WIDE.U32 that writes its
+// carry-OUT to a predicate and takes no carry-IN; the carries are counted into t2 by IADD3.X on the ALU pipe (ptxas folds
+// two carry predicates into one IADD3.X) and Montgomery reduction is interleaved column by column (FIPS): 122
+// IMAD.WIDE.U32 + 8 IMAD.HI + 8 IMAD, no .X multiply-adds at all, 30 registers. MEASURED on B200 (tools/microbench.cu,
+// profiles/microbench_r02.json): an IMAD.WIDE.U32 that writes a carry predicate issues at 8.6 T/s — the same half rate as
+// the carry-in form IMAD.WIDE.U32.X (9.2 T/s; plain IMAD.WIDE.U32: 17.2 T/s). So any 32-bit-limb multiplier whose
+// multiply-adds touch the carry flag is bound by ≈ 4 cycles per multiply-add per SM sub-partition: f_mul_comba reaches
+// 65 G products/s against 67 G/s for the carry chains, and the chains stay the default product. The SQUARE is different:
+// product scanning lets it use 36 instead of 64 partial products (108 instead of 138 multiply-adds) and f_sqr_comba reaches
+// 79 G/s, so f_sqr uses it.
+#if defined(__CUDA_ARCH__)
+DEV void mac3(uint32_t& t0, uint32_t& t1, uint32_t& t2, uint32_t x, uint32_t y) {
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+        "addc.u32 %2, %2, 0;"
+        : "+r"(t0), "+r"(t1), "+r"(t2)
+        : "r"(x), "r"(y));
+}
+#else
+inline void mac3(uint32_t& t0, uint32_t& t1, uint32_t& t2, uint32_t x, uint32_t y) {
+    const uint64_t prod = (uint64_t)x * y, lo = (uint64_t)t0 + (uint32_t)prod, hi = (uint64_t)t1 + (prod >> 32) + (lo >> 32);
+    t0 = (uint32_t)lo;
+    t1 = (uint32_t)hi;
+    t2 += (uint32_t)(hi >> 32);
+}
+#endif
+// Montgomery product a·b·2^-256 mod P, canonical. Precondition: a < P; b any value < 2^256.
+template <class C>
+HD Field<C> f_mul_comba(const Field<C>& a, const Field<C>& b) {
+    uint32_t t0 = 0, t1 = 0, t2 = 0, m[8];
+    Field<C> r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int j = 0; j < i; ++j) {
+            mac3(t0, t1, t2, a.l[j], b.l[i - j]);
+            mac3(t0, t1, t2, m[j], C::P(i - j));
+        }
+        mac3(t0, t1, t2, a.l[i], b.l[0]);
+        m[i] = t0 * C::INV;
+        mac3(t0, t1, t2, m[i], C::P(0));  // t0 becomes 0
+        t0 = t1;
+        t1 = t2;
+        t2 = 0;
+    }
+#pragma unroll
+    for (int i = 8; i < 16; ++i) {
+#pragma unroll
+        for (int j = i - 7; j < 8; ++j) {
+            mac3(t0, t1, t2, a.l[j], b.l[i - j]);
+            mac3(t0, t1, t2, m[j], C::P(i - j));
+        }
+        r.l[i - 8] = t0;
+        t0 = t1;
+        t1 = t2;
+        t2 = 0;
+    }
+    return f_reduce_once<C>(r, t0);
+}
+// Montgomery square, a < P (< 2^254). The cross products 2·a_j·a_l (j < l) are taken against the limbs of the doubled
+// upper part of a — d_l = limb l of 2a for l > j+1, and a_l << 1 (no incoming bit) for l = j+1 — so a column needs one
+// multiply-add per unordered pair: 36 instead of 64 products for a·a, 108 instead of 136 in all.
+template <class C>
+HD Field<C> f_sqr_comba(const Field<C>& a) {
+    uint32_t d[8], e[8];
+#pragma unroll
+    for (int l = 1; l < 8; ++l) {
+        d[l] = (a.l[l] << 1) | (a.l[l - 1] >> 31);
+        e[l] = a.l[l] << 1;
+    }
+    uint32_t t0 = 0, t1 = 0, t2 = 0, m[8];
+    Field<C> r;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int l = i - j;
+            if (l > j && l < 8) mac3(t0, t1, t2, a.l[j], l == j + 1 ? e[l] : d[l]);
+        }
+        if ((i & 1) == 0 && i / 2 < 8) mac3(t0, t1, t2, a.l[i / 2], a.l[i / 2]);
+        if (i < 8) {
+#pragma unroll
+            for (int j = 0; j < i; ++j) mac3(t0, t1, t2, m[j], C::P(i - j));
+            m[i] = t0 * C::INV;
+            mac3(t0, t1, t2, m[i], C::P(0));
+        } else {
+#pragma unroll
+            for (int j = i - 7; j < 8; ++j) mac3(t0, t1, t2, m[j], C::P(i - j));
+            r.l[i - 8] = t0;
+        }
+        t0 = t1;
+        t1 = t2;
+        t2 = 0;
+    }
+    return f_reduce_once<C>(r, t0);
+}
 // ---- unsaturated multiplier: 29-bit limbs, carry-free column accumulation ------------------------------------------------
 // On sm_100 the carry-chained IMAD.WIDE.U32.X issues at half the rate of plain IMAD.WIDE.U32 (tools/microbench:
 // 9.1 vs 17.2 T/s) and 104 of the 139 multiply-adds of f_mul_chains are .X forms. Here both operands are re-sliced into
@@ -452,18 +552,25 @@ inline Field<C> f_mul_host64(const Field<C>& a, const Field<C>& b) {
 template <class C>
 HD Field<C> f_mul(const Field<C>& a, const Field<C>& b) {
 #if defined(__CUDA_ARCH__)
-#if defined(B200ZK_MUL_U29)  // measured alternative: 43–45 G mul/s vs 67 G mul/s for the carry chains (profiles/README.md)
+#if defined(B200ZK_MUL_U29)  // measured alternative: 43–45 G mul/s (profiles/README.md)
     return f_mul_u29<C>(a, b);
+#elif defined(B200ZK_MUL_COMBA)  // measured alternative: 65 G mul/s (profiles/microbench_r02.json)
+    return f_mul_comba<C>(a, b);
 #else
-    return f_mul_chains<C>(a, b);
+    return f_mul_chains<C>(a, b);  // 67 G mul/s
 #endif
 #else
     return f_mul_host64<C>(a, b);
 #endif
 }
+// squaring: the product-scanning form needs 108 instead of 138 multiply-adds — 79 G/s against 67 G/s for f_mul(a, a)
 template <class C>
 HD Field<C> f_sqr(const Field<C>& a) {
+#if defined(__CUDA_ARCH__) && !defined(B200ZK_MUL_U29) && !defined(B200ZK_SQR_BY_MUL)
+    return f_sqr_comba<C>(a);
+#else
     return f_mul<C>(a, a);
+#endif
 }
 // out of Montgomery form: a·2^-256 mod P (canonical integer limbs)
 template <class C>

@@ -365,6 +365,10 @@ __global__ void __launch_bounds__(TAIL_THREADS) msm_reduce_tail_kernel(const G1X
     }
     if (t == 0) g1x_store(F_out + g, nxt[0]);
 }
+// per-device kernel attributes; called by b200zk_create for its device
+void msm_init_device() {
+    CUDA_CHECK(cudaFuncSetAttribute(msm_reduce_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * TAIL_THREADS * sizeof(G1X))));
+}
 // one thread per window: Horner over the levels, starting from the tail's F and S
 struct HornerLevels {
     uint32_t log_m[16];
@@ -442,10 +446,10 @@ static void msm_issue_accumulate(MsmSlot& sl, const G1Affine* bases, const Fr* s
     uint32_t chunk = ACC_T_MAX;
     while (chunk > (uint32_t)ACC_T_MIN && (uint64_t)total / chunk < (uint64_t)148 * 16 * 32) chunk >>= 1;
     const uint32_t nthreads = (uint32_t)(((uint64_t)total + chunk - 1) / chunk);
-    prof_begin(PROF_MSM_ACCUMULATE, s);
+    const int prof_h = prof_begin(PROF_MSM_ACCUMULATE, s, (double)total);
     msm_accumulate_kernel<<<(nthreads + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, s>>>(bases, sl.entries.get(), sl.offsets.get(), nb, total, chunk, bucket_sums,
                                                                                               sl.heads_a.get(), sl.keys_a.get());
-    prof_end(s);
+    prof_end(prof_h, s);
     ++g_launch_count;
     CUDA_CHECK(cudaGetLastError());
     // levels >= 2: segment-sum the head list until a single warp covers it
@@ -494,12 +498,7 @@ static void msm_reduce_groups(Context& ctx, const G1X* bucket_sums, uint32_t G, 
         }
         hl.levels = level;
         // the remaining list (<= TAIL_MAX entries per set) in one launch
-        static bool tail_attr_set = false;
         const size_t tail_smem = 2 * TAIL_THREADS * sizeof(G1X);
-        if (!tail_attr_set) {
-            CUDA_CHECK(cudaFuncSetAttribute(msm_reduce_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
-            tail_attr_set = true;
-        }
         // the level sums T_l only need the `tot` lists: they run on an auxiliary stream beside the tail launch
         cudaStream_t side = ctx.aux_streams[0] && level ? ctx.aux_streams[0] : s;
         DevBuf<G1X> tail_f(G, s), tail_s(G, s), T((size_t)std::max<uint32_t>(level, 1) * G, s);
@@ -543,7 +542,6 @@ static void msm_reduce_groups(Context& ctx, const G1X* bucket_sums, uint32_t G, 
 }
 
 // optional cross-rank combine of partial window sums (set through b200zk_set_allgather)
-double g_exchange_seconds = 0;  // host time spent in the partial-sum exchange callback (reported under "other")
 // point range of this rank for an n-point MSM (contiguous shards; the last rank takes the remainder)
 static void shard_range(const Context& ctx, size_t n, size_t& lo, size_t& len) {
     if (ctx.world <= 1 || !ctx.allgather) {
@@ -586,6 +584,18 @@ static void msm_batch_core(Context& ctx, const G1Affine* const* col_bases, const
             // (under the event profiler one column at a time: concurrent streams would inflate each other's bracketed durations)
             const int nslots = ctx.aux_streams[0] && !g_prof_enabled ? (int)std::min<size_t>(nc, MSM_SLOTS) : 1;
             MsmSlot slots[MSM_SLOTS];
+            // declared after the slots, so it runs before their buffers go back to the arena: if anything below throws while
+            // auxiliary streams still have kernels queued on those buffers, drain every stream first
+            struct DrainOnUnwind {
+                Context& c;
+                int nslots;
+                bool armed = true;
+                ~DrainOnUnwind() {
+                    if (!armed) return;
+                    for (int q = 1; q < nslots; ++q) cudaStreamSynchronize(c.aux_streams[q - 1]);
+                    cudaStreamSynchronize(c.stream);
+                }
+            } drain{ctx, nslots};
             for (int q = 0; q < nslots; ++q) {
                 slots[q].st = q == 0 ? s : ctx.aux_streams[q - 1];
                 slots[q].ev = ctx.msm_events[q];
@@ -609,6 +619,7 @@ static void msm_batch_core(Context& ctx, const G1Affine* const* col_bases, const
                 CUDA_CHECK(cudaStreamWaitEvent(s, ctx.msm_join[q - 1], 0));
             }
             CUDA_CHECK(cudaStreamSynchronize(s));  // slot buffers are released below: nothing may still be using them
+            drain.armed = false;
         }
         std::vector<G1X> ws;
         msm_reduce_groups(ctx, bucket_sums.get(), (uint32_t)(nc * cfg.groups), cfg.B, ws);
@@ -646,7 +657,7 @@ static void msm_batch_distribute(Context& ctx, const G1Affine* const* col_bases,
     std::vector<G1X> all(per * world);
     const auto t0 = std::chrono::steady_clock::now();
     if (ctx.allgather(ctx.allgather_user, sums.data(), per * sizeof(G1X), all.data()) != 0) throw std::runtime_error("msm: all-gather callback failed");
-    g_exchange_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    ctx.exchange_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     for (size_t j = 0; j < dealt; ++j) out[j] = msm_finish(cfg, all.data() + (j % world) * per + (j / world) * G);
     std::vector<G1X> acc(G);
     for (size_t j = dealt; j < ncols; ++j) {

@@ -20,9 +20,10 @@
 
 namespace b200zk {
 
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
 bool g_prof_enabled = false;
 std::vector<ProfSpan> g_prof_spans;
+std::mutex g_prof_mu;
 
 static std::mutex g_arena_mu;
 static std::map<cudaStream_t, Arena*> g_arenas;
@@ -170,6 +171,12 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(PassParams P) {
     }
 }
 
+// per-device kernel attributes (dynamic shared memory above 48 KiB); called by b200zk_create for its device
+void ntt_init_device() {
+    const size_t max_smem = ((size_t)2 << (NTT_MAX_R + NTT_MAX_LOGC)) * 16 + SMEM_PAD * 16;
+    CUDA_CHECK(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+}
+
 int ntt_num_passes(uint32_t log_n) { return log_n == 0 ? 0 : (int)((log_n + NTT_MAX_R - 1) / NTT_MAX_R); }
 
 void ntt_run_batch(const NttPlan& plan, const Fr* in, Fr* out, Fr* scratch, uint32_t batch, size_t stride_in, size_t stride_out,
@@ -181,12 +188,6 @@ void ntt_run_batch(const NttPlan& plan, const Fr* in, Fr* out, Fr* scratch, uint
     }
     if (plan.table_log < L) throw std::runtime_error("ntt: twiddle table too small");
     const int np = ntt_num_passes(L);
-    static bool attr_set = false;
-    const size_t max_smem = ((size_t)2 << (NTT_MAX_R + NTT_MAX_LOGC)) * 16 + SMEM_PAD * 16;
-    if (!attr_set) {
-        CUDA_CHECK(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-        attr_set = true;
-    }
     uint32_t s0 = 0;
     for (int p = 0; p < np; ++p) {
         const uint32_t r = L / np + ((uint32_t)p < L % np ? 1 : 0);
@@ -216,9 +217,9 @@ void ntt_run_batch(const NttPlan& plan, const Fr* in, Fr* out, Fr* scratch, uint
         const uint32_t T = 1u << (r + P.logC);
         const size_t smem = (size_t)2 * T * 16 + SMEM_PAD * 16;
         dim3 grid(1u << (L - r - P.logC), batch);
-        prof_begin(PROF_NTT_PASS, stream);
+        const int prof_h = prof_begin(PROF_NTT_PASS, stream, (double)batch * (double)((size_t)1 << (L - 1)) * (r - (P.skip2 ? 2 : 0)));
         ntt_pass_kernel<<<grid, NTT_THREADS, smem, stream>>>(P);
-        prof_end(stream);
+        prof_end(prof_h, stream);
         ++g_launch_count;
         CUDA_CHECK(cudaGetLastError());
         s0 += r;

@@ -369,7 +369,7 @@ __global__ void lp_hist_kernel(const Fr* col, size_t usable, uint32_t n, uint32_
 #pragma unroll
     for (int t = 1; t < 8; ++t) hi |= v.l[t];
     if (hi != 0 || v.l[0] >= n) {
-        atomicExch(err, 1u);
+        atomicOr(err, 1u);  // outside the value domain this counting sort covers
         return;
     }
     atomicAdd(hist + v.l[0], 1u);
@@ -385,7 +385,7 @@ __global__ void lp_value_kernel(const uint32_t* hist_in, const uint32_t* hist_ta
     }
     const uint32_t ci = hist_in[v], ct = hist_tab[v];
     const uint32_t d = ci > 0 ? 1u : 0u;
-    if (d && ct == 0) atomicExch(err, 2u);
+    if (d && ct == 0) atomicOr(err, 2u);  // input value missing from the table
     distinct[v] = d;
     left[v] = ct >= d ? ct - d : 0;
 }
@@ -419,7 +419,7 @@ __global__ void lp_write_kernel(const uint32_t* start_in, const uint32_t* dist_e
         f_store(s_out + row, f_to_mont(ft));
     }
 }
-bool lookup_permute(Context& ctx, const Fr* input, const Fr* table, Fr* a_out, Fr* s_out, size_t n, size_t usable) {
+int lookup_permute(Context& ctx, const Fr* input, const Fr* table, Fr* a_out, Fr* s_out, size_t n, size_t usable) {
     cudaStream_t s = ctx.stream;
     const uint32_t N = (uint32_t)n;
     DevBuf<uint32_t> hist_in(N + 1, s), hist_tab(N + 1, s), distinct(N + 1, s), left(N + 1, s), err(1, s);
@@ -437,12 +437,12 @@ bool lookup_permute(Context& ctx, const Fr* input, const Fr* table, Fr* a_out, F
     CUDA_CHECK(cudaMemcpyAsync(&h[0], err.get(), 4, cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaMemcpyAsync(&h[1], left.get() + N, 4, cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
-    if (h[0] != 0) return false;
+    if (h[0] != 0) return (int)h[0];
     // start_in has empty runs (equal consecutive starts); upper_idx picks the last value whose start <= row, which is
     // the non-empty run containing the row. left_start likewise.
     lp_write_kernel<<<nblocks(usable, 256), 256, 0, s>>>(hist_in.get(), distinct.get(), left.get(), N, usable, h[1], a_out, s_out);
     LAUNCHED(1);
-    return true;
+    return 0;
 }
 
 // ---- Fr::random stream (ChaCha) ------------------------------------------------------------------------------------------

@@ -34,9 +34,13 @@ void perm_numerator(Fr* m, const Fr* v, const Fr& delta_pow_beta, const Fr& gamm
 void lookup_denominator(Fr* p, const Fr* a, const Fr* sp, const Fr& beta, const Fr& gamma, size_t n, cudaStream_t s);
 // p[i] *= (in[i] + beta) * (tab[i] + gamma)
 void lookup_numerator(Fr* p, const Fr* in, const Fr* tab, const Fr& beta, const Fr& gamma, size_t n, cudaStream_t s);
-// permute_expression_pair for values < n. Writes rows [0, usable) of a_out / s_out.
-// Returns false (after synchronising) when an input value is not in the table or a value is >= n.
-bool lookup_permute(Context& ctx, const Fr* input, const Fr* table, Fr* a_out, Fr* s_out, size_t n, size_t usable);
+// permute_expression_pair for values < n: a counting sort over the value domain [0, n), which covers the
+// halo2-base range table. Writes rows [0, usable) of a_out / s_out. Returns (after synchronising) 0 on success or a bit
+// mask: LOOKUP_UNSUPPORTED — an input or table value is >= n (not a range-style table: outside what this sort handles,
+// NOT a statement about the witness); LOOKUP_NOT_IN_TABLE — an input value is missing from the table (halo2's
+// ConstraintSystemFailure).
+constexpr int LOOKUP_UNSUPPORTED = 1, LOOKUP_NOT_IN_TABLE = 2;
+int lookup_permute(Context& ctx, const Fr* input, const Fr* table, Fr* a_out, Fr* s_out, size_t n, size_t usable);
 
 // ---- Fr::random stream: element j of a rand_chacha BlockRng stream = from_u512 of ChaCha block (counter0 + j) ---------
 void fr_random_stream(Fr* out, size_t n, const uint32_t key[8], uint64_t counter0, int rounds, cudaStream_t s);

@@ -16,7 +16,6 @@
 namespace b200zk {
 
 G1Affine msm_run_srs(Context& ctx, int basis, const Fr* scalars, size_t n);
-extern double g_exchange_seconds;
 void msm_batch_srs(Context& ctx, int basis, const Fr* const* cols, size_t ncols, size_t n, G1Affine* out);
 void msm_batch_srs_mixed(Context& ctx, const int* basis, const Fr* const* cols, size_t ncols, size_t n, G1Affine* out);
 
@@ -418,7 +417,7 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
     const Domain& dom = ctx.domain(sh.k);
     const TwiddleTable& tw = ctx.std_table(sh.k + 2);
     host::Transcript tr;
-    const double exchange0 = g_exchange_seconds;
+    const double exchange0 = ctx.exchange_seconds;
     Sharder shard(ctx);
     if (shard.on()) shard.nccl();  // communicator up before the first timed exchange
     auto clock_now = [&]() {
@@ -516,8 +515,8 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
         for (auto& b : blind) b = rng.next();
         rng.skip(2);  // the two Blind(..) draws of commit_values
         if (!shard.mine(l)) continue;
-        if (!lookup_permute(ctx, advice.get() + (size_t)(A + l) * n, table_values, a_out, s_out, n, u)) {
-            lookup_failed = 1;
+        if (const int st = lookup_permute(ctx, advice.get() + (size_t)(A + l) * n, table_values, a_out, s_out, n, u)) {
+            lookup_failed |= (uint32_t)st;
             continue;
         }
         CUDA_CHECK(cudaMemcpyAsync(a_out + u, blind.data(), (bf + 1) * sizeof(Fr), cudaMemcpyHostToDevice, s));
@@ -529,6 +528,7 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
         if (ctx.allgather(ctx.allgather_user, &lookup_failed, sizeof(uint32_t), all.data()) != 0) throw std::runtime_error("lookup status exchange failed");
         for (uint32_t f : all) lookup_failed |= f;
     }
+    if (lookup_failed & LOOKUP_UNSUPPORTED) throw std::invalid_argument("create_proof: lookup values must be < 2^k (range-style tables only)");
     if (lookup_failed) throw SynthesisError("ConstraintSystemFailure: lookup input not in table");
     shard.allgather_columns(perm_cols.get(), L, 2 * n);  // column l = a'_l followed by s'_l
     lap(tm ? &tm->lookup : nullptr);
@@ -920,8 +920,8 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
     tr.write_point(commit_coeff(ctx, buf_b.get(), n));
     lap(tm ? &tm->msm : nullptr);
     if (tm) {  // the MSM stage includes the cross-rank exchange of partial sums: report it separately
-        tm->other += g_exchange_seconds - exchange0;
-        tm->msm -= g_exchange_seconds - exchange0;
+        tm->other += ctx.exchange_seconds - exchange0;
+        tm->msm -= ctx.exchange_seconds - exchange0;
     }
     return tr.proof;
 }

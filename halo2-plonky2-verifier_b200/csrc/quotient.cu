@@ -89,23 +89,23 @@ __global__ void __launch_bounds__(256) h_lookup_kernel(QuotientArgs Q, LookupCos
 
 void h_gates(const QuotientArgs& Q, Fr* h, cudaStream_t s) {
     const size_t en = Q.row_end - Q.row_begin;
-    prof_begin(PROF_QUOTIENT, s);
+    const int prof_h = prof_begin(PROF_QUOTIENT, s, (double)en);
     h_gates_kernel<<<(unsigned)((en + 255) / 256), 256, 0, s>>>(Q, h);
-    prof_end(s);
+    prof_end(prof_h, s);
     LAUNCHED(1);
 }
 void h_permutation(const QuotientArgs& Q, Fr* h, bool final_scale, cudaStream_t s) {
     const size_t en = Q.row_end - Q.row_begin;
-    prof_begin(PROF_QUOTIENT, s);
+    const int prof_h = prof_begin(PROF_QUOTIENT, s, (double)en);
     h_permutation_kernel<<<(unsigned)((en + 255) / 256), 256, 0, s>>>(Q, h, final_scale);
-    prof_end(s);
+    prof_end(prof_h, s);
     LAUNCHED(1);
 }
 void h_lookup(const QuotientArgs& Q, const LookupCosets& Lk, Fr* h, bool final_scale, cudaStream_t s) {
     const size_t en = Q.row_end - Q.row_begin;
-    prof_begin(PROF_QUOTIENT, s);
+    const int prof_h = prof_begin(PROF_QUOTIENT, s, (double)en);
     h_lookup_kernel<<<(unsigned)((en + 255) / 256), 256, 0, s>>>(Q, Lk, h, final_scale);
-    prof_end(s);
+    prof_end(prof_h, s);
     LAUNCHED(1);
 }
 

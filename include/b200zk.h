@@ -68,6 +68,9 @@ B200ZK_API int b200zk_set_msm_tables(b200zk_ctx* ctx, int on);
  * profile_get synchronises, sums the spans recorded since the last reset and clears them. */
 B200ZK_API int b200zk_profile_enable(b200zk_ctx* ctx, int on);
 B200ZK_API int b200zk_profile_get(b200zk_ctx* ctx, int id, double* total_ms, unsigned long long* launches);
+/* algorithmic work of the spans recorded since the last reset (call before profile_get, which clears them): mixed point
+ * additions for id 0, butterflies for id 2, extended rows for id 3 */
+B200ZK_API int b200zk_profile_work(b200zk_ctx* ctx, int id, double* units);
 /* raw device memory helpers for hosts without their own allocator */
 B200ZK_API int b200zk_dev_alloc(b200zk_ctx* ctx, size_t bytes, void** out);
 B200ZK_API int b200zk_dev_free(b200zk_ctx* ctx, void* p);
@@ -136,8 +139,9 @@ B200ZK_API int b200zk_msm_bases_dev(b200zk_ctx* ctx, const b200zk_g1_affine* bas
  * prefix_product    : z[0] = first, z[i] = z[i-1]·m[i-1] (the running product of permutation::prover / lookup::prover).
  * eval_polynomial   : arithmetic::eval_polynomial(poly, point).
  * kate_division     : arithmetic::kate_division(a, b): quotient of a(X) by (X - b), n-1 coefficients.
- * permute_expression_pair : lookup::prover::permute_expression_pair on the first n-7 rows (values must be < n);
- *                     returns B200ZK_ESYNTH when an input is missing from the table. Outputs n-7 rows each. */
+ * permute_expression_pair : lookup::prover::permute_expression_pair on the first n-7 rows, for range-style tables: every
+ *                     input and table value must be < n = 2^k (B200ZK_EINVAL otherwise — an unsupported table, not a
+ *                     verdict on the witness); B200ZK_ESYNTH when an input is missing from the table. n-7 rows out. */
 B200ZK_API int b200zk_batch_invert(b200zk_ctx* ctx, b200zk_fr* a, size_t n);
 B200ZK_API int b200zk_prefix_product(b200zk_ctx* ctx, const b200zk_fr* m, const b200zk_fr* first, b200zk_fr* z, size_t n);
 B200ZK_API int b200zk_eval_polynomial(b200zk_ctx* ctx, const b200zk_fr* poly, size_t n, const b200zk_fr* point, b200zk_fr* out);
@@ -183,7 +187,7 @@ B200ZK_API int b200zk_create_proof_dev(b200zk_ctx* ctx, const b200zk_pk* pk, con
 B200ZK_API int b200zk_evaluate_h(b200zk_ctx* ctx, const b200zk_pk* pk, const b200zk_fr* advice_coeff, const b200zk_fr* perm_z_coeff,
                                  const b200zk_fr* lookup_coeff, const b200zk_fr* y, const b200zk_fr* beta, const b200zk_fr* gamma,
                                  b200zk_fr* h_ext_out);
-/* number of permutation product polynomials (sets of 3 columns) for a shape */
+/* number of permutation product polynomials (sets of degree − 2 = 2 columns) for a shape */
 B200ZK_API uint32_t b200zk_num_sets(uint32_t A, uint32_t L, uint32_t F);
 /* ---- host-only helpers (no CUDA device needed) -------------------------------------------------------------------
  * Sum of n affine G1 points (canonical affine out): combines per-GPU partial MSM results. */
@@ -191,10 +195,6 @@ B200ZK_API int b200zk_g1_sum_host(const b200zk_g1_affine* points, size_t n, b200
 /* Cross-checks the host paths of the shared field/curve code (carry-chain emulation vs 64-bit limbs, group laws) on
  * `iters` pseudo-random inputs; returns 0 when every identity holds. */
 B200ZK_API int b200zk_host_selftest(uint64_t seed, size_t iters);
-/* ---- synthetic circuits of that shape (host only; stands in for the reference's FRI-verifier witness) */
-B200ZK_API size_t b200zk_synth_max_copies(uint32_t k, uint32_t A, uint32_t L, uint32_t F);
-B200ZK_API int b200zk_synth_circuit(uint32_t k, uint32_t A, uint32_t L, uint32_t F, uint64_t seed, b200zk_fr* fixed, b200zk_fr* advice,
-                                    uint32_t* copies, size_t* ncopies);
 
 #ifdef __cplusplus
 }

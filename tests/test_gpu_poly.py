@@ -82,3 +82,9 @@ def test_permute_expression_pair(ctx, k, kind):
     with pytest.raises(b200zk.B200zkError) as e:
         ctx.permute_expression_pair(k, bad, table)
     assert e.value.code == b200zk.ESYNTH
+    # a value outside [0, n) is an UNSUPPORTED table/input for this counting sort (EINVAL), not a constraint failure
+    big = inp.copy()
+    big[n // 5] = O.to_mont(n + 3)
+    with pytest.raises(b200zk.B200zkError) as e:
+        ctx.permute_expression_pair(k, big, table)
+    assert e.value.code == b200zk.EINVAL

@@ -65,3 +65,14 @@ def test_host_selftest_and_g1_sum():
 def test_synth_rejects_bad_arguments():
     with pytest.raises(b200zk.B200zkError):
         b200zk.synth_circuit(3, 1, 1, 1)
+
+
+def test_workload_generator_is_not_in_the_product_library():
+    """The synthetic-circuit generator is its own host library (workload/): the product library exports no test-input code,
+    so bench.py's reference arm can build its input without mapping libb200zk."""
+    import workload
+
+    assert not hasattr(b200zk.lib(), "b200zk_synth_circuit")
+    f, a, c = workload.synth_circuit(6, 2, 1, 1, seed=5)
+    f2, a2, c2 = b200zk.synth_circuit(6, 2, 1, 1, seed=5)
+    assert np.array_equal(f, f2) and np.array_equal(a, a2) and np.array_equal(c, c2)

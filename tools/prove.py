@@ -20,4 +20,4 @@ if check:
     t = time.time(); opk = O.ProvingKey(params, k, A, L, F, fixed, copies); print("oracle keygen s", round(time.time() - t, 2), "threads", O.lib().oracle_get_threads(), flush=True)
     want = opk.create_proof(advice, 0); print("oracle create_proof s", round(opk.last_seconds, 2), flush=True)
     print("bytes equal:", want == proof, "verify:", opk.verify(proof))
-os._exit(0)
+pk.close(); ctx.close()

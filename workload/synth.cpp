@@ -1,5 +1,6 @@
-// Synthetic circuits of the halo2-base shape (host only; the counterpart of halo2-base's `utils::testing` for this
-// backend). The reference's real witness — the FRI-verifier cell stream of verifier/src/stark/mod.rs:594-616 — needs the
+// Synthetic circuits of the halo2-base shape: the WORKLOAD GENERATOR of bench.py and the tests (host only, its own small
+// shared library libfriworkload.so — neither part of the product library nor of the oracle, so both bench arms can use it;
+// the counterpart of halo2-base's `utils::testing` circuit builders). The reference's real witness — the FRI-verifier cell stream of verifier/src/stark/mod.rs:594-616 — needs the
 // Rust gadgets plus plonky2/plonky2x, none of which exist here, so bench and tests prove shape- and
 // distribution-faithful stand-ins: the cell stream replays the reference's measured mix
 // (verifier/profile/bn254_rev.svg: 68 % Goldilocks range-check cells, 15 % 64-bit arithmetic, 17 % full-width Poseidon
@@ -9,14 +10,25 @@
 //     7 "shift" cells, then a second 10-cell range check — 27 advice cells, 8 limbs copied into lookup columns;
 //   * Goldilocks mul_add rows: 64-bit a, b, c with d = a + b·c;
 //   * full-width rows (Poseidon-BN254 S-box / mix): uniformly random Fr operands, chained d -> a.
+#include <algorithm>
+#include <cstddef>
+#include <stdexcept>
 #include <vector>
 
-#include "../../include/b200zk.h"
-#include "prover.cuh"
+#include "../halo2-plonky2-verifier_b200/csrc/field.cuh"  // host path of the field arithmetic (no CUDA needed)
 
 using namespace b200zk;
 
 namespace {
+
+// column counts of halo2-base's BaseConfig — the same layout b200zk_keygen documents
+struct Shape {
+    uint32_t k, A, L, F;
+    uint32_t num_advice() const { return A + L; }
+    uint32_t num_fixed() const { return F + 1 + A; }  // constants, lookup table, gate selectors
+    uint32_t table_col() const { return F; }
+    uint32_t selector_col(uint32_t c) const { return F + 1 + c; }
+};
 
 struct SplitMix {
     uint64_t s;
@@ -221,14 +233,16 @@ struct Builder {
 
 extern "C" {
 
-size_t b200zk_synth_max_copies(uint32_t k, uint32_t A, uint32_t L, uint32_t F) {
+__attribute__((visibility("default"))) size_t friworkload_max_copies(uint32_t k, uint32_t A, uint32_t L, uint32_t F) {
     (void)L; (void)F;
     return (size_t)A * ((size_t)1 << k) + 64;
 }
 
-int b200zk_synth_circuit(uint32_t k, uint32_t A, uint32_t L, uint32_t F, uint64_t seed, b200zk_fr* fixed, b200zk_fr* advice, uint32_t* copies,
-                         size_t* ncopies) {
-    if (!fixed || !advice || !copies || !ncopies || k < 5 || k > 26 || A == 0 || F == 0) return B200ZK_EINVAL;
+// fixed: num_fixed × 2^k, advice: (A+L) × 2^k field elements (uint64_t[4] Montgomery limbs, column-major); copies: up to
+// friworkload_max_copies × {col_a,row_a,col_b,row_b}. Returns 0, -2 for bad arguments, -4 when the shape cannot be filled.
+__attribute__((visibility("default"))) int friworkload_synth_circuit(uint32_t k, uint32_t A, uint32_t L, uint32_t F, uint64_t seed, uint64_t* fixed,
+                                                                      uint64_t* advice, uint32_t* copies, size_t* ncopies) {
+    if (!fixed || !advice || !copies || !ncopies || k < 5 || k > 26 || A == 0 || F == 0) return -2;
     try {
         Builder b;
         b.sh = Shape{k, A, L, F};
@@ -240,15 +254,15 @@ int b200zk_synth_circuit(uint32_t k, uint32_t A, uint32_t L, uint32_t F, uint64_
         b.fixed = (Fr*)fixed;
         b.advice = (Fr*)advice;
         b.copies = copies;
-        b.max_copies = b200zk_synth_max_copies(k, A, L, F);
+        b.max_copies = friworkload_max_copies(k, A, L, F);
         b.rng.s = seed * 0x2545f4914f6cdd1dull + 0x1234567ull;
         memset(fixed, 0, sizeof(Fr) * b.n * b.sh.num_fixed());
         memset(advice, 0, sizeof(Fr) * b.n * b.sh.num_advice());
         b.build();
         *ncopies = b.ncopies;
-        return B200ZK_OK;
+        return 0;
     } catch (const std::exception&) {
-        return B200ZK_ESTATE;
+        return -4;
     }
 }
 

@@ -790,7 +790,7 @@ int b200zk_permute_expression_pair(b200zk_ctx* ctx, uint32_t k, const b200zk_fr*
     CUDA_CHECK(cudaMemcpyAsync(din.get(), input, 32 * n, cudaMemcpyHostToDevice, s));
     CUDA_CHECK(cudaMemcpyAsync(dtab.get(), table, 32 * n, cudaMemcpyHostToDevice, s));
     const int st = lookup_permute(ctx->c, din.get(), dtab.get(), da.get(), ds.get(), n, u);
-    if (st & LOOKUP_UNSUPPORTED) throw std::invalid_argument("permute_expression_pair: unsupported table — every input and table value must be < 2^k (range-style tables)");
+    if (st & LOOKUP_UNSUPPORTED) throw std::invalid_argument("permute_expression_pair: unsupported table — every table value must be < 2^k (range-style tables)");
     if (st & LOOKUP_NOT_IN_TABLE) throw SynthesisError("ConstraintSystemFailure: lookup input not in table");
     CUDA_CHECK(cudaMemcpyAsync(a_out, da.get(), 32 * u, cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaMemcpyAsync(s_out, ds.get(), 32 * u, cudaMemcpyDeviceToHost, s));

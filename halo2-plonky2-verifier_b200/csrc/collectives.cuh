@@ -1,8 +1,10 @@
 // NCCL over NVLink/NVSwitch for the bulk exchanges of the sharded prover: broadcast of per-column
 // results (coefficient forms, extended cosets) from the rank that computed them and the all-gather of h(X) row ranges.
-// One process per GPU (torchrun); the library opens the NCCL that the host process already loaded (torch's bundled
-// libnccl.so.2) with dlopen, so there is no link-time dependency and no second copy. The 128-byte ncclUniqueId is
-// bootstrapped through the host all-gather callback the caller registered with b200zk_set_allgather.
+// The library opens the NCCL that the host process already loaded (torch's bundled libnccl.so.2) with dlopen, so there is
+// no link-time dependency and no second copy. One process per GPU (torchrun): the 128-byte ncclUniqueId is bootstrapped
+// through the host all-gather callback registered with b200zk_set_allgather — the callback's ONLY use. One process for all
+// GPUs (b200zk_create_multi): the id is shared in memory. Every later exchange, including the small host-side ones
+// (partial MSM sums, evaluations, status words), is an ncclAllGather on the context's stream.
 #pragma once
 #include <dlfcn.h>
 
@@ -25,6 +27,9 @@ struct Nccl {
     int (*CommDestroy)(void*) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
     int rank = 0, world = 1;
+    // staging of the small host all-gathers: one device buffer [world][cap] and pinned host mirrors
+    uint8_t *stage_dev = nullptr, *stage_pin = nullptr;
+    size_t stage_cap = 0;
 
     void check(int rc, const char* what) {
         if (rc != 0) throw std::runtime_error(std::string("NCCL ") + what + " failed: " + (GetErrorString ? GetErrorString(rc) : "?"));
@@ -34,9 +39,8 @@ struct Nccl {
         f = (F)dlsym(lib, name);
         if (!f) throw std::runtime_error(std::string("NCCL symbol missing: ") + name);
     }
-    void init(Context& ctx) {
-        rank = ctx.rank;
-        world = ctx.world;
+    void load() {
+        if (lib) return;
         lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);  // the copy the host process (torch) already loaded
         if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW);
         if (!lib) throw std::runtime_error("libnccl.so.2 not found (multi-GPU needs NCCL in the host process)");
@@ -50,6 +54,13 @@ struct Nccl {
         sym(GroupEnd, "ncclGroupEnd");
         sym(CommDestroy, "ncclCommDestroy");
         sym(GetErrorString, "ncclGetErrorString");
+    }
+    // one process per GPU: the id travels through the host callback
+    void init(Context& ctx) {
+        rank = ctx.rank;
+        world = ctx.world;
+        load();
+        if (!ctx.allgather) throw std::runtime_error("multi-GPU context without a bootstrap callback (b200zk_set_allgather) or an in-process communicator");
         UniqueId id;
         memset(&id, 0, sizeof(id));
         if (rank == 0) check(GetUniqueId(&id), "GetUniqueId");
@@ -57,7 +68,27 @@ struct Nccl {
         if (ctx.allgather(ctx.allgather_user, &id, sizeof(id), all.data()) != 0) throw std::runtime_error("NCCL bootstrap all-gather failed");
         check(CommInitRank(&comm, world, all[0], rank), "CommInitRank");
     }
+    // one process, one thread per GPU: every thread calls this with the id that rank 0 made (the calls block until all joined)
+    void init_with_id(int rank_, int world_, const UniqueId& id) {
+        rank = rank_;
+        world = world_;
+        load();
+        check(CommInitRank(&comm, world, id, rank), "CommInitRank");
+    }
+    void ensure_stage(size_t bytes_per_rank, cudaStream_t stream) {
+        const size_t need = ((bytes_per_rank + 255) & ~(size_t)255);
+        if (need <= stage_cap) return;
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        if (stage_dev) cudaFree(stage_dev);
+        if (stage_pin) cudaFreeHost(stage_pin);
+        stage_dev = stage_pin = nullptr;
+        stage_cap = std::max<size_t>(need, 4096);
+        CUDA_CHECK(cudaMalloc((void**)&stage_dev, stage_cap * world));
+        CUDA_CHECK(cudaHostAlloc((void**)&stage_pin, stage_cap * (world + 1), cudaHostAllocDefault));
+    }
     ~Nccl() {
+        if (stage_dev) cudaFree(stage_dev);
+        if (stage_pin) cudaFreeHost(stage_pin);
         if (comm && CommDestroy) CommDestroy(comm);
     }
 };
@@ -68,7 +99,7 @@ struct Sharder {
     Context& ctx;
     bool enabled = true;  // false: this call works on the local GPU alone even inside a multi-rank job
     explicit Sharder(Context& c) : ctx(c) {}
-    bool on() const { return enabled && ctx.world > 1 && ctx.allgather; }
+    bool on() const { return enabled && ctx.sharded(); }
     int owner(size_t i, size_t off = 0) const { return on() ? (int)((i + off) % ctx.world) : 0; }
     bool mine(size_t i, size_t off = 0) const { return !on() || owner(i, off) == ctx.rank; }
     Nccl& nccl() {
@@ -78,6 +109,29 @@ struct Sharder {
             ctx.nccl = n;
         }
         return *ctx.nccl;
+    }
+    // All-gather of `bytes` HOST bytes from every rank into recv[world][bytes] (host): H2D of this rank's piece, one
+    // ncclAllGather on the context's stream, D2H of everything, one stream synchronisation. ~30 µs over NVLink instead of a
+    // round trip through the host process's own collective layer.
+    void host_allgather(const void* send, size_t bytes, void* recv) {
+        Nccl& nc = nccl();
+        nc.ensure_stage(bytes, ctx.stream);
+        uint8_t* pin_send = nc.stage_pin + nc.stage_cap * nc.world;
+        memcpy(pin_send, send, bytes);
+        CUDA_CHECK(cudaMemcpyAsync(nc.stage_dev + (size_t)nc.rank * bytes, pin_send, bytes, cudaMemcpyHostToDevice, ctx.stream));
+        nc.check(nc.AllGather(nc.stage_dev + (size_t)nc.rank * bytes, nc.stage_dev, bytes, 1, nc.comm, ctx.stream), "AllGather");
+        CUDA_CHECK(cudaMemcpyAsync(nc.stage_pin, nc.stage_dev, bytes * nc.world, cudaMemcpyDeviceToHost, ctx.stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+        memcpy(recv, nc.stage_pin, bytes * nc.world);
+    }
+    // the same for a piece that is already in DEVICE memory (the partial sums of a commit batch): no upload
+    void dev_to_host_allgather(const void* send_dev, size_t bytes, void* recv) {
+        Nccl& nc = nccl();
+        nc.ensure_stage(bytes, ctx.stream);
+        nc.check(nc.AllGather(send_dev, nc.stage_dev, bytes, 1, nc.comm, ctx.stream), "AllGather");
+        CUDA_CHECK(cudaMemcpyAsync(nc.stage_pin, nc.stage_dev, bytes * nc.world, cudaMemcpyDeviceToHost, ctx.stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+        memcpy(recv, nc.stage_pin, bytes * nc.world);
     }
     void group_start() {
         if (on()) nccl().check(nccl().GroupStart(), "GroupStart");

@@ -71,6 +71,9 @@ struct Srs {
     // precomputed window tables T[w][i] = 2^(tab_c·w)·P_i (msm.cu, merged-bucket mode); empty when disabled
     DevBuf<G1Affine> g_tab, gl_tab;
     uint32_t tab_c = 0;
+    // multi-GPU: whether EVERY rank built the table of g / g_lagrange (-1 = not agreed yet). Table building depends on each
+    // rank's free memory; ranks that disagreed would pick different MSM configurations and exchange mismatched sums.
+    mutable int tab_agreed[2] = {-1, -1};
     // the verifier-side G2 points (g2, s·g2) as file bytes: RawBytes (256 B) after setup, or whatever a read file carried
     std::vector<uint8_t> g2_bytes;
     int g2_format = 0;
@@ -107,7 +110,10 @@ struct Context {
     void* allgather_user = nullptr;
     double exchange_seconds = 0;  // host time spent in the cross-rank exchange of partial MSM sums (reported under "other")
     bool msm_tables_enabled = true;
-    std::shared_ptr<struct Nccl> nccl;  // collectives.cuh, created on first use when world > 1
+    std::shared_ptr<struct Nccl> nccl;  // collectives.cuh: created on first use from the bootstrap callback (one process per
+                                        // GPU), or installed by b200zk_create_multi (one process, one thread per GPU)
+    // this context is one rank of a multi-GPU job
+    bool sharded() const { return world > 1 && (allgather != nullptr || nccl != nullptr); }
 
     // table of the standard 2^t-th root with t >= log_n
     const TwiddleTable& std_table(uint32_t log_n) {

@@ -25,7 +25,7 @@
 #include <algorithm>
 #include <chrono>
 
-#include "context.cuh"
+#include "collectives.cuh"
 
 namespace b200zk {
 
@@ -472,9 +472,11 @@ static void msm_issue_accumulate(MsmSlot& sl, const G1Affine* bases, const Fr* s
 
 // Phase B for `G` bucket sets of B buckets each (window-major): F(set) = Σ_b (b+1)·bucket[b] -> sums_host[G] (XYZZ).
 // One reduction serves every column of a batch: the deep levels are latency bound (≈0.12 ms each whatever G is).
-static void msm_reduce_groups(Context& ctx, const G1X* bucket_sums, uint32_t G, uint32_t B, std::vector<G1X>& sums_host) {
+// With `gather_ranks` > 1 the G sums of every rank are all-gathered on the device (NCCL, straight out of the reduction's
+// output buffer) before the one read-back: sums_host then holds gather_ranks·G entries, rank-major.
+static void msm_reduce_groups(Context& ctx, const G1X* bucket_sums, uint32_t G, uint32_t B, std::vector<G1X>& sums_host, int gather_ranks = 1) {
     cudaStream_t s = ctx.stream;
-    sums_host.assign(G, g1x_identity());
+    sums_host.assign((size_t)G * gather_ranks, g1x_identity());
     if (G == 0) return;
     DevBuf<G1X> wsums(G, s);
     {
@@ -537,6 +539,12 @@ static void msm_reduce_groups(Context& ctx, const G1X* bucket_sums, uint32_t G, 
         }
         CUDA_CHECK(cudaGetLastError());
     }
+    if (gather_ranks > 1) {
+        const auto t0 = std::chrono::steady_clock::now();
+        Sharder(ctx).dev_to_host_allgather(wsums.get(), G * sizeof(G1X), sums_host.data());
+        ctx.exchange_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        return;
+    }
     CUDA_CHECK(cudaMemcpyAsync(sums_host.data(), wsums.get(), G * sizeof(G1X), cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
 }
@@ -544,7 +552,7 @@ static void msm_reduce_groups(Context& ctx, const G1X* bucket_sums, uint32_t G, 
 // optional cross-rank combine of partial window sums (set through b200zk_set_allgather)
 // point range of this rank for an n-point MSM (contiguous shards; the last rank takes the remainder)
 static void shard_range(const Context& ctx, size_t n, size_t& lo, size_t& len) {
-    if (ctx.world <= 1 || !ctx.allgather) {
+    if (!ctx.sharded()) {
         lo = 0;
         len = n;
         return;
@@ -561,8 +569,9 @@ static void check_cfg(const MsmConfig& cfg, size_t n) {
 // `ncols` MSMs with one configuration: per-column bucket accumulation, ONE bucket reduction for all columns. Column j reads
 // the bases at col_bases[j] (the two SRS bases can be mixed in a batch); with col_partial[j] set, only this rank's point
 // range of column j is accumulated. sums_out gets cfg.groups entries per column: the (partial) window sums, XYZZ.
+// `gather_ranks` > 1 (one reduction round only): sums_out holds every rank's sums, rank-major (see msm_reduce_groups).
 static void msm_batch_core(Context& ctx, const G1Affine* const* col_bases, const Fr* const* cols, const uint8_t* col_partial, size_t ncols, size_t n,
-                           const MsmConfig& cfg, std::vector<G1X>& sums_out) {
+                           const MsmConfig& cfg, std::vector<G1X>& sums_out, int gather_ranks = 1) {
     check_cfg(cfg, n);
     cudaStream_t s = ctx.stream;
     size_t shard_lo = 0, shard_len = n;
@@ -571,6 +580,7 @@ static void msm_batch_core(Context& ctx, const G1Affine* const* col_bases, const
     sums_out.clear();
     // bound the scratch: at most 32 columns (≈2 GiB of bucket sums at c = 20) per reduction round
     const size_t round = 32;
+    if (gather_ranks > 1 && ncols > round) throw std::logic_error("msm: device-side gather needs a single reduction round");
     for (size_t c0 = 0; c0 < ncols; c0 += round) {
         const size_t nc = std::min(round, ncols - c0);
         DevBuf<G1X> bucket_sums((size_t)nc * nb, s);
@@ -622,7 +632,7 @@ static void msm_batch_core(Context& ctx, const G1Affine* const* col_bases, const
             drain.armed = false;
         }
         std::vector<G1X> ws;
-        msm_reduce_groups(ctx, bucket_sums.get(), (uint32_t)(nc * cfg.groups), cfg.B, ws);
+        msm_reduce_groups(ctx, bucket_sums.get(), (uint32_t)(nc * cfg.groups), cfg.B, ws, gather_ranks);
         sums_out.insert(sums_out.end(), ws.begin(), ws.end());
     }
 }
@@ -638,7 +648,7 @@ static G1Affine msm_finish(const MsmConfig& cfg, const G1X* sums) {
 // the q finished sums and the rem partial window sums of every rank, and the partial ones are added on the host.
 static void msm_batch_distribute(Context& ctx, const G1Affine* const* col_bases, const Fr* const* cols, size_t ncols, size_t n, const MsmConfig& cfg,
                                  G1Affine* out) {
-    const bool dist = ctx.world > 1 && ctx.allgather;
+    const bool dist = ctx.sharded();
     const size_t G = cfg.groups;
     std::vector<G1X> sums;
     if (!dist) {
@@ -652,12 +662,24 @@ static void msm_batch_distribute(Context& ctx, const G1Affine* const* col_bases,
     std::vector<uint8_t> partial;
     for (size_t j = ctx.rank; j < dealt; j += world) my_bases.push_back(col_bases[j]), my_cols.push_back(cols[j]), partial.push_back(0);
     for (size_t j = dealt; j < ncols; ++j) my_bases.push_back(col_bases[j]), my_cols.push_back(cols[j]), partial.push_back(1);
-    msm_batch_core(ctx, my_bases.data(), my_cols.data(), partial.data(), my_cols.size(), n, cfg, sums);
     const size_t per = (q + rem) * G;  // entries per rank, the same on every rank
-    std::vector<G1X> all(per * world);
-    const auto t0 = std::chrono::steady_clock::now();
-    if (ctx.allgather(ctx.allgather_user, sums.data(), per * sizeof(G1X), all.data()) != 0) throw std::runtime_error("msm: all-gather callback failed");
-    ctx.exchange_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    std::vector<G1X> all;
+    if (ctx.nccl && my_cols.size() <= 32) {
+        // the library's own communicator is up (create_proof brings it up): the partial sums go from the reduction's output
+        // buffer through one ncclAllGather and come back to the host in one copy
+        msm_batch_core(ctx, my_bases.data(), my_cols.data(), partial.data(), my_cols.size(), n, cfg, all, (int)world);
+    } else {
+        msm_batch_core(ctx, my_bases.data(), my_cols.data(), partial.data(), my_cols.size(), n, cfg, sums);
+        all.resize(per * world);
+        const auto t0 = std::chrono::steady_clock::now();
+        if (ctx.nccl) {
+            Sharder(ctx).host_allgather(sums.data(), per * sizeof(G1X), all.data());
+        } else {  // no communicator: the host's all-gather callback carries the sums (hosts without NCCL, single-GPU replays)
+            if (!ctx.allgather || ctx.allgather(ctx.allgather_user, sums.data(), per * sizeof(G1X), all.data()) != 0)
+                throw std::runtime_error("msm: all-gather callback failed");
+        }
+        ctx.exchange_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
     for (size_t j = 0; j < dealt; ++j) out[j] = msm_finish(cfg, all.data() + (j % world) * per + (j / world) * G);
     std::vector<G1X> acc(G);
     for (size_t j = dealt; j < ncols; ++j) {
@@ -684,7 +706,16 @@ void msm_batch_srs_mixed(Context& ctx, const int* basis, const Fr* const* cols, 
     bool uniform = true;
     for (size_t j = 1; j < ncols; ++j) uniform = uniform && basis[j] == basis[0];
     auto table = [&](int b) -> const DevBuf<G1Affine>& { return b == 0 ? srs.g_tab : srs.gl_tab; };
-    auto has_table = [&](int b) { return table(b).size() != 0 && n * 8 >= srs.n; };
+    if (ctx.sharded() && ctx.nccl && srs.tab_agreed[0] < 0) {  // one exchange per SRS: use a table only if every rank has it
+        uint32_t mine[2] = {table(0).size() != 0, table(1).size() != 0};
+        std::vector<uint32_t> all(2 * (size_t)ctx.world);
+        Sharder(ctx).host_allgather(mine, sizeof(mine), all.data());
+        for (int b = 0; b < 2; ++b) {
+            srs.tab_agreed[b] = 1;
+            for (int r = 0; r < ctx.world; ++r) srs.tab_agreed[b] &= (int)all[2 * r + b];
+        }
+    }
+    auto has_table = [&](int b) { return table(b).size() != 0 && srs.tab_agreed[b] != 0 && n * 8 >= srs.n; };
     if (!uniform && !(has_table(0) && has_table(1))) {  // the two bases would use different configurations: one call per run
         for (size_t j0 = 0; j0 < ncols;) {
             size_t j1 = j0 + 1;

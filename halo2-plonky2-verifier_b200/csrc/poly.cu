@@ -361,7 +361,7 @@ void lookup_numerator(Fr* p, const Fr* in, const Fr* tab, const Fr& beta, const 
 //   a'[row] = value whose run contains row; s'[row] = a'[row] on the first row of a run, else the leftover table value
 //   number R-1-idx in ascending order, idx = rank of the row among repeated rows (upstream pops repeated rows from
 //   the end while walking leftovers in ascending order).
-__global__ void lp_hist_kernel(const Fr* col, size_t usable, uint32_t n, uint32_t* hist, uint32_t* err) {
+__global__ void lp_hist_kernel(const Fr* col, size_t usable, uint32_t n, uint32_t* hist, uint32_t* err, uint32_t err_bit) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= usable) return;
     const Fr v = f_from_mont(f_load(col + i));
@@ -369,7 +369,7 @@ __global__ void lp_hist_kernel(const Fr* col, size_t usable, uint32_t n, uint32_
 #pragma unroll
     for (int t = 1; t < 8; ++t) hi |= v.l[t];
     if (hi != 0 || v.l[0] >= n) {
-        atomicOr(err, 1u);  // outside the value domain this counting sort covers
+        atomicOr(err, err_bit);  // outside the value domain [0, n) this counting sort covers
         return;
     }
     atomicAdd(hist + v.l[0], 1u);
@@ -426,8 +426,9 @@ int lookup_permute(Context& ctx, const Fr* input, const Fr* table, Fr* a_out, Fr
     CUDA_CHECK(cudaMemsetAsync(hist_in.get(), 0, (N + 1) * 4, s));
     CUDA_CHECK(cudaMemsetAsync(hist_tab.get(), 0, (N + 1) * 4, s));
     CUDA_CHECK(cudaMemsetAsync(err.get(), 0, 4, s));
-    lp_hist_kernel<<<nblocks(usable, 256), 256, 0, s>>>(input, usable, N, hist_in.get(), err.get());
-    lp_hist_kernel<<<nblocks(usable, 256), 256, 0, s>>>(table, usable, N, hist_tab.get(), err.get());
+    // a TABLE value >= n is outside what this sort supports; an INPUT value >= n is then simply missing from the table
+    lp_hist_kernel<<<nblocks(usable, 256), 256, 0, s>>>(input, usable, N, hist_in.get(), err.get(), (uint32_t)LOOKUP_NOT_IN_TABLE);
+    lp_hist_kernel<<<nblocks(usable, 256), 256, 0, s>>>(table, usable, N, hist_tab.get(), err.get(), (uint32_t)LOOKUP_UNSUPPORTED);
     lp_value_kernel<<<nblocks(N + 1, 256), 256, 0, s>>>(hist_in.get(), hist_tab.get(), N, distinct.get(), left.get(), err.get());
     LAUNCHED(3);
     exclusive_scan_u32(hist_in.get(), hist_in.get(), N + 1, s);    // start_in

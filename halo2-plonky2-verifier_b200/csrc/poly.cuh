@@ -36,9 +36,9 @@ void lookup_denominator(Fr* p, const Fr* a, const Fr* sp, const Fr& beta, const 
 void lookup_numerator(Fr* p, const Fr* in, const Fr* tab, const Fr& beta, const Fr& gamma, size_t n, cudaStream_t s);
 // permute_expression_pair for values < n: a counting sort over the value domain [0, n), which covers the
 // halo2-base range table. Writes rows [0, usable) of a_out / s_out. Returns (after synchronising) 0 on success or a bit
-// mask: LOOKUP_UNSUPPORTED — an input or table value is >= n (not a range-style table: outside what this sort handles,
-// NOT a statement about the witness); LOOKUP_NOT_IN_TABLE — an input value is missing from the table (halo2's
-// ConstraintSystemFailure).
+// mask: LOOKUP_UNSUPPORTED — a TABLE value is >= n (not a range-style table: outside what this sort handles, NOT a
+// statement about the witness); LOOKUP_NOT_IN_TABLE — an input value is missing from the table (halo2's
+// ConstraintSystemFailure; an input >= n is missing from any supported table).
 constexpr int LOOKUP_UNSUPPORTED = 1, LOOKUP_NOT_IN_TABLE = 2;
 int lookup_permute(Context& ctx, const Fr* input, const Fr* table, Fr* a_out, Fr* s_out, size_t n, size_t usable);
 

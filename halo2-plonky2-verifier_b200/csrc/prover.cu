@@ -289,7 +289,7 @@ static void eval_many_dist(Context& ctx, Sharder& shard, const std::vector<const
     for (size_t i = ctx.rank; i < m; i += world) mine.push_back(polys[i]);
     std::vector<Fr> send(per, f_zero<FrCfg>()), recv(per * world);
     fr_eval_many(ctx, mine, n, point, send.data());
-    if (ctx.allgather(ctx.allgather_user, send.data(), per * sizeof(Fr), recv.data()) != 0) throw std::runtime_error("evaluation all-gather failed");
+    shard.host_allgather(send.data(), per * sizeof(Fr), recv.data());
     for (size_t i = 0; i < m; ++i) out[i] = recv[(i % world) * per + i / world];
 }
 
@@ -525,10 +525,10 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
     }
     if (shard.on() && L) {  // a failure seen by one rank must stop every rank before the next collective
         std::vector<uint32_t> all(ctx.world);
-        if (ctx.allgather(ctx.allgather_user, &lookup_failed, sizeof(uint32_t), all.data()) != 0) throw std::runtime_error("lookup status exchange failed");
+        shard.host_allgather(&lookup_failed, sizeof(uint32_t), all.data());
         for (uint32_t f : all) lookup_failed |= f;
     }
-    if (lookup_failed & LOOKUP_UNSUPPORTED) throw std::invalid_argument("create_proof: lookup values must be < 2^k (range-style tables only)");
+    if (lookup_failed & LOOKUP_UNSUPPORTED) throw std::invalid_argument("create_proof: lookup table values must be < 2^k (range-style tables only)");
     if (lookup_failed) throw SynthesisError("ConstraintSystemFailure: lookup input not in table");
     shard.allgather_columns(perm_cols.get(), L, 2 * n);  // column l = a'_l followed by s'_l
     lap(tm ? &tm->lookup : nullptr);
@@ -589,7 +589,7 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
         }
         if (dist_sets) {
             std::vector<Fr> all((size_t)NS * ctx.world);
-            if (ctx.allgather(ctx.allgather_user, E.data(), NS * sizeof(Fr), all.data()) != 0) throw std::runtime_error("grand-product exchange failed");
+            shard.host_allgather(E.data(), NS * sizeof(Fr), all.data());
             for (uint32_t set = 0; set < NS; ++set) E[set] = all[(size_t)shard.owner(set) * NS + set];
         }
         std::vector<Fr> blind((size_t)NS * bf);

@@ -51,6 +51,7 @@ void srs_build_tables(Context& ctx) {
     srs.g_tab.release();
     srs.gl_tab.release();
     srs.tab_n = 0;
+    srs.tab_agreed[0] = srs.tab_agreed[1] = -1;
     if (!ctx.msm_tables_enabled) return;
     // full-range tables on every rank: column-dealt batches need all points, point-range shards index into the same table
     size_t lo = 0, len = srs.n;

@@ -140,8 +140,8 @@ B200ZK_API int b200zk_msm_bases_dev(b200zk_ctx* ctx, const b200zk_g1_affine* bas
  * eval_polynomial   : arithmetic::eval_polynomial(poly, point).
  * kate_division     : arithmetic::kate_division(a, b): quotient of a(X) by (X - b), n-1 coefficients.
  * permute_expression_pair : lookup::prover::permute_expression_pair on the first n-7 rows, for range-style tables: every
- *                     input and table value must be < n = 2^k (B200ZK_EINVAL otherwise — an unsupported table, not a
- *                     verdict on the witness); B200ZK_ESYNTH when an input is missing from the table. n-7 rows out. */
+ *                     table value must be < n = 2^k (B200ZK_EINVAL otherwise — an unsupported table, not a verdict on
+ *                     the witness); B200ZK_ESYNTH when an input is missing from the table. n-7 rows out. */
 B200ZK_API int b200zk_batch_invert(b200zk_ctx* ctx, b200zk_fr* a, size_t n);
 B200ZK_API int b200zk_prefix_product(b200zk_ctx* ctx, const b200zk_fr* m, const b200zk_fr* first, b200zk_fr* z, size_t n);
 B200ZK_API int b200zk_eval_polynomial(b200zk_ctx* ctx, const b200zk_fr* poly, size_t n, const b200zk_fr* point, b200zk_fr* out);

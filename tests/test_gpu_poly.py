@@ -82,9 +82,15 @@ def test_permute_expression_pair(ctx, k, kind):
     with pytest.raises(b200zk.B200zkError) as e:
         ctx.permute_expression_pair(k, bad, table)
     assert e.value.code == b200zk.ESYNTH
-    # a value outside [0, n) is an UNSUPPORTED table/input for this counting sort (EINVAL), not a constraint failure
+    # a TABLE value outside [0, n) is an unsupported table for this counting sort (EINVAL), not a constraint failure;
+    # an input value outside [0, n) is missing from every supported table (ESYNTH)
+    big_table = table.copy()
+    big_table[n // 5] = O.to_mont(n + 3)
+    with pytest.raises(b200zk.B200zkError) as e:
+        ctx.permute_expression_pair(k, inp, big_table)
+    assert e.value.code == b200zk.EINVAL
     big = inp.copy()
-    big[n // 5] = O.to_mont(n + 3)
+    big[n // 5] = O.to_mont(O.R_MOD - 2)
     with pytest.raises(b200zk.B200zkError) as e:
         ctx.permute_expression_pair(k, big, table)
-    assert e.value.code == b200zk.EINVAL
+    assert e.value.code == b200zk.ESYNTH

@@ -338,6 +338,12 @@ def main():
                                                   "Gbutterfly_s": ntt_bfly / (ntt_ms * 1e-3) / 1e9 if ntt_ms else None},
                                      "quotient": {"ms": q_ms, "launches": q_n}},
     }
+    if dist is not None:
+        # per-rank stage split of the one profiled step (stream synchronised at every stage boundary and around every
+        # collective): `comm` = wall time inside collectives incl. waiting for the slowest peer, already contained in the stages
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, {k_: round(v * 1e3, 2) for k_, v in stages.items()})
+        line["per_rank_stages_ms"] = per_rank
     if rank == 0 and world == 1 and not args.no_extras:  # single-GPU side lines (a sharded context would wait for its peers)
         line.update(side_lines(ctx, stream, torch, np, k))
     pk.close()

@@ -94,6 +94,25 @@ class Context:
             raise B200zkError(rc, "no usable CUDA device (libb200zk has no CPU fallback)" if rc == ENODEV else "b200zk_create failed")
         self.device = device
 
+    @classmethod
+    def multi(cls, devices):
+        """b200zk_create_multi: ONE process driving several GPUs (one worker thread per device inside the library, NCCL among
+        them). srs_setup / srs_load / keygen / create_proof / msm on the returned context run sharded over all devices and
+        return the single-GPU results byte for byte."""
+        devices = [int(d) for d in devices]
+        self = cls.__new__(cls)
+        self._h = ctypes.c_void_p()
+        arr = (ctypes.c_int * len(devices))(*devices)
+        rc = lib().b200zk_create_multi(arr, len(devices), ctypes.byref(self._h))
+        if rc != OK:
+            raise B200zkError(rc, "b200zk_create_multi failed (no usable CUDA devices, duplicate ordinals, or NCCL not loadable)")
+        self.device = devices[0]
+        self.devices = devices
+        return self
+
+    def group_size(self):
+        return int(lib().b200zk_group_size(self._h))
+
     def close(self):
         if getattr(self, "_h", None):
             lib().b200zk_destroy(self._h)
@@ -365,7 +384,7 @@ class Context:
         return ProvingKey(self, k, A, L, F, fixed, copies)
 
 
-TIMING_KEYS = ("upload", "msm", "ntt", "lookup", "products", "quotient", "evals", "shplonk", "other")
+TIMING_KEYS = ("upload", "msm", "ntt", "lookup", "products", "quotient", "evals", "shplonk", "other", "comm")
 
 
 class ProvingKey:
@@ -438,7 +457,7 @@ class ProvingKey:
         k, A, L, F = self.shape
         buf = np.empty(self.proof_size(), dtype=np.uint8)
         plen = ctypes.c_size_t(0)
-        tm = np.zeros(9, dtype=np.float64)
+        tm = np.zeros(len(TIMING_KEYS), dtype=np.float64)
         if device_ptr is not None:
             self.ctx._check(lib().b200zk_create_proof_dev(self.ctx._h, self._h, ctypes.c_void_p(device_ptr), ctypes.c_uint64(rng_seed), _p(buf),
                                                           ctypes.byref(plen), _p(tm) if timings else None))

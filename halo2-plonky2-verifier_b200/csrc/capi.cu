@@ -18,8 +18,61 @@ void srs_read(Context& ctx, const uint8_t* data, size_t len, int format);
 size_t srs_write(Context& ctx, int format, uint8_t* out, size_t cap);
 }
 
+#include <thread>
+
 struct b200zk_ctx {
     Context c;
+    // device group (b200zk_create_multi): this is rank 0 and owns the contexts of ranks 1..N-1
+    std::vector<b200zk_ctx*> peers;
+    std::vector<Fr*> group_advice;  // per peer: a device buffer for the witness of b200zk_create_proof_dev (grown on demand)
+    std::vector<size_t> group_advice_cap;
+    b200zk_ctx* rank_ctx(int r) { return r == 0 ? this : peers[r - 1]; }
+    int group_size() const { return 1 + (int)peers.size(); }
+};
+
+// One process, several GPUs: a call on the group context runs on every device in lockstep, one worker thread per device
+// (the sharded prover is SPMD: every rank executes the same create_proof and meets its peers in the collectives).
+// Workers re-enter the same exported function with their rank's context; tls_group_worker stops the recursion there.
+static thread_local bool tls_group_worker = false;
+template <class F>
+static int group_call(b200zk_ctx* ctx, F&& fn) {
+    const int N = ctx->group_size();
+    std::vector<int> rc(N, 0);
+    std::vector<std::thread> th;
+    for (int r = 1; r < N; ++r)
+        th.emplace_back([&, r]() {
+            tls_group_worker = true;
+            rc[r] = fn(ctx->rank_ctx(r), r);
+        });
+    tls_group_worker = true;
+    rc[0] = fn(ctx, 0);
+    tls_group_worker = false;
+    for (auto& t : th) t.join();
+    for (int r = 0; r < N; ++r)
+        if (rc[r] != 0) {
+            if (r != 0) ctx->c.last_error = "device group rank " + std::to_string(r) + ": " + ctx->rank_ctx(r)->c.last_error;
+            return rc[r];
+        }
+    return 0;
+}
+#define GROUP_DISPATCH(ctx, expr)                                            \
+    if ((ctx) && !(ctx)->peers.empty() && !tls_group_worker)                 \
+        return group_call((ctx), [&](b200zk_ctx* rctx, int rank) -> int {    \
+            (void)rank;                                                      \
+            return (expr);                                                   \
+        });
+// entry points that take device pointers of ONE device (or are per-device by nature) run on rank 0 alone in a group
+struct SoloGuard {
+    Context* c = nullptr;
+    explicit SoloGuard(b200zk_ctx* ctx) {
+        if (ctx && !ctx->peers.empty() && !tls_group_worker) {
+            c = &ctx->c;
+            c->solo = true;
+        }
+    }
+    ~SoloGuard() {
+        if (c) c->solo = false;
+    }
 };
 
 #define API_BEGIN(ctx)                      \
@@ -91,8 +144,83 @@ int b200zk_create(int device, b200zk_ctx** out) {
     *out = ctx;
     return B200ZK_OK;
 }
+int b200zk_create_multi(const int* devices, int ndev, b200zk_ctx** out) {
+    if (!out || !devices || ndev < 1 || ndev > 64) return B200ZK_EINVAL;
+    for (int i = 0; i < ndev; ++i)
+        for (int j = 0; j < i; ++j)
+            if (devices[i] == devices[j]) return B200ZK_EINVAL;  // one rank per GPU
+    std::vector<b200zk_ctx*> ctxs(ndev, nullptr);
+    int rc = B200ZK_OK;
+    for (int i = 0; i < ndev && rc == B200ZK_OK; ++i) rc = b200zk_create(devices[i], &ctxs[i]);
+    auto fail = [&](int code) {
+        for (auto* c : ctxs)
+            if (c) b200zk_destroy(c);
+        return code;
+    };
+    if (rc != B200ZK_OK) return fail(rc);
+    if (ndev == 1) {
+        *out = ctxs[0];
+        return B200ZK_OK;
+    }
+    // the communicator: the id is made here and shared in memory; ncclCommInitRank blocks until every rank has joined,
+    // hence one thread per device
+    Nccl::UniqueId id;
+    memset(&id, 0, sizeof(id));
+    try {
+        Nccl boot;
+        boot.load();
+        boot.check(boot.GetUniqueId(&id), "GetUniqueId");
+    } catch (const std::exception&) {
+        return fail(B200ZK_ESTATE);
+    }
+    std::vector<int> ok(ndev, 0);
+    std::vector<std::thread> th;
+    for (int r = 0; r < ndev; ++r)
+        th.emplace_back([&, r]() {
+            try {
+                if (cudaSetDevice(devices[r]) != cudaSuccess) return;
+                auto n = std::make_shared<Nccl>();
+                n->init_with_id(r, ndev, id);
+                ctxs[r]->c.rank = r;
+                ctxs[r]->c.world = ndev;
+                ctxs[r]->c.nccl = n;
+                ok[r] = 1;
+            } catch (const std::exception& e) {
+                ctxs[r]->c.last_error = e.what();
+            }
+        });
+    for (auto& t : th) t.join();
+    for (int r = 0; r < ndev; ++r)
+        if (!ok[r]) return fail(B200ZK_ESTATE);
+    ctxs[0]->peers.assign(ctxs.begin() + 1, ctxs.end());
+    ctxs[0]->group_advice.assign(ndev - 1, nullptr);
+    ctxs[0]->group_advice_cap.assign(ndev - 1, 0);
+    *out = ctxs[0];
+    return B200ZK_OK;
+}
+int b200zk_group_size(b200zk_ctx* ctx) { return ctx ? ctx->group_size() : 0; }
 int b200zk_destroy(b200zk_ctx* ctx) {
     if (!ctx) return B200ZK_EINVAL;
+    if (!ctx->peers.empty()) {
+        // communicators first, all ranks at once (ncclCommDestroy may wait for its peers), then the contexts
+        std::vector<std::thread> th;
+        for (int r = 0; r < ctx->group_size(); ++r)
+            th.emplace_back([ctx, r]() {
+                b200zk_ctx* rc = ctx->rank_ctx(r);
+                cudaSetDevice(rc->c.device);
+                cudaStreamSynchronize(rc->c.stream);
+                rc->c.nccl.reset();
+            });
+        for (auto& t : th) t.join();
+        for (size_t i = 0; i < ctx->peers.size(); ++i) {
+            if (ctx->group_advice[i]) {
+                cudaSetDevice(ctx->peers[i]->c.device);
+                cudaFree(ctx->group_advice[i]);
+            }
+            b200zk_destroy(ctx->peers[i]);
+        }
+        ctx->peers.clear();
+    }
     cudaSetDevice(ctx->c.device);
     cudaStreamSynchronize(ctx->c.stream);
     cudaStream_t s = ctx->c.stream;
@@ -131,6 +259,7 @@ int b200zk_destroy(b200zk_ctx* ctx) {
 const char* b200zk_last_error(b200zk_ctx* ctx) { return ctx ? ctx->c.last_error.c_str() : "null context"; }
 void* b200zk_stream(b200zk_ctx* ctx) { return ctx ? (void*)ctx->c.stream : nullptr; }
 int b200zk_sync(b200zk_ctx* ctx) {
+    GROUP_DISPATCH(ctx, b200zk_sync(rctx))
     API_BEGIN(ctx)
     CUDA_CHECK(cudaStreamSynchronize(ctx->c.stream));
     API_END(ctx)
@@ -177,6 +306,7 @@ int b200zk_profile_work(b200zk_ctx* ctx, int id, double* units) {
     API_END(ctx)
 }
 int b200zk_set_allgather(b200zk_ctx* ctx, int rank, int world, b200zk_allgather_fn fn, void* user) {
+    if (ctx && !ctx->peers.empty()) return B200ZK_EINVAL;  // a device group has its own communicator
     API_BEGIN(ctx)
     if (world < 1 || rank < 0 || rank >= world || (world > 1 && !fn)) throw std::invalid_argument("set_allgather: bad arguments");
     ctx->c.rank = rank;
@@ -187,6 +317,7 @@ int b200zk_set_allgather(b200zk_ctx* ctx, int rank, int world, b200zk_allgather_
     API_END(ctx)
 }
 int b200zk_set_msm_tables(b200zk_ctx* ctx, int on) {
+    GROUP_DISPATCH(ctx, b200zk_set_msm_tables(rctx, on))
     API_BEGIN(ctx)
     ctx->c.msm_tables_enabled = on != 0;
     srs_build_tables(ctx->c);
@@ -423,6 +554,7 @@ int b200zk_extended_to_coeff(b200zk_ctx* ctx, uint32_t k, const b200zk_fr* in, b
 extern "C" {
 
 int b200zk_srs_load(b200zk_ctx* ctx, uint32_t k, const b200zk_g1_affine* g, const b200zk_g1_affine* g_lagrange) {
+    GROUP_DISPATCH(ctx, b200zk_srs_load(rctx, k, g, g_lagrange))
     API_BEGIN(ctx)
     if (!g || !g_lagrange || k > 26) throw std::invalid_argument("srs_load: bad arguments");
     Context& c = ctx->c;
@@ -445,6 +577,7 @@ static const G1Affine* srs_basis(Context& c, int basis, size_t n) {
     return basis == 0 ? c.srs->g.get() : c.srs->g_lagrange.get();
 }
 int b200zk_msm_bases_dev(b200zk_ctx* ctx, const b200zk_g1_affine* bases_dev, const b200zk_fr* scalars_dev, size_t n, b200zk_g1_affine* out) {
+    SoloGuard solo(ctx);
     API_BEGIN(ctx)
     if (!out || (n && (!bases_dev || !scalars_dev))) throw std::invalid_argument("msm: null argument");
     G1Affine r = msm_run(ctx->c, (const G1Affine*)bases_dev, (const Fr*)scalars_dev, n);
@@ -452,6 +585,7 @@ int b200zk_msm_bases_dev(b200zk_ctx* ctx, const b200zk_g1_affine* bases_dev, con
     API_END(ctx)
 }
 int b200zk_msm_dev(b200zk_ctx* ctx, int basis, const b200zk_fr* scalars_dev, size_t n, b200zk_g1_affine* out) {
+    SoloGuard solo(ctx);
     API_BEGIN(ctx)
     if (!out || (n && !scalars_dev)) throw std::invalid_argument("msm: null argument");
     srs_basis(ctx->c, basis, n);
@@ -460,6 +594,7 @@ int b200zk_msm_dev(b200zk_ctx* ctx, int basis, const b200zk_fr* scalars_dev, siz
     API_END(ctx)
 }
 int b200zk_msm_batch_dev(b200zk_ctx* ctx, int basis, const b200zk_fr* const* cols_dev, size_t ncols, size_t n, b200zk_g1_affine* out) {
+    SoloGuard solo(ctx);
     API_BEGIN(ctx)
     if (!out || (ncols && !cols_dev)) throw std::invalid_argument("msm_batch: null argument");
     srs_basis(ctx->c, basis, n);
@@ -469,6 +604,10 @@ int b200zk_msm_batch_dev(b200zk_ctx* ctx, int basis, const b200zk_fr* const* col
     API_END(ctx)
 }
 int b200zk_msm_batch(b200zk_ctx* ctx, int basis, const b200zk_fr* const* cols, size_t ncols, size_t n, b200zk_g1_affine* out) {
+    if (ctx && !ctx->peers.empty() && !tls_group_worker) {  // every rank uploads the columns and takes its share; rank 0's results are returned
+        std::vector<std::vector<b200zk_g1_affine>> scratch(ctx->group_size(), std::vector<b200zk_g1_affine>(out ? ncols : 0));
+        return group_call(ctx, [&](b200zk_ctx* rctx, int rank) -> int { return b200zk_msm_batch(rctx, basis, cols, ncols, n, rank == 0 ? out : scratch[rank].data()); });
+    }
     API_BEGIN(ctx)
     if (!out || (ncols && !cols)) throw std::invalid_argument("msm_batch: null argument");
     Context& c = ctx->c;
@@ -497,6 +636,10 @@ int b200zk_msm_batch(b200zk_ctx* ctx, int basis, const b200zk_fr* const* cols, s
     API_END(ctx)
 }
 int b200zk_msm(b200zk_ctx* ctx, int basis, const b200zk_fr* scalars, size_t n, b200zk_g1_affine* out) {
+    if (ctx && !ctx->peers.empty() && !tls_group_worker) {  // point-range shards on every device, partial sums over NCCL
+        std::vector<b200zk_g1_affine> scratch(ctx->group_size());
+        return group_call(ctx, [&](b200zk_ctx* rctx, int rank) -> int { return b200zk_msm(rctx, basis, scalars, n, rank == 0 ? out : &scratch[rank]); });
+    }
     API_BEGIN(ctx)
     if (!out || (n && !scalars)) throw std::invalid_argument("msm: null argument");
     Context& c = ctx->c;
@@ -508,6 +651,10 @@ int b200zk_msm(b200zk_ctx* ctx, int basis, const b200zk_fr* scalars, size_t n, b
     API_END(ctx)
 }
 int b200zk_msm_bases(b200zk_ctx* ctx, const b200zk_g1_affine* bases, const b200zk_fr* scalars, size_t n, b200zk_g1_affine* out) {
+    if (ctx && !ctx->peers.empty() && !tls_group_worker) {
+        std::vector<b200zk_g1_affine> scratch(ctx->group_size());
+        return group_call(ctx, [&](b200zk_ctx* rctx, int rank) -> int { return b200zk_msm_bases(rctx, bases, scalars, n, rank == 0 ? out : &scratch[rank]); });
+    }
     API_BEGIN(ctx)
     if (!out || (n && (!scalars || !bases))) throw std::invalid_argument("msm: null argument");
     Context& c = ctx->c;
@@ -527,12 +674,27 @@ int b200zk_msm_bases(b200zk_ctx* ctx, const b200zk_g1_affine* bases, const b200z
 // ---- keygen / create_proof ------------------------------------------------------------------------------------------
 struct b200zk_pk {
     std::unique_ptr<ProvingKeyDev> pk;
+    std::vector<b200zk_pk*> peers;  // device group: the keys of ranks 1..N-1 (every rank holds the whole key)
+    const b200zk_pk* rank_pk(int r) const { return r == 0 ? this : peers[r - 1]; }
 };
 
 extern "C" {
 
 int b200zk_keygen(b200zk_ctx* ctx, uint32_t k, uint32_t A, uint32_t L, uint32_t F, const b200zk_fr* fixed, const uint32_t* copies, size_t ncopies,
                   b200zk_pk** out) {
+    if (ctx && !ctx->peers.empty() && !tls_group_worker) {
+        if (!out) return B200ZK_EINVAL;
+        std::vector<b200zk_pk*> pks(ctx->group_size(), nullptr);
+        const int rc = group_call(ctx, [&](b200zk_ctx* rctx, int rank) -> int { return b200zk_keygen(rctx, k, A, L, F, fixed, copies, ncopies, &pks[rank]); });
+        if (rc != B200ZK_OK) {
+            for (int r = 0; r < ctx->group_size(); ++r)
+                if (pks[r]) b200zk_pk_free(ctx->rank_ctx(r), pks[r]);
+            return rc;
+        }
+        pks[0]->peers.assign(pks.begin() + 1, pks.end());
+        *out = pks[0];
+        return B200ZK_OK;
+    }
     API_BEGIN(ctx)
     if (!fixed || !out || (ncopies && !copies)) throw std::invalid_argument("keygen: null argument");
     Shape sh{k, A, L, F};
@@ -541,6 +703,12 @@ int b200zk_keygen(b200zk_ctx* ctx, uint32_t k, uint32_t A, uint32_t L, uint32_t 
     API_END(ctx)
 }
 int b200zk_pk_free(b200zk_ctx* ctx, b200zk_pk* pk) {
+    if (ctx && pk && !pk->peers.empty() && !tls_group_worker) {
+        if (pk->peers.size() != ctx->peers.size()) return B200ZK_EINVAL;
+        std::vector<b200zk_pk*> peers;
+        peers.swap(pk->peers);
+        for (size_t i = 0; i < peers.size(); ++i) b200zk_pk_free(ctx->peers[i], peers[i]);
+    }
     API_BEGIN(ctx)
     delete pk;
     API_END(ctx)
@@ -578,12 +746,14 @@ int b200zk_pk_get_column(b200zk_ctx* ctx, const b200zk_pk* pk, int which, uint32
     API_END(ctx)
 }
 int b200zk_srs_setup_trapdoor(b200zk_ctx* ctx, uint32_t k, const b200zk_fr* s) {
+    GROUP_DISPATCH(ctx, b200zk_srs_setup_trapdoor(rctx, k, s))
     API_BEGIN(ctx)
     if (!s) throw std::invalid_argument("srs_setup: null trapdoor");
     srs_setup(ctx->c, k, load_fr(s));
     API_END(ctx)
 }
 int b200zk_srs_setup(b200zk_ctx* ctx, uint32_t k, const uint8_t seed[32], b200zk_fr* trapdoor_out) {
+    GROUP_DISPATCH(ctx, b200zk_srs_setup(rctx, k, seed, rank == 0 ? trapdoor_out : nullptr))
     API_BEGIN(ctx)
     if (!seed) throw std::invalid_argument("srs_setup: null seed");
     host::FrRandomStream rng = host::FrRandomStream::chacha20_from_seed(seed);
@@ -594,6 +764,7 @@ int b200zk_srs_setup(b200zk_ctx* ctx, uint32_t k, const uint8_t seed[32], b200zk
 }
 size_t b200zk_srs_file_size(uint32_t k, int format) { return srs_file_size(k, format); }
 int b200zk_srs_read(b200zk_ctx* ctx, const uint8_t* data, size_t len, int format) {
+    GROUP_DISPATCH(ctx, b200zk_srs_read(rctx, data, len, format))
     API_BEGIN(ctx)
     if (!data) throw std::invalid_argument("srs_read: null data");
     srs_read(ctx->c, data, len, format);
@@ -617,6 +788,34 @@ int b200zk_srs_download(b200zk_ctx* ctx, b200zk_g1_affine* g, b200zk_g1_affine* 
 size_t b200zk_proof_size(uint32_t k, uint32_t A, uint32_t L, uint32_t F) { return Shape{k, A, L, F}.proof_size(); }
 static int create_proof_impl(b200zk_ctx* ctx, const b200zk_pk* pk, const b200zk_fr* advice, bool on_device, uint64_t rng_seed, uint8_t* proof_out,
                              size_t* proof_len, double* timings) {
+    if (ctx && !ctx->peers.empty() && !tls_group_worker) {
+        // device group: every rank proves in lockstep (the sharded prover); rank 0's proof is returned — all ranks produce
+        // the same bytes. A device-resident witness lives on rank 0's GPU and is copied to the peers over NVLink first.
+        if (!pk || !advice || !proof_out || !proof_len || pk->peers.size() != ctx->peers.size()) return B200ZK_EINVAL;
+        const int N = ctx->group_size();
+        const size_t bytes = (size_t)pk->pk->shape.num_advice() * pk->pk->shape.n() * sizeof(Fr), psize = pk->pk->shape.proof_size();
+        std::vector<std::vector<uint8_t>> proofs(N, std::vector<uint8_t>(psize));
+        std::vector<size_t> lens(N, 0);
+        std::vector<const b200zk_fr*> adv(N, advice);
+        if (on_device)
+            for (int r = 1; r < N; ++r) {
+                b200zk_ctx* rc = ctx->rank_ctx(r);
+                if (ctx->group_advice_cap[r - 1] < bytes) {
+                    cudaSetDevice(rc->c.device);
+                    if (ctx->group_advice[r - 1]) cudaFree(ctx->group_advice[r - 1]);
+                    ctx->group_advice[r - 1] = nullptr;
+                    ctx->group_advice_cap[r - 1] = 0;
+                    if (cudaMalloc((void**)&ctx->group_advice[r - 1], bytes) != cudaSuccess) return B200ZK_ECUDA;
+                    ctx->group_advice_cap[r - 1] = bytes;
+                }
+                if (cudaMemcpyPeer(ctx->group_advice[r - 1], rc->c.device, advice, ctx->c.device, bytes) != cudaSuccess) return B200ZK_ECUDA;
+                adv[r] = (const b200zk_fr*)ctx->group_advice[r - 1];
+            }
+        return group_call(ctx, [&](b200zk_ctx* rctx, int rank) -> int {
+            return create_proof_impl(rctx, pk->rank_pk(rank), adv[rank], on_device, rng_seed, rank == 0 ? proof_out : proofs[rank].data(),
+                                     rank == 0 ? proof_len : &lens[rank], rank == 0 ? timings : nullptr);
+        });
+    }
     API_BEGIN(ctx)
     if (!pk || !advice || !proof_out || !proof_len) throw std::invalid_argument("create_proof: null argument");
     host::FrRandomStream rng = host::FrRandomStream::std_rng_seed_from_u64(rng_seed);
@@ -625,7 +824,7 @@ static int create_proof_impl(b200zk_ctx* ctx, const b200zk_pk* pk, const b200zk_
     memcpy(proof_out, proof.data(), proof.size());
     *proof_len = proof.size();
     if (timings) {
-        const double t[9] = {tm.upload, tm.msm, tm.ntt, tm.lookup, tm.products, tm.quotient, tm.evals, tm.shplonk, tm.other};
+        const double t[10] = {tm.upload, tm.msm, tm.ntt, tm.lookup, tm.products, tm.quotient, tm.evals, tm.shplonk, tm.other, tm.comm};
         memcpy(timings, t, sizeof(t));
     }
     API_END(ctx)

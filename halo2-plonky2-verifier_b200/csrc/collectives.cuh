@@ -8,6 +8,8 @@
 #pragma once
 #include <dlfcn.h>
 
+#include <chrono>
+
 #include "context.cuh"
 
 namespace b200zk {
@@ -99,6 +101,22 @@ struct Sharder {
     Context& ctx;
     bool enabled = true;  // false: this call works on the local GPU alone even inside a multi-rank job
     explicit Sharder(Context& c) : ctx(c) {}
+    // brackets one collective when tracing: local work queued before it is drained first, so the span is the collective alone
+    struct CommSpan {
+        Context& c;
+        std::chrono::steady_clock::time_point t0;
+        explicit CommSpan(Context& ctx_) : c(ctx_) {
+            if (!c.comm_trace) return;
+            cudaStreamSynchronize(c.stream);
+            t0 = std::chrono::steady_clock::now();
+        }
+        ~CommSpan() {
+            if (!c.comm_trace) return;
+            cudaStreamSynchronize(c.stream);
+            c.comm_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            ++c.comm_calls;
+        }
+    };
     bool on() const { return enabled && ctx.sharded(); }
     int owner(size_t i, size_t off = 0) const { return on() ? (int)((i + off) % ctx.world) : 0; }
     bool mine(size_t i, size_t off = 0) const { return !on() || owner(i, off) == ctx.rank; }
@@ -115,6 +133,7 @@ struct Sharder {
     // round trip through the host process's own collective layer.
     void host_allgather(const void* send, size_t bytes, void* recv) {
         Nccl& nc = nccl();
+        CommSpan span(ctx);
         nc.ensure_stage(bytes, ctx.stream);
         uint8_t* pin_send = nc.stage_pin + nc.stage_cap * nc.world;
         memcpy(pin_send, send, bytes);
@@ -127,6 +146,7 @@ struct Sharder {
     // the same for a piece that is already in DEVICE memory (the partial sums of a commit batch): no upload
     void dev_to_host_allgather(const void* send_dev, size_t bytes, void* recv) {
         Nccl& nc = nccl();
+        CommSpan span(ctx);
         nc.ensure_stage(bytes, ctx.stream);
         nc.check(nc.AllGather(send_dev, nc.stage_dev, bytes, 1, nc.comm, ctx.stream), "AllGather");
         CUDA_CHECK(cudaMemcpyAsync(nc.stage_pin, nc.stage_dev, bytes * nc.world, cudaMemcpyDeviceToHost, ctx.stream));
@@ -142,6 +162,7 @@ struct Sharder {
     // every rank ends up with the owner's copy of buf[0..count)
     void broadcast(Fr* buf, size_t count, int root) {
         if (!on()) return;
+        CommSpan span(ctx);
         nccl().check(nccl().Broadcast(buf, buf, count * sizeof(Fr), /*ncclUint8*/ 1, root, nccl().comm, ctx.stream), "Broadcast");
     }
     // Columns base[c·len .. (c+1)·len), c < ncols, each complete on rank owner(c, off) only: afterwards complete everywhere.
@@ -149,6 +170,7 @@ struct Sharder {
     // launch): stage[r][j] = the j-th column owned by rank r = column first(r) + j·world.
     void allgather_columns(Fr* base, size_t ncols, size_t len, size_t off = 0) {
         if (!on() || ncols == 0) return;
+        CommSpan span(ctx);
         const size_t world = ctx.world, per = (ncols + world - 1) / world;
         auto first = [&](size_t r) { return (r + world - off % world) % world; };  // smallest column index owned by rank r
         DevBuf<Fr> stage(world * per * len, ctx.stream);
@@ -169,6 +191,7 @@ struct Sharder {
     void exchange_row_slices(Fr* const* cols, size_t ncols, OwnerFn owner_of, size_t en, size_t before, size_t after) {
         if (!on()) return;
         Nccl& nc = nccl();
+        CommSpan span(ctx);
         const size_t R = en / ctx.world;
         auto for_segments = [&](int d, auto&& fn) {  // contiguous pieces of rank d's window
             const long long start = (long long)(R * d) - (long long)before, end = (long long)(R * (d + 1)) + (long long)after;
@@ -206,6 +229,7 @@ struct Sharder {
     // buf holds world equal chunks; this rank filled chunk `rank`
     void all_gather_inplace(Fr* buf, size_t chunk) {
         if (!on()) return;
+        CommSpan span(ctx);
         nccl().check(nccl().AllGather(buf + (size_t)ctx.rank * chunk, buf, chunk * sizeof(Fr), 1, nccl().comm, ctx.stream), "AllGather");
     }
 };

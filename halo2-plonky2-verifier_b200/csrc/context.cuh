@@ -108,12 +108,18 @@ struct Context {
     int rank = 0, world = 1;
     AllGatherFn allgather = nullptr;
     void* allgather_user = nullptr;
+    // with comm_trace set (the timings mode of create_proof) every collective is bracketed by stream synchronisations and
+    // its wall time — transfer plus waiting for the slowest peer — is added to comm_seconds
+    bool comm_trace = false;
+    double comm_seconds = 0;
+    unsigned comm_calls = 0;
     double exchange_seconds = 0;  // host time spent in the cross-rank exchange of partial MSM sums (reported under "other")
     bool msm_tables_enabled = true;
     std::shared_ptr<struct Nccl> nccl;  // collectives.cuh: created on first use from the bootstrap callback (one process per
                                         // GPU), or installed by b200zk_create_multi (one process, one thread per GPU)
     // this context is one rank of a multi-GPU job
-    bool sharded() const { return world > 1 && (allgather != nullptr || nccl != nullptr); }
+    bool solo = false;  // set around calls that must run on this GPU alone although the context belongs to a device group
+    bool sharded() const { return !solo && world > 1 && (allgather != nullptr || nccl != nullptr); }
 
     // table of the standard 2^t-th root with t >= log_n
     const TwiddleTable& std_table(uint32_t log_n) {

@@ -66,7 +66,15 @@ MsmConfig msm_config_merged(uint32_t c, size_t table_n) {
 }
 // measured at S20-bn / S22-bn: the msm stage is flat for caps 17..21 (fewer buckets trade against more windows) and
 // worse below 16; 20 keeps the table smallest
-uint32_t msm_table_window_bits(uint32_t k) { return k < 8 ? 8 : (k > 20 ? 20 : k); }
+uint32_t msm_table_window_bits(uint32_t k, int world) {
+    uint32_t c = k < 8 ? 8 : (k > 20 ? 20 : k);
+    (void)world;
+    if (const char* e = getenv("B200ZK_TABLE_BITS")) {  // experiments: window bits of the precomputed tables
+        const int v = atoi(e);
+        if (v >= 8 && v <= 22) c = (uint32_t)v;
+    }
+    return c;
+}
 
 DEV G1X g1x_load(const G1X* p) {
     G1X r;

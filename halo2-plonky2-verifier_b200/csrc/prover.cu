@@ -418,6 +418,13 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
     const TwiddleTable& tw = ctx.std_table(sh.k + 2);
     host::Transcript tr;
     const double exchange0 = ctx.exchange_seconds;
+    struct TraceGuard {  // collectives are traced only while a timed call is running
+        Context& c;
+        bool was;
+        ~TraceGuard() { c.comm_trace = was; }
+    } trace_guard{ctx, ctx.comm_trace};
+    ctx.comm_trace = tm != nullptr;
+    const double comm0 = ctx.comm_seconds;
     Sharder shard(ctx);
     if (shard.on()) shard.nccl();  // communicator up before the first timed exchange
     auto clock_now = [&]() {
@@ -922,6 +929,7 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
     if (tm) {  // the MSM stage includes the cross-rank exchange of partial sums: report it separately
         tm->other += ctx.exchange_seconds - exchange0;
         tm->msm -= ctx.exchange_seconds - exchange0;
+        tm->comm = ctx.comm_seconds - comm0;
     }
     return tr.proof;
 }

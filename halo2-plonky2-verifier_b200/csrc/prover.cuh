@@ -45,6 +45,8 @@ struct ProvingKeyDev {
 // wall-clock split of one create_proof call (seconds, stream synchronised at each boundary)
 struct ProofTimings {
     double upload = 0, msm = 0, ntt = 0, lookup = 0, products = 0, quotient = 0, evals = 0, shplonk = 0, other = 0;
+    // multi-GPU: wall time inside collectives (transfer + waiting for the slowest peer); already contained in the stages above
+    double comm = 0;
 };
 
 std::unique_ptr<ProvingKeyDev> keygen(Context& ctx, const Shape& sh, const Fr* fixed_host, const uint32_t* copies, size_t ncopies);

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(128) fixed_base_kernel(const Fr* scalars, size
 
 void msm_build_table(Context& ctx, const G1Affine* bases, size_t n, uint32_t c, DevBuf<G1Affine>& table);
 void srs_g2_raw(const Fr& s_trapdoor, uint8_t out[256]);
-uint32_t msm_table_window_bits(uint32_t k);
+uint32_t msm_table_window_bits(uint32_t k, int world);
 
 // window tables for both bases of the loaded SRS (msm.cu merged-bucket mode)
 void srs_build_tables(Context& ctx) {
@@ -57,7 +57,7 @@ void srs_build_tables(Context& ctx) {
     size_t lo = 0, len = srs.n;
     uint32_t lg = 0;
     while (((size_t)1 << (lg + 1)) <= len) ++lg;
-    srs.tab_c = msm_table_window_bits(lg);
+    srs.tab_c = msm_table_window_bits(lg, ctx.world);
     const uint32_t W = (255 + srs.tab_c - 1) / srs.tab_c;
     if ((size_t)W * len >= ((size_t)1 << 31)) return;  // entry indices are 31-bit: fall back to the generic path
     // a table is W× the basis (56 GiB at k = 26): build it only while at least 35 % of the device (and 16 GiB) stays free

@@ -48,6 +48,18 @@ enum {
 
 /* ---- context ------------------------------------------------------------------------------------------- */
 B200ZK_API int b200zk_create(int device, b200zk_ctx** out);
+/* One process, several GPUs (`b200zk_create(const int* devices, int ndev)`): the returned context owns one
+ * device context and one worker thread per listed device (distinct CUDA ordinals) and an NCCL communicator among them
+ * (NCCL is taken from the process, libnccl.so.2). b200zk_srs_*, b200zk_keygen, b200zk_create_proof(_dev), b200zk_msm,
+ * b200zk_msm_batch and b200zk_msm_bases called on it run on every device in lockstep — commit batches dealt by column with
+ * the remainder split by point range, NTTs by column, h(X) by row slice, partial sums over NVLink — and return what a
+ * single-GPU context returns, byte for byte. This is what a single test process such as the reference's
+ * `bench_builder` caller (verifier/src/stark/mod.rs:543, :593) binds to use all GPUs of a box. Entry points that take device
+ * pointers (`*_dev` MSM / NTT forms, dev_alloc, h2d …) and the column primitives address the first device alone.
+ * ndev = 1 is the same as b200zk_create(devices[0]). */
+B200ZK_API int b200zk_create_multi(const int* devices, int ndev, b200zk_ctx** out);
+/* number of devices behind the context (1 for b200zk_create) */
+B200ZK_API int b200zk_group_size(b200zk_ctx* ctx);
 B200ZK_API int b200zk_destroy(b200zk_ctx* ctx);
 B200ZK_API const char* b200zk_last_error(b200zk_ctx* ctx);
 /* cudaStream_t of the context, for event timing by the caller */
@@ -169,8 +181,9 @@ B200ZK_API int b200zk_pk_get_column(b200zk_ctx* ctx, const b200zk_pk* pk, int wh
 B200ZK_API size_t b200zk_proof_size(uint32_t k, uint32_t A, uint32_t L, uint32_t F);
 /* create_proof::<KZGCommitmentScheme<Bn256>, ProverSHPLONK, Challenge255, StdRng, Blake2bWrite> for ONE circuit without
  * instances. `advice`: (A+L) × 2^k witness values, column-major (rows >= 2^k − 7 are overwritten by blinding).
- * rng = StdRng::seed_from_u64(rng_seed). `proof_out` must hold b200zk_proof_size bytes. `timings` (optional, 9 doubles):
- * seconds spent in upload, msm, ntt, lookup, products, quotient, evals, shplonk, other. */
+ * rng = StdRng::seed_from_u64(rng_seed). `proof_out` must hold b200zk_proof_size bytes. `timings` (optional, 10 doubles):
+ * seconds spent in upload, msm, ntt, lookup, products, quotient, evals, shplonk, other, and — multi-GPU, already contained in
+ * the stages before it — inside collectives (transfer plus waiting for the slowest peer). */
 B200ZK_API int b200zk_create_proof(b200zk_ctx* ctx, const b200zk_pk* pk, const b200zk_fr* advice, uint64_t rng_seed, uint8_t* proof_out,
                                    size_t* proof_len, double* timings);
 /* same with the advice columns already resident in device memory (the witness upload excluded) */

@@ -144,6 +144,37 @@ def test_full_size_proof_verifies(ctx):
     assert not ver.verify(pk.create_proof(advice, 0))[0]
 
 
+def test_full_size_proof_bytes_equal_oracle(ctx):
+    """The headline configuration itself (BASELINE configs[1], S20-bn: k=20, 14+3+1 columns, 41 MSMs of 2^20): the GPU proof
+    must be BYTE-IDENTICAL to the CPU oracle's proof of the same circuit, SRS and rng seed — every commitment, evaluation
+    and the SHPLONK opening. The oracle proves on the host cores (≈ 50 s on 16 threads + ≈ 25 s keygen); its SRS is the one
+    the device generated (device SRS generation is pinned against the oracle's at small k in test_gpu_srs.py), which skips
+    a third of the CPU time. A log of this comparison is kept in profiles/parity_k20_S20bn_r02.log."""
+    import time
+
+    k, A, L, F = 20, 14, 3, 1
+    trapdoor = ctx.srs_setup(k)
+    g, gl = ctx.srs_download()
+    fixed, advice, copies = b200zk.synth_circuit(k, A, L, F, seed=0)
+    pk = ctx.keygen(k, A, L, F, fixed, copies)
+    got = pk.create_proof(advice, 0)
+    params = O.Params.load(k, trapdoor, g, gl)
+    del g, gl
+    t0 = time.time()
+    opk = O.ProvingKey(params, k, A, L, F, fixed, copies)
+    t_keygen = time.time() - t0
+    fc, pc = pk.commitments()
+    ofc, opc = opk.get(0), opk.get(1)
+    assert np.array_equal(fc, ofc) and np.array_equal(pc, opc)  # keygen_vk: every fixed / permutation commitment
+    want = opk.create_proof(advice, 0)
+    print(f"k=20 S20-bn: oracle keygen {t_keygen:.1f} s, oracle create_proof {opk.last_seconds:.1f} s on {O.lib().oracle_get_threads()} threads; "
+          f"proof bytes equal: {got == want}")
+    assert got == want, first_diff(got, want)
+    ok, err = opk.verify(got, pairing=True)
+    assert ok, err
+    pk.close()
+
+
 @pytest.mark.parametrize("shape", [(6, 1, 1, 1), (8, 3, 2, 1), (9, 2, 0, 1), (11, 14, 3, 1)])
 def test_evaluate_h_standalone(ctx, shape):
     """Row H through its own entry point (b200zk_evaluate_h) on RANDOM coefficient-form inputs — h is a polynomial

@@ -158,6 +158,12 @@ class Context:
         self._ag = ALLGATHER_FN(trampoline)
         self._check(lib().b200zk_set_allgather(self._h, int(rank), int(world), self._ag, None))
 
+    COMPAT_NO_UNUSED_BLIND_DRAWS, COMPAT_LOOKUP_FILL_ASCENDING, COMPAT_POINT_SIGN_BIT7 = 1, 2, 4
+
+    def set_compat(self, flags=0, random_poly_chunks=0):
+        """The [UNVERIFIED-1..4] switches of SURVEY.md §8c (include/b200zk.h); (0, 0) = defaults."""
+        self._check(lib().b200zk_set_compat(self._h, ctypes.c_uint32(flags), ctypes.c_uint32(random_poly_chunks)))
+
     def set_msm_tables(self, on=True):
         self._check(lib().b200zk_set_msm_tables(self._h, int(bool(on))))
 

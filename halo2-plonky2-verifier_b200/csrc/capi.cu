@@ -128,6 +128,9 @@ int b200zk_create(int device, b200zk_ctx** out) {
     if (cudaStreamCreateWithFlags(&ctx->c.copy_stream, cudaStreamNonBlocking) != cudaSuccess) ctx->c.copy_stream = nullptr;
     cudaEventCreateWithFlags(&ctx->c.copy_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->c.copy_done, cudaEventDisableTiming);
+    if (cudaStreamCreateWithFlags(&ctx->c.comm_stream, cudaStreamNonBlocking) != cudaSuccess) ctx->c.comm_stream = nullptr;
+    cudaEventCreateWithFlags(&ctx->c.comm_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->c.comm_done, cudaEventDisableTiming);
     if (cudaHostAlloc((void**)&ctx->c.pinned_u32, 64, cudaHostAllocDefault) != cudaSuccess) {
         b200zk_destroy(ctx);
         return B200ZK_ECUDA;
@@ -249,6 +252,12 @@ int b200zk_destroy(b200zk_ctx* ctx) {
     if (ctx->c.stage_buf) cudaFreeHost(ctx->c.stage_buf);
     for (auto& e : ctx->c.stage_ev)
         if (e) cudaEventDestroy(e);
+    if (ctx->c.comm_stream) {
+        cudaStreamSynchronize(ctx->c.comm_stream);
+        cudaStreamDestroy(ctx->c.comm_stream);
+    }
+    if (ctx->c.comm_fork) cudaEventDestroy(ctx->c.comm_fork);
+    if (ctx->c.comm_done) cudaEventDestroy(ctx->c.comm_done);
     if (ctx->c.copy_fork) cudaEventDestroy(ctx->c.copy_fork);
     if (ctx->c.copy_done) cudaEventDestroy(ctx->c.copy_done);
     if (ctx->c.pinned_u32) cudaFreeHost(ctx->c.pinned_u32);
@@ -314,6 +323,17 @@ int b200zk_set_allgather(b200zk_ctx* ctx, int rank, int world, b200zk_allgather_
     ctx->c.allgather = fn;
     ctx->c.allgather_user = user;
     ctx->c.nccl.reset();
+    API_END(ctx)
+}
+int b200zk_set_compat(b200zk_ctx* ctx, uint32_t flags, uint32_t random_poly_chunks) {
+    GROUP_DISPATCH(ctx, b200zk_set_compat(rctx, flags, random_poly_chunks))
+    API_BEGIN(ctx)
+    if (flags & ~7u) throw std::invalid_argument("set_compat: unknown flag bits");
+    Compat& c = ctx->c.compat;
+    c.draw_unused_blinds = !(flags & B200ZK_COMPAT_NO_UNUSED_BLIND_DRAWS);
+    c.lookup_fill_from_end = !(flags & B200ZK_COMPAT_LOOKUP_FILL_ASCENDING);
+    c.point_sign_bit = (flags & B200ZK_COMPAT_POINT_SIGN_BIT7) ? 7 : 6;
+    c.random_poly_chunks = random_poly_chunks;
     API_END(ctx)
 }
 int b200zk_set_msm_tables(b200zk_ctx* ctx, int on) {
@@ -988,7 +1008,7 @@ int b200zk_permute_expression_pair(b200zk_ctx* ctx, uint32_t k, const b200zk_fr*
     DevBuf<Fr> din(n, s), dtab(n, s), da(n, s), ds(n, s);
     CUDA_CHECK(cudaMemcpyAsync(din.get(), input, 32 * n, cudaMemcpyHostToDevice, s));
     CUDA_CHECK(cudaMemcpyAsync(dtab.get(), table, 32 * n, cudaMemcpyHostToDevice, s));
-    const int st = lookup_permute(ctx->c, din.get(), dtab.get(), da.get(), ds.get(), n, u);
+    const int st = lookup_permute(ctx->c, din.get(), dtab.get(), da.get(), ds.get(), n, u, ctx->c.compat.lookup_fill_from_end);
     if (st & LOOKUP_UNSUPPORTED) throw std::invalid_argument("permute_expression_pair: unsupported table — every table value must be < 2^k (range-style tables)");
     if (st & LOOKUP_NOT_IN_TABLE) throw SynthesisError("ConstraintSystemFailure: lookup input not in table");
     CUDA_CHECK(cudaMemcpyAsync(a_out, da.get(), 32 * u, cudaMemcpyDeviceToHost, s));

@@ -166,22 +166,56 @@ struct Sharder {
         nccl().check(nccl().Broadcast(buf, buf, count * sizeof(Fr), /*ncclUint8*/ 1, root, nccl().comm, ctx.stream), "Broadcast");
     }
     // Columns base[c·len .. (c+1)·len), c < ncols, each complete on rank owner(c, off) only: afterwards complete everywhere.
-    // One all-gather over an owner-major staging buffer instead of ncols broadcasts (NVSwitch all-gather bandwidth, one
-    // launch): stage[r][j] = the j-th column owned by rank r = column first(r) + j·world.
-    void allgather_columns(Fr* base, size_t ncols, size_t len, size_t off = 0) {
-        if (!on() || ncols == 0) return;
-        CommSpan span(ctx);
+    // Uneven ownership: one in-place broadcast per column from its owner, all in ONE NCCL group (they run concurrently over
+    // NVSwitch) — only the payload moves and nothing is staged. Even ownership: one all-gather over an owner-major staging
+    // buffer (stage[r][j] = the j-th column owned by rank r = column first(r) + j·world).
+    // `st` = the stream the collective runs on (the context's stream, or its comm stream for an overlapped exchange).
+    void allgather_columns_on(cudaStream_t st, Fr* base, size_t ncols, size_t len, size_t off) {
+        Nccl& nc = nccl();
+        if (ncols % ctx.world != 0 || st != ctx.stream) {
+            nc.check(nc.GroupStart(), "GroupStart");
+            for (size_t c = 0; c < ncols; ++c)
+                nc.check(nc.Broadcast(base + c * len, base + c * len, len * sizeof(Fr), 1, owner(c, off), nc.comm, st), "Broadcast");
+            nc.check(nc.GroupEnd(), "GroupEnd");
+            return;
+        }
         const size_t world = ctx.world, per = (ncols + world - 1) / world;
         auto first = [&](size_t r) { return (r + world - off % world) % world; };  // smallest column index owned by rank r
         DevBuf<Fr> stage(world * per * len, ctx.stream);
         for (size_t c = first(ctx.rank), j = 0; c < ncols; c += world, ++j)
             CUDA_CHECK(cudaMemcpyAsync(stage.get() + ((size_t)ctx.rank * per + j) * len, base + c * len, len * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx.stream));
-        all_gather_inplace(stage.get(), per * len);
+        nc.check(nc.AllGather(stage.get() + (size_t)ctx.rank * per * len, stage.get(), per * len * sizeof(Fr), 1, nc.comm, ctx.stream), "AllGather");
         for (size_t r = 0; r < world; ++r) {
             if (r == (size_t)ctx.rank) continue;
             for (size_t c = first(r), j = 0; c < ncols; c += world, ++j)
                 CUDA_CHECK(cudaMemcpyAsync(base + c * len, stage.get() + (r * per + j) * len, len * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx.stream));
         }
+    }
+    void allgather_columns(Fr* base, size_t ncols, size_t len, size_t off = 0) {
+        if (!on() || ncols == 0) return;
+        CommSpan span(ctx);
+        allgather_columns_on(ctx.stream, base, ncols, len, off);
+    }
+    // The same exchange on the context's comm stream: it starts once everything queued on the main stream so far is done and
+    // runs beside the kernels launched afterwards; the main stream must not touch the columns until async_wait(). Several
+    // async exchanges may be queued before one wait. (Traced calls run it synchronously so that the comm timing stays a
+    // bracketed span.)
+    void allgather_columns_async(Fr* base, size_t ncols, size_t len, size_t off = 0) {
+        if (!on() || ncols == 0) return;
+        if (ctx.comm_trace || !ctx.comm_stream) {
+            allgather_columns(base, ncols, len, off);
+            return;
+        }
+        CUDA_CHECK(cudaEventRecord(ctx.comm_fork, ctx.stream));
+        CUDA_CHECK(cudaStreamWaitEvent(ctx.comm_stream, ctx.comm_fork, 0));
+        allgather_columns_on(ctx.comm_stream, base, ncols, len, off);
+        ctx.comm_pending = true;
+    }
+    void async_wait() {
+        if (!ctx.comm_pending) return;
+        CUDA_CHECK(cudaEventRecord(ctx.comm_done, ctx.comm_stream));
+        CUDA_CHECK(cudaStreamWaitEvent(ctx.stream, ctx.comm_done, 0));
+        ctx.comm_pending = false;
     }
     // Row-slice exchange for the h(X) stage: column c (length en, complete on owner(c) only) is needed by rank d only on
     // the extended rows d evaluates plus the rotation halo — rows [d·R − before, (d+1)·R + after) mod en, R = en / world.

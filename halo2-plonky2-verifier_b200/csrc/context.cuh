@@ -82,6 +82,18 @@ struct Srs {
 typedef int (*AllGatherFn)(void* user, const void* send, size_t bytes, void* recv);
 
 
+// Upstream details that change proof BYTES and could not be checked against halo2-axiom's source in this container
+// (SURVEY.md §8c items 1–4). One switch each, mirrored bit for bit by the oracle (oracle/curve.hpp `Compat`); the defaults
+// are the classic PSE-halo2 behaviour. b200zk_set_compat flips them — the day the real source is consulted, a mismatch is
+// a flag flip, not a rewrite.
+struct Compat {
+    bool draw_unused_blinds = true;    // [1] create_proof draws the Blind(..) scalars that KZG commitments ignore
+    bool lookup_fill_from_end = true;  // [2] permute_expression_pair: ascending leftovers go to repeated rows popped from the END
+    uint32_t random_poly_chunks = 0;   // [3] vanishing::commit: 0 = n sequential draws; T = T worker chunks, each filled from its own
+                                       //     ChaCha20Rng whose 32-byte seed is drawn from the main stream
+    int point_sign_bit = 6;            // [4] y-sign flag bit of compressed G1 points (6 or 7; the identity flag takes the other)
+};
+
 constexpr int MSM_SLOTS = 4;  // MSM columns in flight per commit batch
 constexpr int STAGE_WORKERS = 6, STAGE_SLOTS = 2;  // pinned staging of pageable uploads (upload.cuh)
 
@@ -92,6 +104,9 @@ struct Context {
     cudaEvent_t msm_events[MSM_SLOTS] = {}, msm_join[MSM_SLOTS - 1] = {}, msm_fork = nullptr;
     cudaStream_t copy_stream = nullptr;    // witness upload overlapped with the first advice commitments (prover.cu)
     cudaEvent_t copy_fork = nullptr, copy_done = nullptr;
+    cudaStream_t comm_stream = nullptr;    // multi-GPU: collectives whose result is needed late overlap the kernels in between
+    cudaEvent_t comm_fork = nullptr, comm_done = nullptr;
+    bool comm_pending = false;
     uint8_t* stage_buf = nullptr;          // pinned staging slots for pageable host buffers, allocated on first use
     cudaEvent_t stage_ev[STAGE_WORKERS * STAGE_SLOTS] = {};
     uint32_t* pinned_u32 = nullptr;        // pinned words for the entry-count read-backs (one per slot)
@@ -118,6 +133,7 @@ struct Context {
     std::shared_ptr<struct Nccl> nccl;  // collectives.cuh: created on first use from the bootstrap callback (one process per
                                         // GPU), or installed by b200zk_create_multi (one process, one thread per GPU)
     // this context is one rank of a multi-GPU job
+    Compat compat;
     bool solo = false;  // set around calls that must run on this GPU alone although the context belongs to a device group
     bool sharded() const { return !solo && world > 1 && (allgather != nullptr || nccl != nullptr); }
 

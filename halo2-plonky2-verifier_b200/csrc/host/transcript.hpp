@@ -100,23 +100,24 @@ inline void field_to_bytes(const Field<C>& a, uint8_t out[32]) {
     Field<C> c = f_from_mont(a);
     memcpy(out, c.l, 32);
 }
-// halo2curves G1Affine::to_bytes: x LE, bit 6 of byte 31 = y odd, bit 7 = identity
-inline void g1_to_bytes(const G1Affine& p, uint8_t out[32]) {
+// halo2curves G1Affine::to_bytes: x LE, bit `sign_bit` (6 by default, [UNVERIFIED-4]) of byte 31 = y odd, the other of
+// bits 6/7 = identity
+inline void g1_to_bytes(const G1Affine& p, uint8_t out[32], int sign_bit = 6) {
     if (g1_is_identity(p)) {
         memset(out, 0, 32);
-        out[31] |= 0x80;
+        out[31] |= (uint8_t)(1u << (sign_bit == 6 ? 7 : 6));
         return;
     }
     field_to_bytes(p.x, out);
     uint8_t yb[32];
     field_to_bytes(p.y, yb);
-    out[31] |= (uint8_t)((yb[0] & 1) << 6);
+    out[31] |= (uint8_t)((yb[0] & 1) << sign_bit);
 }
 
 // Blake2bWrite<Vec<u8>, G1Affine, Challenge255<G1Affine>>
 class Transcript {
    public:
-    Transcript() : hash_("Halo2-Transcript") {}
+    explicit Transcript(int point_sign_bit = 6) : hash_("Halo2-Transcript"), sign_bit_(point_sign_bit) {}
     void common_point(const G1Affine& p) {
         if (g1_is_identity(p)) throw std::runtime_error("transcript: cannot absorb the point at infinity");
         uint8_t b[65];
@@ -143,7 +144,7 @@ class Transcript {
     void write_point(const G1Affine& p) {
         common_point(p);
         uint8_t b[32];
-        g1_to_bytes(p, b);
+        g1_to_bytes(p, b, sign_bit_);
         proof.insert(proof.end(), b, b + 32);
     }
     void write_scalar(const Fr& s) {
@@ -156,15 +157,20 @@ class Transcript {
 
    private:
     Blake2b512 hash_;
+    int sign_bit_;
 };
 
-// rand_chacha BlockRng stream seen as a sequence of Fr::random draws: draw j = from_u512(block j).
-// (Every consumer on this path draws whole field elements — 16 words = one block — so the stream stays block aligned.)
+// rand_chacha BlockRng keystream: block j (16 words) = ChaCha(key, counter j). Fr::random takes 16 consecutive words
+// (from_u512). `pos` is the position in 32-bit words; as long as only whole field elements are drawn it stays block
+// aligned and draw j = from_u512(block j) — which is what the device-side generator (poly.cu fr_random_stream) relies on.
+// fill_bytes (used only by the chunk-seeded random polynomial variant, [UNVERIFIED-3]) may leave it half a block off.
 class FrRandomStream {
    public:
     uint32_t key[8];
     int rounds;
-    uint64_t draws = 0;
+    uint64_t pos = 0;
+    bool aligned() const { return pos % 16 == 0; }
+    uint64_t block_index() const { return pos / 16; }
 
     static FrRandomStream std_rng_seed_from_u64(uint64_t state) {  // StdRng = ChaCha12, PCG32-expanded seed
         FrRandomStream r;
@@ -182,9 +188,9 @@ class FrRandomStream {
         memcpy(r.key, seed, 32);
         return r;
     }
-    Fr next() {
+    void block(uint64_t counter, uint32_t out[16]) const {
         uint32_t in[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key[0], key[1], key[2], key[3],
-                           key[4], key[5], key[6], key[7], (uint32_t)draws, (uint32_t)(draws >> 32), 0u, 0u};
+                           key[4], key[5], key[6], key[7], (uint32_t)counter, (uint32_t)(counter >> 32), 0u, 0u};
         uint32_t x[16];
         memcpy(x, in, 64);
         auto rl = [](uint32_t v, int n) { return (v << n) | (v >> (32 - n)); };
@@ -198,11 +204,31 @@ class FrRandomStream {
             qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15);
             qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14);
         }
-        for (int i = 0; i < 16; ++i) x[i] += in[i];
-        ++draws;
-        return f_from_u512<FrCfg>(x);
+        for (int i = 0; i < 16; ++i) out[i] = x[i] + in[i];
     }
-    void skip(uint64_t n) { draws += n; }
+    // the next `count` keystream words
+    void words(uint32_t* out, size_t count) {
+        uint32_t blk[16];
+        uint64_t have = ~0ull;
+        for (size_t i = 0; i < count; ++i, ++pos) {
+            if (pos / 16 != have) {
+                have = pos / 16;
+                block(have, blk);
+            }
+            out[i] = blk[pos % 16];
+        }
+    }
+    Fr next() {
+        uint32_t w[16];
+        words(w, 16);
+        return f_from_u512<FrCfg>(w);
+    }
+    void fill_bytes32(uint8_t out[32]) {  // RngCore::fill_bytes of 32 bytes: eight whole words off the stream
+        uint32_t w[8];
+        words(w, 8);
+        memcpy(out, w, 32);
+    }
+    void skip(uint64_t n) { pos += 16 * n; }
 };
 
 }  // namespace host

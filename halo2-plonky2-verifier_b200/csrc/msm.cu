@@ -64,11 +64,13 @@ MsmConfig msm_config_merged(uint32_t c, size_t table_n) {
     m.table_n = table_n;
     return m;
 }
-// measured at S20-bn / S22-bn: the msm stage is flat for caps 17..21 (fewer buckets trade against more windows) and
-// worse below 16; 20 keeps the table smallest
+// measured at S20-bn / S22-bn on one GPU: the msm stage is flat for caps 17..21 (fewer buckets trade against more windows)
+// and worse below 16; 20 keeps the table smallest. On 4 and more GPUs the accumulation of a column shrinks with the rank
+// count but its bucket reduction does not (every rank reduces a full bucket set for each column it touches), so two bits
+// fewer pay: S20-bn on 8 GPUs 47.4 ms (c=20) -> 43.7 ms (c=18), 44.1 ms at c=16 (profiles/bench_r02_8gpu_c*.json).
 uint32_t msm_table_window_bits(uint32_t k, int world) {
     uint32_t c = k < 8 ? 8 : (k > 20 ? 20 : k);
-    (void)world;
+    if (world >= 4 && c >= 12) c = std::min<uint32_t>(c, k >= 2 ? k - 2 : c);
     if (const char* e = getenv("B200ZK_TABLE_BITS")) {  // experiments: window bits of the precomputed tables
         const int v = atoi(e);
         if (v >= 8 && v <= 22) c = (uint32_t)v;

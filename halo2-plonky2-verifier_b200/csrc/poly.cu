@@ -399,7 +399,7 @@ DEV uint32_t upper_idx(const uint32_t* starts, uint32_t n, uint32_t p) {  // lar
     return lo;
 }
 __global__ void lp_write_kernel(const uint32_t* start_in, const uint32_t* dist_excl, const uint32_t* left_start, uint32_t n, size_t usable,
-                                uint32_t R, Fr* a_out, Fr* s_out) {
+                                uint32_t R, Fr* a_out, Fr* s_out, int fill_from_end) {
     size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= usable) return;
     const uint32_t v = upper_idx(start_in, n, (uint32_t)row);  // start_in[v] <= row < start_in[v+1] (runs are non-empty)
@@ -412,14 +412,14 @@ __global__ void lp_write_kernel(const uint32_t* start_in, const uint32_t* dist_e
     } else {
         const uint32_t d_incl = dist_excl[v] + 1;                 // distinct values <= v
         const uint32_t idx = (uint32_t)row - d_incl;              // rank among repeated rows (ascending)
-        const uint32_t j = R - 1 - idx;                           // leftover number j (ascending)
+        const uint32_t j = fill_from_end ? R - 1 - idx : idx;     // leftover number j (ascending) [UNVERIFIED-2]
         const uint32_t t = upper_idx(left_start, n, j);
         Fr ft = f_zero<FrCfg>();
         ft.l[0] = t;
         f_store(s_out + row, f_to_mont(ft));
     }
 }
-int lookup_permute(Context& ctx, const Fr* input, const Fr* table, Fr* a_out, Fr* s_out, size_t n, size_t usable) {
+int lookup_permute(Context& ctx, const Fr* input, const Fr* table, Fr* a_out, Fr* s_out, size_t n, size_t usable, bool fill_from_end) {
     cudaStream_t s = ctx.stream;
     const uint32_t N = (uint32_t)n;
     DevBuf<uint32_t> hist_in(N + 1, s), hist_tab(N + 1, s), distinct(N + 1, s), left(N + 1, s), err(1, s);
@@ -441,7 +441,7 @@ int lookup_permute(Context& ctx, const Fr* input, const Fr* table, Fr* a_out, Fr
     if (h[0] != 0) return (int)h[0];
     // start_in has empty runs (equal consecutive starts); upper_idx picks the last value whose start <= row, which is
     // the non-empty run containing the row. left_start likewise.
-    lp_write_kernel<<<nblocks(usable, 256), 256, 0, s>>>(hist_in.get(), distinct.get(), left.get(), N, usable, h[1], a_out, s_out);
+    lp_write_kernel<<<nblocks(usable, 256), 256, 0, s>>>(hist_in.get(), distinct.get(), left.get(), N, usable, h[1], a_out, s_out, fill_from_end ? 1 : 0);
     LAUNCHED(1);
     return 0;
 }

@@ -40,7 +40,8 @@ void lookup_numerator(Fr* p, const Fr* in, const Fr* tab, const Fr& beta, const 
 // statement about the witness); LOOKUP_NOT_IN_TABLE — an input value is missing from the table (halo2's
 // ConstraintSystemFailure; an input >= n is missing from any supported table).
 constexpr int LOOKUP_UNSUPPORTED = 1, LOOKUP_NOT_IN_TABLE = 2;
-int lookup_permute(Context& ctx, const Fr* input, const Fr* table, Fr* a_out, Fr* s_out, size_t n, size_t usable);
+// fill_from_end: ascending leftovers go to the repeated rows popped from the end (classic rule) or, false, in ascending order
+int lookup_permute(Context& ctx, const Fr* input, const Fr* table, Fr* a_out, Fr* s_out, size_t n, size_t usable, bool fill_from_end = true);
 
 // ---- Fr::random stream: element j of a rand_chacha BlockRng stream = from_u512 of ChaCha block (counter0 + j) ---------
 void fr_random_stream(Fr* out, size_t n, const uint32_t key[8], uint64_t counter0, int rounds, cudaStream_t s);

@@ -407,8 +407,22 @@ void evaluate_h(Context& ctx, const ProvingKeyDev& pk, const Fr* advice_coeff, c
     CUDA_CHECK(cudaStreamSynchronize(s));
 }
 
+static std::vector<uint8_t> create_proof_body(Context& ctx, const ProvingKeyDev& pk, const Fr* advice_in, bool advice_on_device,
+                                              host::FrRandomStream& rng, ProofTimings* tm);
 std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const Fr* advice_in, bool advice_on_device, host::FrRandomStream& rng,
                                   ProofTimings* tm) {
+    try {
+        return create_proof_body(ctx, pk, advice_in, advice_on_device, rng, tm);
+    } catch (...) {
+        // the transient columns have gone back to the arena (bookkeeping only): an exchange still running on the comm stream
+        // must drain before the next call can hand that memory out again
+        if (ctx.comm_stream) cudaStreamSynchronize(ctx.comm_stream);
+        ctx.comm_pending = false;
+        throw;
+    }
+}
+static std::vector<uint8_t> create_proof_body(Context& ctx, const ProvingKeyDev& pk, const Fr* advice_in, bool advice_on_device,
+                                              host::FrRandomStream& rng, ProofTimings* tm) {
     const Shape& sh = pk.shape;
     need_srs(ctx, sh.k);
     cudaStream_t s = ctx.stream;
@@ -416,7 +430,11 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
     const uint32_t bf = Shape::blinding_factors, NA = sh.num_advice(), A = sh.A, L = sh.L, F = sh.F, P = sh.num_perm(), NS = sh.num_sets();
     const Domain& dom = ctx.domain(sh.k);
     const TwiddleTable& tw = ctx.std_table(sh.k + 2);
-    host::Transcript tr;
+    host::Transcript tr(ctx.compat.point_sign_bit);
+    // [UNVERIFIED-1] Blind(..) scalars: drawn upstream (the stream advances) but unused by KZG commitments
+    auto skip_unused_blinds = [&](uint64_t count) {
+        if (ctx.compat.draw_unused_blinds) rng.skip(count);
+    };
     const double exchange0 = ctx.exchange_seconds;
     struct TraceGuard {  // collectives are traced only while a timed call is running
         Context& c;
@@ -446,7 +464,7 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
     DevBuf<Fr> advice((size_t)NA * n, s);
     std::vector<Fr> blind((size_t)NA * (bf + 1));
     for (auto& b : blind) b = rng.next();
-    rng.skip(NA);  // Blind(..) per column: drawn upstream, unused by KZG commitments
+    skip_unused_blinds(NA);  // Blind(..) per advice column
     // the copy stream must be idle before `advice` can go back to the arena, whichever way this function is left
     struct CopyJoin {
         cudaStream_t st;
@@ -520,9 +538,9 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
         Fr* s_out = perm_cols.get() + (size_t)(2 * l + 1) * n;
         std::vector<Fr> blind(2 * (bf + 1));
         for (auto& b : blind) b = rng.next();
-        rng.skip(2);  // the two Blind(..) draws of commit_values
+        skip_unused_blinds(2);  // the two Blind(..) draws of commit_values
         if (!shard.mine(l)) continue;
-        if (const int st = lookup_permute(ctx, advice.get() + (size_t)(A + l) * n, table_values, a_out, s_out, n, u)) {
+        if (const int st = lookup_permute(ctx, advice.get() + (size_t)(A + l) * n, table_values, a_out, s_out, n, u, ctx.compat.lookup_fill_from_end)) {
             lookup_failed |= (uint32_t)st;
             continue;
         }
@@ -604,7 +622,7 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
         for (uint32_t set = 0; set < NS; ++set) {
             Fr* z = z_polys.get() + (size_t)set * n;
             for (uint32_t i = 0; i < bf; ++i) blind[(size_t)set * bf + i] = rng.next();  // every rank draws every value: the streams stay in step
-            rng.skip(1);
+            skip_unused_blinds(1);
             if (builds(set)) {
                 if (set > 0) fr_scale(z, carry, n, s);
                 CUDA_CHECK(cudaMemcpyAsync(z + (n - bf), blind.data() + (size_t)set * bf, bf * sizeof(Fr), cudaMemcpyHostToDevice, s));
@@ -622,7 +640,7 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
         std::vector<uint32_t> my_lookups;
         for (uint32_t l = 0; l < L; ++l) {
             for (uint32_t i = 0; i < bf; ++i) blind[(size_t)l * bf + i] = rng.next();
-            rng.skip(1);
+            skip_unused_blinds(1);
             if (shard.mine(l)) my_lookups.push_back(l);
         }
         DevBuf<Fr> p(my_lookups.size() * n, s);
@@ -644,9 +662,24 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
     }
     // step 7: vanishing::commit (D.7): n sequential Fr::random draws = n consecutive ChaCha blocks, generated in place
     DevBuf<Fr> random_poly(n, s);
-    fr_random_stream(random_poly.get(), n, rng.key, rng.draws, rng.rounds, s);
-    rng.skip(n);
-    rng.skip(1);
+    if (ctx.compat.random_poly_chunks == 0) {  // [UNVERIFIED-3] n sequential draws = n consecutive blocks of the main stream
+        if (!rng.aligned()) throw std::logic_error("create_proof: random stream not block aligned");
+        fr_random_stream(random_poly.get(), n, rng.key, rng.block_index(), rng.rounds, s);
+        rng.skip(n);
+    } else {  // one ChaCha20Rng per worker chunk, seeded from the main stream (T chunks of n / T, plus one for a remainder)
+        const size_t T = std::min<size_t>(ctx.compat.random_poly_chunks, n), chunk = n / T, n_chunks = T + (n % T != 0 ? 1 : 0);
+        std::vector<host::FrRandomStream> seeds;
+        for (size_t c = 0; c < n_chunks; ++c) {
+            uint8_t seed[32];
+            rng.fill_bytes32(seed);
+            seeds.push_back(host::FrRandomStream::chacha20_from_seed(seed));
+        }
+        for (size_t c = 0; c < n_chunks; ++c) {
+            const size_t lo = c * chunk, hi = std::min(n, (c + 1) * chunk);
+            fr_random_stream(random_poly.get() + lo, hi - lo, seeds[c].key, 0, seeds[c].rounds, s);
+        }
+    }
+    skip_unused_blinds(1);
     lap(tm ? &tm->other : nullptr);
     // The permutation products, the lookup products (Lagrange basis) and the random polynomial (coefficient basis) are
     // written to the transcript back to back with no challenge in between: ONE commit batch, one bucket reduction. Sharded,
@@ -676,7 +709,7 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
                 dev_lagrange_to_coeff(ctx, sh.k, z_polys.get() + (size_t)set * n);
                 dev_coeff_to_extended(ctx, sh.k, z_polys.get() + (size_t)set * n, z_cosets.get() + (size_t)set * en);
             }
-        shard.allgather_columns(z_polys.get(), NS, n);
+        shard.allgather_columns_async(z_polys.get(), NS, n);  // coefficient forms are first read by the evaluations at x
         std::vector<Fr*> cs(NS);
         for (uint32_t set = 0; set < NS; ++set) cs[set] = z_cosets.get() + (size_t)set * en;
         shard.exchange_row_slices(cs.data(), NS, [&](size_t c) { return shard.owner(c); }, en, HALO_BEFORE, HALO_AFTER);
@@ -696,7 +729,7 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
                 dev_lagrange_to_coeff(ctx, sh.k, advice_polys.get() + (size_t)c * n);
                 dev_coeff_to_extended(ctx, sh.k, advice_polys.get() + (size_t)c * n, advice_cosets.get() + (size_t)c * en);
             }
-        shard.allgather_columns(advice_polys.get(), NA, n, OFF_ADVICE_NTT);
+        shard.allgather_columns_async(advice_polys.get(), NA, n, OFF_ADVICE_NTT);
         std::vector<Fr*> cs(NA);
         for (uint32_t c = 0; c < NA; ++c) cs[c] = advice_cosets.get() + (size_t)c * en;
         shard.exchange_row_slices(cs.data(), NA, [&](size_t c) { return shard.owner(c, OFF_ADVICE_NTT); }, en, HALO_BEFORE, HALO_AFTER);
@@ -710,11 +743,12 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
     dev_extended_to_coeff(ctx, sh.k, h.get(), h_coeff.get());
     h.release();
     lap(tm ? &tm->ntt : nullptr);
-    rng.skip(3);
+    skip_unused_blinds(3);
     for (const G1Affine& cm : commit_batch(ctx, 0, h_coeff.get(), n, 3, n)) tr.write_point(cm);
     lap(tm ? &tm->msm : nullptr);
     const Fr x = tr.squeeze_challenge();
     const Fr xn = f_pow_u64(x, n);
+    shard.async_wait();  // the overlapped all-gathers of the z and advice coefficient forms
     // step 11: evaluations (D.10)
     const Fr x_next = dom.rotate_omega(x, 1), x_prev = dom.rotate_omega(x, -1), x_last = dom.rotate_omega(x, -(int)(bf + 1));
     const Fr x_rot2 = dom.rotate_omega(x, 2), x_rot3 = dom.rotate_omega(x, 3);

@@ -73,6 +73,18 @@ B200ZK_API unsigned long long b200zk_launch_count(void);
  * MPI all-gather) and return 0. All ranks must issue the same MSM calls in the same order. world = 1 disables it. */
 typedef int (*b200zk_allgather_fn)(void* user, const void* send, size_t bytes, void* recv);
 B200ZK_API int b200zk_set_allgather(b200zk_ctx* ctx, int rank, int world, b200zk_allgather_fn fn, void* user);
+/* Upstream details that change proof BYTES and that could not be checked against halo2-axiom's source (no Rust sources in
+ * the build image; SURVEY.md §8c items 1–4). Each is one switch, mirrored by the CPU oracle; 0 / 0 = the defaults (classic
+ * PSE-halo2 behaviour). If a proof ever differs from the Rust prover's, flipping a bit here is the fix:
+ *   NO_UNUSED_BLIND_DRAWS : create_proof does not draw the `Blind` scalars that KZG commitments ignore (default: it does)
+ *   LOOKUP_FILL_ASCENDING : permute_expression_pair assigns the ascending leftover table values to the repeated rows in
+ *                           ascending order (default: to the repeated rows popped from the end)
+ *   POINT_SIGN_BIT7       : compressed G1 points carry the y-sign in bit 7 and the identity flag in bit 6 (default: 6 / 7)
+ *   random_poly_chunks    : vanishing::commit's random polynomial: 0 = n sequential Fr::random draws (default); T > 0 = T
+ *                           worker chunks of n / T (plus one for a remainder), each filled from its own ChaCha20Rng whose
+ *                           32-byte seed is drawn from the caller's stream (upstream's thread-count-dependent variant) */
+enum { B200ZK_COMPAT_NO_UNUSED_BLIND_DRAWS = 1, B200ZK_COMPAT_LOOKUP_FILL_ASCENDING = 2, B200ZK_COMPAT_POINT_SIGN_BIT7 = 4 };
+B200ZK_API int b200zk_set_compat(b200zk_ctx* ctx, uint32_t flags, uint32_t random_poly_chunks);
 /* Precomputed window tables 2^(c·w)·P_i for the SRS bases (one bucket set per MSM, no host fold; costs W× SRS memory).
  * On by default; switch off before loading a large SRS to save memory. */
 B200ZK_API int b200zk_set_msm_tables(b200zk_ctx* ctx, int on);

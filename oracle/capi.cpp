@@ -14,6 +14,15 @@ static std::string g_err;
 EXPORT const char* oracle_last_error() { return g_err.c_str(); }
 EXPORT void oracle_set_threads(int n) { num_threads_ref() = n > 0 ? n : (int)std::max(1u, std::thread::hardware_concurrency()); }
 EXPORT int oracle_get_threads() { return num_threads(); }
+// the [UNVERIFIED-1..4] switches (curve.hpp `Compat`): bit 0 = do NOT draw unused Blind scalars, bit 1 = ascending lookup
+// fill, bit 2 = y-sign flag in bit 7; random_poly_chunks as in Compat. (0, 0) restores the defaults.
+EXPORT void oracle_set_compat(uint32_t flags, uint32_t random_poly_chunks) {
+    Compat& c = compat();
+    c.draw_unused_blinds = !(flags & 1u);
+    c.lookup_fill_from_end = !(flags & 2u);
+    c.point_sign_bit = (flags & 4u) ? 7 : 6;
+    c.random_poly_chunks = random_poly_chunks;
+}
 
 // ---- fields (which: 0 = Fr, 1 = Fq); all elements are 4×u64 Montgomery limbs ------------------------
 template <class F>

@@ -6,6 +6,22 @@
 
 namespace oracle {
 
+// Upstream details that change proof BYTES and could not be checked against halo2-axiom's source in this container
+// (SURVEY.md §8c items 1–4). One switch each, mirrored bit for bit by the product (csrc/context.cuh `Compat`,
+// b200zk_set_compat); the defaults are the classic PSE-halo2 behaviour. Set through oracle_set_compat.
+struct Compat {
+    bool draw_unused_blinds = true;    // [1] create_proof draws the Blind(..) scalars that KZG commitments ignore
+    bool lookup_fill_from_end = true;  // [2] permute_expression_pair: ascending leftovers go to repeated rows popped from the END
+    uint32_t random_poly_chunks = 0;   // [3] vanishing::commit: 0 = n sequential draws; T = T worker chunks, each filled from its own
+                                       //     ChaCha20Rng whose 32-byte seed is drawn from the main stream (thread-count dependent upstream)
+    int point_sign_bit = 6;            // [4] y-sign flag bit of compressed G1 points (6 or 7)
+};
+inline Compat& compat() {
+    static Compat c;
+    return c;
+}
+
+
 struct G1Affine {
     Fq x, y;  // identity is (0,0) — halo2curves convention
     static G1Affine identity() { return G1Affine{Fq::zero(), Fq::zero()}; }
@@ -20,22 +36,26 @@ struct G1Affine {
 
     // GroupEncoding of halo2curves' `new_curve_impl!` (32 bytes: LE x, bit 6 of byte 31 = y is odd,
     // bit 7 of byte 31 = identity). SURVEY.md §8c unverified item 4 — isolated here.
+    // [UNVERIFIED-4] flag bits of the 32-byte compressed form: y-sign in bit compat().point_sign_bit (6 by default) of
+    // byte 31, identity flag in the other of bits 6/7
     void to_bytes(uint8_t out[32]) const {
+        const int sb = compat().point_sign_bit, ib = sb == 6 ? 7 : 6;
         if (is_identity()) {
             memset(out, 0, 32);
-            out[31] |= 0x80;
+            out[31] |= (uint8_t)(1u << ib);
             return;
         }
         x.to_bytes(out);
         uint8_t yb[32];
         y.to_bytes(yb);
-        out[31] |= (yb[0] & 1) << 6;
+        out[31] |= (uint8_t)((yb[0] & 1) << sb);
     }
     static bool from_bytes(const uint8_t in[32], G1Affine& out) {
+        const int sb = compat().point_sign_bit, ib = sb == 6 ? 7 : 6;
         uint8_t tmp[32];
         memcpy(tmp, in, 32);
-        bool is_inf = tmp[31] >> 7;
-        int ysign = (tmp[31] >> 6) & 1;
+        bool is_inf = (tmp[31] >> ib) & 1;
+        int ysign = (tmp[31] >> sb) & 1;
         tmp[31] &= 0x3f;
         Fq x;
         if (!Fq::from_bytes(tmp, x)) return false;

@@ -248,12 +248,18 @@ inline bool permute_expression_pair(const Shape& sh, const Poly& input, const Po
             repeated.push_back(row);
         }
     }
+    if (compat().lookup_fill_from_end) {
+        for (auto& kv : leftover)
+            for (uint32_t c = 0; c < kv.second.second; ++c) {
+                s_out[repeated.back()] = kv.second.first;
+                repeated.pop_back();
+            }
+        return repeated.empty();
+    }
+    size_t next = 0;  // the other fill order: the i-th repeated row (ascending) takes the i-th leftover (ascending)
     for (auto& kv : leftover)
-        for (uint32_t c = 0; c < kv.second.second; ++c) {
-            s_out[repeated.back()] = kv.second.first;
-            repeated.pop_back();
-        }
-    return repeated.empty();
+        for (uint32_t c = 0; c < kv.second.second; ++c) s_out[repeated[next++]] = kv.second.first;
+    return next == repeated.size();
 }
 
 inline Fr evaluate_vanishing_polynomial(const std::vector<Fr>& roots, const Fr& z) {
@@ -467,7 +473,10 @@ inline std::vector<uint8_t> create_proof(const Params& params, const ProvingKey&
     // step 1: blind + commit advice (D.3)
     for (uint32_t c = 0; c < NA; ++c)
         for (size_t r = u; r < n; ++r) advice[c][r] = rng.random_fr();
-    for (uint32_t c = 0; c < NA; ++c) (void)rng.random_fr();  // Blind(..) per column; unused by KZG
+    auto unused_blind = [&]() {  // [UNVERIFIED-1] Blind(..) scalars: drawn (the stream advances) but unused by KZG commitments
+        if (compat().draw_unused_blinds) (void)rng.random_fr();
+    };
+    for (uint32_t c = 0; c < NA; ++c) unused_blind();  // Blind(..) per column
     {
         std::vector<G1> cm(NA);
         for (uint32_t c = 0; c < NA; ++c) cm[c] = params.commit_lagrange(advice[c]);
@@ -485,10 +494,10 @@ inline std::vector<uint8_t> create_proof(const Params& params, const ProvingKey&
         for (uint32_t i = 0; i <= bf; ++i) perm_in[l].push_back(rng.random_fr());
         for (uint32_t i = 0; i <= bf; ++i) perm_tab[l].push_back(rng.random_fr());
         perm_in_poly[l] = dom.lagrange_to_coeff(perm_in[l]);
-        (void)rng.random_fr();
+        unused_blind();
         G1 ca = params.commit_lagrange(perm_in[l]);
         perm_tab_poly[l] = dom.lagrange_to_coeff(perm_tab[l]);
-        (void)rng.random_fr();
+        unused_blind();
         G1 cs = params.commit_lagrange(perm_tab[l]);
         tr.write_point(ca.to_affine());
         tr.write_point(cs.to_affine());
@@ -529,7 +538,7 @@ inline std::vector<uint8_t> create_proof(const Params& params, const ProvingKey&
             for (size_t r = 1; r < n; ++r) z[r] = z[r - 1] * m[r - 1];
             for (size_t r = n - bf; r < n; ++r) z[r] = rng.random_fr();
             last_z = z[n - (bf + 1)];
-            (void)rng.random_fr();
+            unused_blind();
             G1 cm = params.commit_lagrange(z);
             Poly zp = dom.lagrange_to_coeff(z);
             z_cosets.push_back(dom.coeff_to_extended(zp));
@@ -556,15 +565,27 @@ inline std::vector<uint8_t> create_proof(const Params& params, const ProvingKey&
         z[0] = Fr::one();
         for (size_t r = 1; r < n - bf; ++r) z[r] = z[r - 1] * p[r - 1];
         for (size_t r = n - bf; r < n; ++r) z[r] = rng.random_fr();
-        (void)rng.random_fr();
+        unused_blind();
         G1 cm = params.commit_lagrange(z);
         lk_z_poly[l] = dom.lagrange_to_coeff(z);
         tr.write_point(cm.to_affine());
     }
     // step 7: vanishing::commit (D.7) [UNVERIFIED-3: sequential draws]
     Poly random_poly(n);
-    for (size_t i = 0; i < n; ++i) random_poly[i] = rng.random_fr();
-    (void)rng.random_fr();
+    if (compat().random_poly_chunks == 0) {
+        for (size_t i = 0; i < n; ++i) random_poly[i] = rng.random_fr();
+    } else {  // one ChaCha20Rng per worker chunk, seeded from the main stream (T chunks of n / T, plus one for a remainder)
+        const size_t T = std::min<size_t>(compat().random_poly_chunks, n), chunk = n / T, n_chunks = T + (n % T != 0 ? 1 : 0);
+        std::vector<ChaChaRng> seeds;
+        for (size_t c = 0; c < n_chunks; ++c) {
+            uint8_t seed[32];
+            rng.fill_bytes(seed, 32);
+            seeds.push_back(ChaChaRng::chacha20_from_seed(seed));
+        }
+        for (size_t c = 0; c < n_chunks; ++c)
+            for (size_t i = c * chunk; i < std::min(n, (c + 1) * chunk); ++i) random_poly[i] = seeds[c].random_fr();
+    }
+    unused_blind();
     tr.write_point(params.commit(random_poly).to_affine());
     ch.y = tr.squeeze_challenge();
     // step 8/9: advice polys, cosets, evaluate_h (D.8)
@@ -577,7 +598,7 @@ inline std::vector<uint8_t> create_proof(const Params& params, const ProvingKey&
     Poly h_coeff = dom.extended_to_coeff(std::move(h));
     std::vector<Poly> h_pieces;
     for (uint32_t j = 0; j < dom.quotient_poly_degree; ++j) h_pieces.emplace_back(h_coeff.begin() + j * n, h_coeff.begin() + (j + 1) * n);
-    for (uint32_t j = 0; j < dom.quotient_poly_degree; ++j) (void)rng.random_fr();
+    for (uint32_t j = 0; j < dom.quotient_poly_degree; ++j) unused_blind();
     {
         std::vector<G1> cm;
         for (auto& p : h_pieces) cm.push_back(params.commit(p));

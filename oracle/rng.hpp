@@ -85,6 +85,12 @@ struct ChaChaRng {
             return (hi << 32) | lo;
         }
     }
+    void fill_bytes(uint8_t* out, size_t nbytes) {  // BlockRng::fill_bytes: whole words off the stream
+        for (size_t i = 0; i < nbytes; i += 4) {
+            const uint32_t w = next_u32();
+            memcpy(out + i, &w, nbytes - i < 4 ? nbytes - i : 4);
+        }
+    }
     Fr random_fr() {
         u64 w[8];
         for (int i = 0; i < 8; ++i) w[i] = next_u64();

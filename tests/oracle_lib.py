@@ -181,6 +181,12 @@ def eval_polynomial(poly, point):
     return out
 
 
+def set_compat(flags=0, random_poly_chunks=0):
+    """The [UNVERIFIED-1..4] switches of SURVEY.md §8c on the oracle side (oracle/curve.hpp `Compat`): same bits as
+    b200zk_set_compat. Global to the oracle library; tests reset it to (0, 0)."""
+    lib().oracle_set_compat(ctypes.c_uint32(flags), ctypes.c_uint32(random_poly_chunks))
+
+
 class Params:
     """ParamsKZG<Bn256> (oracle side). `setup(k)` mirrors halo2-base gen_srs: ChaCha20Rng::from_seed([0;32])."""
 

@@ -129,6 +129,9 @@ int b200zk_create(int device, b200zk_ctx** out) {
     cudaEventCreateWithFlags(&ctx->c.copy_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->c.copy_done, cudaEventDisableTiming);
     if (cudaStreamCreateWithFlags(&ctx->c.comm_stream, cudaStreamNonBlocking) != cudaSuccess) ctx->c.comm_stream = nullptr;
+    if (cudaStreamCreateWithFlags(&ctx->c.ntt_stream, cudaStreamNonBlocking) != cudaSuccess) ctx->c.ntt_stream = nullptr;
+    cudaEventCreateWithFlags(&ctx->c.ntt_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->c.ntt_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->c.comm_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->c.comm_done, cudaEventDisableTiming);
     if (cudaHostAlloc((void**)&ctx->c.pinned_u32, 64, cudaHostAllocDefault) != cudaSuccess) {
@@ -256,6 +259,13 @@ int b200zk_destroy(b200zk_ctx* ctx) {
         cudaStreamSynchronize(ctx->c.comm_stream);
         cudaStreamDestroy(ctx->c.comm_stream);
     }
+    if (ctx->c.ntt_stream) {
+        cudaStreamSynchronize(ctx->c.ntt_stream);
+        ctx->c.side_scratch.release();
+        cudaStreamDestroy(ctx->c.ntt_stream);
+    }
+    if (ctx->c.ntt_fork) cudaEventDestroy(ctx->c.ntt_fork);
+    if (ctx->c.ntt_done) cudaEventDestroy(ctx->c.ntt_done);
     if (ctx->c.comm_fork) cudaEventDestroy(ctx->c.comm_fork);
     if (ctx->c.comm_done) cudaEventDestroy(ctx->c.comm_done);
     if (ctx->c.copy_fork) cudaEventDestroy(ctx->c.copy_fork);
@@ -914,6 +924,7 @@ int b200zk_host_selftest(uint64_t seed, size_t iters) {
         if (!f_eq(f_mul_chains(a, b), f_mul_host64(a, b))) return -10;                       // the multipliers agree
         if (!f_eq(f_mul_comba(a, b), f_mul_host64(a, b))) return -16;
         if (!f_eq(f_sqr_comba(a), f_mul_host64(a, a))) return -17;
+        if (!f_eq(f_mul2_add(a, b, c, a), f_add(f_mul_host64(a, b), f_mul_host64(c, a)))) return -19;  // fused dual product
         if (!f_eq(f_mul(a, f_add(b, c)), f_add(f_mul(a, b), f_mul(a, c)))) return -11;       // distributivity
         if (!f_eq(f_sub(f_add(a, b), b), a)) return -12;
         if (!f_is_zero(a) && !f_eq(f_mul(a, f_inv(a)), f_one<FrCfg>())) return -13;

@@ -104,6 +104,12 @@ struct Context {
     cudaEvent_t msm_events[MSM_SLOTS] = {}, msm_join[MSM_SLOTS - 1] = {}, msm_fork = nullptr;
     cudaStream_t copy_stream = nullptr;    // witness upload overlapped with the first advice commitments (prover.cu)
     cudaEvent_t copy_fork = nullptr, copy_done = nullptr;
+    // transforms that do not depend on the transcript (the advice columns' lagrange_to_coeff / coeff_to_extended) run on this
+    // stream beside the commit batches: the MSM kernels leave ≈ 20 % of the multiplier pipe idle (latency-bound phases), which
+    // the NTT kernels fill (prover.cu)
+    cudaStream_t ntt_stream = nullptr;
+    cudaEvent_t ntt_fork = nullptr, ntt_done = nullptr;
+    DevBuf<Fr> side_scratch;
     cudaStream_t comm_stream = nullptr;    // multi-GPU: collectives whose result is needed late overlap the kernels in between
     cudaEvent_t comm_fork = nullptr, comm_done = nullptr;
     bool comm_pending = false;
@@ -157,6 +163,13 @@ struct Context {
         }
         return scratch.get();
     }
+    Fr* get_side_scratch(size_t n) {  // scratch of the transforms on ntt_stream
+        if (side_scratch.size() < n) {
+            CUDA_CHECK(cudaStreamSynchronize(ntt_stream));
+            side_scratch.alloc_persistent(n, ntt_stream);
+        }
+        return side_scratch.get();
+    }
     const Domain& domain(uint32_t k) {
         auto it = domains.find(k);
         if (it != domains.end()) return *it->second;
@@ -205,22 +218,23 @@ inline NttPlan make_plan(Context& ctx, uint32_t log_n, bool inverse) {
     p.inverse = inverse;
     return p;
 }
-inline void dev_lagrange_to_coeff(Context& ctx, uint32_t k, Fr* a, uint32_t batch = 1, size_t stride = 0) {
+// `side`: run on the context's ntt_stream with its own scratch (see Context::ntt_stream) instead of the main stream
+inline void dev_lagrange_to_coeff(Context& ctx, uint32_t k, Fr* a, uint32_t batch = 1, size_t stride = 0, bool side = false) {
     const Domain& d = ctx.domain(k);
     NttPlan p = make_plan(ctx, k, true);
     p.post_scale3 = d.post_l2c();
-    Fr* scratch = ntt_num_passes(k) > 1 ? ctx.get_scratch(d.n * batch) : nullptr;
-    ntt_run_batch(p, a, a, scratch, batch, stride, stride, d.n, ctx.stream);
+    Fr* scratch = ntt_num_passes(k) > 1 ? (side ? ctx.get_side_scratch(d.n * batch) : ctx.get_scratch(d.n * batch)) : nullptr;
+    ntt_run_batch(p, a, a, scratch, batch, stride, stride, d.n, side ? ctx.ntt_stream : ctx.stream);
 }
 inline void dev_coeff_to_extended(Context& ctx, uint32_t k, const Fr* in, Fr* out, uint32_t batch = 1, size_t stride_in = 0,
-                                  size_t stride_out = 0) {
+                                  size_t stride_out = 0, bool side = false) {
     const Domain& d = ctx.domain(k);
     NttPlan p = make_plan(ctx, k + 2, false);
     p.pre_scale3 = d.pre_coset();
     p.in_len = d.n;
     // multi-pass transforms bounce through scratch; the output buffer itself can serve when batch == 1
-    Fr* scratch = ctx.get_scratch(d.extended_n * batch);
-    ntt_run_batch(p, in, out, scratch, batch, stride_in, stride_out, d.extended_n, ctx.stream);
+    Fr* scratch = side ? ctx.get_side_scratch(d.extended_n * batch) : ctx.get_scratch(d.extended_n * batch);
+    ntt_run_batch(p, in, out, scratch, batch, stride_in, stride_out, d.extended_n, side ? ctx.ntt_stream : ctx.stream);
 }
 inline void dev_extended_to_coeff(Context& ctx, uint32_t k, const Fr* in, Fr* out) {
     const Domain& d = ctx.domain(k);

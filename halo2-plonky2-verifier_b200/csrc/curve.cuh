@@ -3,6 +3,8 @@
 // Affine points use the halo2curves layout (x‖y, 64 B, identity = (0,0)). Accumulators use extended
 // Jacobian "XYZZ" coordinates (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2): mixed add 8M+2S, no inversions; the
 // representation never leaves the library — results are normalised to canonical affine at the boundary.
+// Squares use the 108-multiply-add square of field.cuh and each formula's Y3 = A·B − C·D is one fused dual product with a
+// single Montgomery reduction (f_mul2_sub): a mixed addition costs 6 products + 2 squares + 1 dual product.
 #pragma once
 #include "field.cuh"
 
@@ -52,7 +54,7 @@ HD G1X g1x_dbl(const G1X& p) {
     Fq xx = f_sqr(p.x), m = f_add(f_dbl(xx), xx);
     G1X r;
     r.x = f_sub(f_sqr(m), f_dbl(s));
-    r.y = f_sub(f_mul(m, f_sub(s, r.x)), f_mul(w, p.y));
+    r.y = f_mul2_sub(m, f_sub(s, r.x), w, p.y);
     r.zz = f_mul(v, p.zz);
     r.zzz = f_mul(w, p.zzz);
     return r;
@@ -62,7 +64,7 @@ HD G1X g1x_dbl_affine(const G1Affine& p) {
     Fq xx = f_sqr(p.x), m = f_add(f_dbl(xx), xx);
     G1X r;
     r.x = f_sub(f_sqr(m), f_dbl(s));
-    r.y = f_sub(f_mul(m, f_sub(s, r.x)), f_mul(w, p.y));
+    r.y = f_mul2_sub(m, f_sub(s, r.x), w, p.y);
     r.zz = v;
     r.zzz = w;
     return r;
@@ -80,7 +82,7 @@ HD G1X g1x_add_affine(const G1X& a, const G1Affine& b) {
     Fq pp = f_sqr(p), ppp = f_mul(p, pp), q = f_mul(a.x, pp);
     G1X o;
     o.x = f_sub(f_sub(f_sqr(r), ppp), f_dbl(q));
-    o.y = f_sub(f_mul(r, f_sub(q, o.x)), f_mul(a.y, ppp));
+    o.y = f_mul2_sub(r, f_sub(q, o.x), a.y, ppp);  // two products, one Montgomery reduction
     o.zz = f_mul(a.zz, pp);
     o.zzz = f_mul(a.zzz, ppp);
     return o;
@@ -99,7 +101,7 @@ HD G1X g1x_add(const G1X& a, const G1X& b) {
     Fq pp = f_sqr(p), ppp = f_mul(p, pp), q = f_mul(u1, pp);
     G1X o;
     o.x = f_sub(f_sub(f_sqr(r), ppp), f_dbl(q));
-    o.y = f_sub(f_mul(r, f_sub(q, o.x)), f_mul(s1, ppp));
+    o.y = f_mul2_sub(r, f_sub(q, o.x), s1, ppp);
     o.zz = f_mul(f_mul(a.zz, b.zz), pp);
     o.zzz = f_mul(f_mul(a.zzz, b.zzz), ppp);
     return o;

@@ -388,6 +388,39 @@ HD Field<C> f_mul_comba(const Field<C>& a, const Field<C>& b) {
     }
     return f_reduce_once<C>(r, t0);
 }
+// (a1·b1 + a2·b2)·2^-256 mod P with ONE Montgomery reduction (all four operands < P, so the double-width sum is < 2P² and
+// the reduced value < 1.4 P: one conditional subtraction): 128 + 72 multiply-adds instead of 2 × 136. The point-addition
+// formulas have one such pair each (Y3 = R·(Q − X3) − Y1·PPP).
+template <class C>
+HD Field<C> f_mul2_add(const Field<C>& a1, const Field<C>& b1, const Field<C>& a2, const Field<C>& b2) {
+    uint32_t t0 = 0, t1 = 0, t2 = 0, m[8];
+    Field<C> r;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int l = i - j;
+            if (l >= 0 && l < 8) {
+                mac3(t0, t1, t2, a1.l[j], b1.l[l]);
+                mac3(t0, t1, t2, a2.l[j], b2.l[l]);
+            }
+        }
+        if (i < 8) {
+#pragma unroll
+            for (int j = 0; j < i; ++j) mac3(t0, t1, t2, m[j], C::P(i - j));
+            m[i] = t0 * C::INV;
+            mac3(t0, t1, t2, m[i], C::P(0));
+        } else {
+#pragma unroll
+            for (int j = i - 7; j < 8; ++j) mac3(t0, t1, t2, m[j], C::P(i - j));
+            r.l[i - 8] = t0;
+        }
+        t0 = t1;
+        t1 = t2;
+        t2 = 0;
+    }
+    return f_reduce_once<C>(r, t0);
+}
 // Montgomery square, a < P (< 2^254). The cross products 2·a_j·a_l (j < l) are taken against the limbs of the doubled
 // upper part of a — d_l = limb l of 2a for l > j+1, and a_l << 1 (no incoming bit) for l = j+1 — so a column needs one
 // multiply-add per unordered pair: 36 instead of 64 products for a·a, 108 instead of 136 in all.
@@ -570,6 +603,15 @@ HD Field<C> f_sqr(const Field<C>& a) {
     return f_sqr_comba<C>(a);
 #else
     return f_mul<C>(a, a);
+#endif
+}
+// a1·b1 − a2·b2
+template <class C>
+HD Field<C> f_mul2_sub(const Field<C>& a1, const Field<C>& b1, const Field<C>& a2, const Field<C>& b2) {
+#if defined(__CUDA_ARCH__) && !defined(B200ZK_NO_FUSED_MUL2)
+    return f_mul2_add<C>(a1, b1, f_neg<C>(a2), b2);
+#else
+    return f_sub<C>(f_mul<C>(a1, b1), f_mul<C>(a2, b2));
 #endif
 }
 // out of Montgomery form: a·2^-256 mod P (canonical integer limbs)

@@ -417,6 +417,7 @@ std::vector<uint8_t> create_proof(Context& ctx, const ProvingKeyDev& pk, const F
         // the transient columns have gone back to the arena (bookkeeping only): an exchange still running on the comm stream
         // must drain before the next call can hand that memory out again
         if (ctx.comm_stream) cudaStreamSynchronize(ctx.comm_stream);
+        if (ctx.ntt_stream) cudaStreamSynchronize(ctx.ntt_stream);
         ctx.comm_pending = false;
         throw;
     }
@@ -462,6 +463,36 @@ static std::vector<uint8_t> create_proof_body(Context& ctx, const ProvingKeyDev&
     tr.common_scalar(pk.transcript_repr);
     // step 1: upload, blind, commit advice (D.3)
     DevBuf<Fr> advice((size_t)NA * n, s);
+    // The advice columns' coefficient forms and extended cosets do not depend on the transcript: once the blinded columns
+    // are on the device they are computed on the side stream, beside the commit batches (which leave part of the
+    // multiplier pipe idle in their latency-bound phases); the main stream joins right before h(X) needs them.
+    DevBuf<Fr> advice_polys((size_t)NA * n, s), advice_cosets((size_t)NA * en, s);
+    const bool side_ntt = ctx.ntt_stream != nullptr && !g_prof_enabled;
+    auto advice_transforms = [&](bool side) {  // sharded: column c is transformed by rank (c + OFF_ADVICE_NTT) mod world
+        cudaStream_t st = side ? ctx.ntt_stream : s;
+        if (!shard.on()) {
+            CUDA_CHECK(cudaMemcpyAsync(advice_polys.get(), advice.get(), (size_t)NA * n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+            dev_lagrange_to_coeff(ctx, sh.k, advice_polys.get(), NA, n, side);
+            for (uint32_t c = 0; c < NA; ++c)
+                dev_coeff_to_extended(ctx, sh.k, advice_polys.get() + (size_t)c * n, advice_cosets.get() + (size_t)c * en, 1, 0, 0, side);
+            return;
+        }
+        for (uint32_t c = 0; c < NA; ++c)
+            if (shard.mine(c, OFF_ADVICE_NTT)) {
+                CUDA_CHECK(cudaMemcpyAsync(advice_polys.get() + (size_t)c * n, advice.get() + (size_t)c * n, n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+                dev_lagrange_to_coeff(ctx, sh.k, advice_polys.get() + (size_t)c * n, 1, 0, side);
+                dev_coeff_to_extended(ctx, sh.k, advice_polys.get() + (size_t)c * n, advice_cosets.get() + (size_t)c * en, 1, 0, 0, side);
+            }
+    };
+    // starts the side-stream transforms once everything queued so far on the main stream (and, if given, `also`) is done
+    auto fork_advice_transforms = [&](cudaEvent_t also) {
+        if (!side_ntt) return;
+        CUDA_CHECK(cudaEventRecord(ctx.ntt_fork, s));
+        CUDA_CHECK(cudaStreamWaitEvent(ctx.ntt_stream, ctx.ntt_fork, 0));
+        if (also) CUDA_CHECK(cudaStreamWaitEvent(ctx.ntt_stream, also, 0));
+        advice_transforms(true);
+        CUDA_CHECK(cudaEventRecord(ctx.ntt_done, ctx.ntt_stream));
+    };
     std::vector<Fr> blind((size_t)NA * (bf + 1));
     for (auto& b : blind) b = rng.next();
     skip_unused_blinds(NA);  // Blind(..) per advice column
@@ -503,6 +534,7 @@ static std::vector<uint8_t> create_proof_body(Context& ctx, const ProvingKeyDev&
             if (shard.mine(c)) upload(c, c + 1, s, true);
         shard.allgather_columns(advice.get(), NA, n);
         blind_rows(0, NA, s);
+        fork_advice_transforms(nullptr);
     } else if (ahead < NA) {
         CUDA_CHECK(cudaEventRecord(ctx.copy_fork, s));
         CUDA_CHECK(cudaStreamWaitEvent(ctx.copy_stream, ctx.copy_fork, 0));
@@ -513,6 +545,7 @@ static std::vector<uint8_t> create_proof_body(Context& ctx, const ProvingKeyDev&
     } else {
         upload(0, NA, s, true);
         blind_rows(0, NA, s);
+        fork_advice_transforms(nullptr);
     }
     CUDA_CHECK(cudaStreamSynchronize(s));
     lap(tm ? &tm->upload : nullptr);
@@ -521,6 +554,7 @@ static std::vector<uint8_t> create_proof_body(Context& ctx, const ProvingKeyDev&
         stager.join();
         blind_rows(ahead, NA, ctx.copy_stream);
         CUDA_CHECK(cudaEventRecord(ctx.copy_done, ctx.copy_stream));
+        fork_advice_transforms(ctx.copy_done);  // all columns and their blinding rows are up once copy_done has fired
         CUDA_CHECK(cudaStreamWaitEvent(s, ctx.copy_done, 0));
         for (const G1Affine& cm : commit_batch(ctx, 1, advice.get() + (size_t)ahead * n, n, NA - ahead, n)) tr.write_point(cm);
     }
@@ -718,17 +752,9 @@ static std::vector<uint8_t> create_proof_body(Context& ctx, const ProvingKeyDev&
     lap(tm ? &tm->ntt : nullptr);
     const Fr y = tr.squeeze_challenge();
     // step 8/9: advice polys + cosets, h(X) (D.8)
-    DevBuf<Fr> advice_polys((size_t)NA * n, s), advice_cosets((size_t)NA * en, s);
-    CUDA_CHECK(cudaMemcpyAsync(advice_polys.get(), advice.get(), (size_t)NA * n * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
-    if (!shard.on()) {
-        dev_lagrange_to_coeff(ctx, sh.k, advice_polys.get(), NA, n);
-        for (uint32_t c = 0; c < NA; ++c) dev_coeff_to_extended(ctx, sh.k, advice_polys.get() + (size_t)c * n, advice_cosets.get() + (size_t)c * en);
-    } else {  // column c is transformed by rank c mod world and broadcast over NCCL
-        for (uint32_t c = 0; c < NA; ++c)
-            if (shard.mine(c, OFF_ADVICE_NTT)) {
-                dev_lagrange_to_coeff(ctx, sh.k, advice_polys.get() + (size_t)c * n);
-                dev_coeff_to_extended(ctx, sh.k, advice_polys.get() + (size_t)c * n, advice_cosets.get() + (size_t)c * en);
-            }
+    if (side_ntt) CUDA_CHECK(cudaStreamWaitEvent(s, ctx.ntt_done, 0));
+    else advice_transforms(false);
+    if (shard.on()) {  // coefficient forms: overlapped all-gather (first read by the evaluations); cosets: row slices
         shard.allgather_columns_async(advice_polys.get(), NA, n, OFF_ADVICE_NTT);
         std::vector<Fr*> cs(NA);
         for (uint32_t c = 0; c < NA; ++c) cs[c] = advice_cosets.get() + (size_t)c * en;

@@ -121,6 +121,7 @@ __global__ void fmul_kernel(Field<C>* out, const Field<C>* in, int iters) {
             if (MODE == 0) x[i] = f_mul_chains<C>(x[i], w);
             if (MODE == 1) x[i] = f_mul_comba<C>(x[i], w);
             if (MODE == 2) x[i] = f_sqr_comba<C>(x[i]);
+            if (MODE == 3) x[i] = f_mul2_add<C>(x[i], w, w, x[i]);
         }
     }
     Field<C> s = x[0];
@@ -144,8 +145,14 @@ __global__ void check_kernel(unsigned long long* bad, unsigned long long seed, i
         a = f_reduce_once<C>(a, 0);
         const Field<C> r0 = f_mul_chains<C>(a, b), r1 = f_mul_comba<C>(a, b);
         const Field<C> s0 = f_mul_chains<C>(a, a), s1 = f_sqr_comba<C>(a);
+        Field<C> c = b;
+        c.l[7] &= 0x3fffffffu;
+        c = f_reduce_once<C>(c, 0);
+        c = f_reduce_once<C>(c, 0);
+        const Field<C> d0 = f_sub<C>(f_mul_chains<C>(a, c), f_mul_chains<C>(c, s0)), d1 = f_mul2_add<C>(a, c, f_neg<C>(c), s0);
         if (!f_eq(r0, r1)) ++n_bad;
         if (!f_eq(s0, s1)) ++n_bad;
+        if (!f_eq(d0, d1)) ++n_bad;
     }
     if (n_bad) atomicAdd(bad, n_bad);
 }
@@ -196,12 +203,13 @@ int main() {
         const double ops = (double)blocks * threads * it2 * 8;
         printf(", \"dfma_Tops\": %.3f, \"coissue_ms\": {\"imad_wide_x_only\": %.3f, \"dfma_only\": %.3f, \"both\": %.3f}", ops / t2 / 1e9, t1, t2, t3);
     }
-    const char* names[3] = {"chains_mul", "comba_mul", "comba_sqr"};
-    for (int mode = 0; mode < 3; ++mode) {
+    const char* names[4] = {"chains_mul", "comba_mul", "comba_sqr", "fused_dual_product"};
+    for (int mode = 0; mode < 4; ++mode) {
         float ms1 = 0, ms2 = 0;
         if (mode == 0) { ms1 = time_ms([&] { fmul_kernel<0, 1, FrCfg><<<blocks, threads>>>((Fr*)buf, din, 512); }); ms2 = time_ms([&] { fmul_kernel<0, 2, FrCfg><<<blocks, threads>>>((Fr*)buf, din, 512); }); }
         if (mode == 1) { ms1 = time_ms([&] { fmul_kernel<1, 1, FrCfg><<<blocks, threads>>>((Fr*)buf, din, 512); }); ms2 = time_ms([&] { fmul_kernel<1, 2, FrCfg><<<blocks, threads>>>((Fr*)buf, din, 512); }); }
         if (mode == 2) { ms1 = time_ms([&] { fmul_kernel<2, 1, FrCfg><<<blocks, threads>>>((Fr*)buf, din, 512); }); ms2 = time_ms([&] { fmul_kernel<2, 2, FrCfg><<<blocks, threads>>>((Fr*)buf, din, 512); }); }
+        if (mode == 3) { ms1 = time_ms([&] { fmul_kernel<3, 1, FrCfg><<<blocks, threads>>>((Fr*)buf, din, 512); }); ms2 = time_ms([&] { fmul_kernel<3, 2, FrCfg><<<blocks, threads>>>((Fr*)buf, din, 512); }); }
         printf(", \"fr_%s_Gops_ilp1\": %.2f, \"fr_%s_Gops_ilp2\": %.2f", names[mode], (double)blocks * threads * 512 / ms1 / 1e6, names[mode],
                (double)blocks * threads * 512 * 2 / ms2 / 1e6);
     }
@@ -210,7 +218,7 @@ int main() {
         check_kernel<FrCfg><<<sms * 4, 128>>>(bad, 1, 256);
         check_kernel<FqCfg><<<sms * 4, 128>>>(bad, 2, 256);
         unsigned long long hb = ~0ull; cudaMemcpy(&hb, bad, 8, cudaMemcpyDeviceToHost);
-        printf(", \"comba_vs_chains_checked\": %llu, \"comba_vs_chains_mismatches\": %llu", (unsigned long long)sms * 4 * 128 * 256 * 2 * 2, hb);
+        printf(", \"comba_vs_chains_checked\": %llu, \"comba_vs_chains_mismatches\": %llu", (unsigned long long)sms * 4 * 128 * 256 * 2 * 3, hb);
     }
     cudaError_t e = cudaDeviceSynchronize();
     printf(", \"cuda\": \"%s\"}\n", cudaGetErrorString(e));

@@ -158,6 +158,11 @@ class Context:
         self._ag = ALLGATHER_FN(trampoline)
         self._check(lib().b200zk_set_allgather(self._h, int(rank), int(world), self._ag, None))
 
+    def comm_init(self):
+        """Bring up the library's NCCL communicator (collective over all ranks) so that standalone MSM calls exchange their
+        partial sums inside the library."""
+        self._check(lib().b200zk_comm_init(self._h))
+
     COMPAT_NO_UNUSED_BLIND_DRAWS, COMPAT_LOOKUP_FILL_ASCENDING, COMPAT_POINT_SIGN_BIT7 = 1, 2, 4
 
     def set_compat(self, flags=0, random_poly_chunks=0):

@@ -335,6 +335,15 @@ int b200zk_set_allgather(b200zk_ctx* ctx, int rank, int world, b200zk_allgather_
     ctx->c.nccl.reset();
     API_END(ctx)
 }
+int b200zk_comm_init(b200zk_ctx* ctx) {
+    if (ctx && !ctx->peers.empty()) return B200ZK_OK;  // a device group is born with its communicator
+    API_BEGIN(ctx)
+    if (ctx->c.world > 1) {
+        Sharder sh(ctx->c);
+        sh.nccl();
+    }
+    API_END(ctx)
+}
 int b200zk_set_compat(b200zk_ctx* ctx, uint32_t flags, uint32_t random_poly_chunks) {
     GROUP_DISPATCH(ctx, b200zk_set_compat(rctx, flags, random_poly_chunks))
     API_BEGIN(ctx)

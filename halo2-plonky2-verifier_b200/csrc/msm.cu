@@ -235,7 +235,17 @@ __global__ void __launch_bounds__(ACC_THREADS) msm_accumulate_kernel(const G1Aff
     bool started_before = __ldg(offsets + cur) < p0;
     head_keys[t] = started_before ? cur : INVALID_KEY;
     G1X acc = g1x_identity();
+    // software pipeline: the entry and the 64-byte base of the NEXT addition are requested before the current one starts —
+    // the base is a random gather from the window table (mostly DRAM) and would otherwise sit in front of every addition
+    uint32_t e_next = __ldg(entries + p0);
+    G1Affine b_next = g1a_load_ro(bases + (e_next & 0x7fffffffu));
     for (uint32_t p = p0; p < p1; ++p) {
+        const uint32_t e = e_next;
+        G1Affine b = b_next;
+        if (p + 1 < p1) {
+            e_next = __ldg(entries + p + 1);
+            b_next = g1a_load_ro(bases + (e_next & 0x7fffffffu));
+        }
         if (p == end) {
             g1x_store(started_before ? heads + t : bucket_sums + cur, acc);
             acc = g1x_identity();
@@ -245,8 +255,6 @@ __global__ void __launch_bounds__(ACC_THREADS) msm_accumulate_kernel(const G1Aff
             cur = find_bucket(offsets, nb, p);
             end = __ldg(offsets + cur + 1);
         }
-        const uint32_t e = __ldg(entries + p);
-        G1Affine b = g1a_load_ro(bases + (e & 0x7fffffffu));
         if (e >> 31) b.y = f_neg(b.y);
         acc = g1x_add_affine(acc, b);
     }

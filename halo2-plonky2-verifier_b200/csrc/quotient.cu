@@ -25,8 +25,8 @@ __global__ void __launch_bounds__(256) h_gates_kernel(QuotientArgs Q, Fr* h) {
     Fr v = f_zero<FrCfg>();
     for (uint32_t c = 0; c < Q.A; ++c) {
         const Fr* a = Q.advice[c];
-        const Fr g = f_mul(f_load(Q.fixed[Q.F + 1 + c] + i), f_sub(f_add(f_load(a + i), f_mul(f_load(a + i1), f_load(a + i2))), f_load(a + i3)));
-        v = f_add(f_mul(v, Q.y), g);
+        const Fr g = f_sub(f_add(f_load(a + i), f_mul(f_load(a + i1), f_load(a + i2))), f_load(a + i3));
+        v = f_mul2_add(v, Q.y, f_load(Q.fixed[Q.F + 1 + c] + i), g);  // v·y + q·g with one Montgomery reduction
     }
     f_store(h + i, v);
 }
@@ -42,11 +42,11 @@ __global__ void __launch_bounds__(256) h_permutation_kernel(QuotientArgs Q, Fr* 
     const uint32_t ns = Q.num_sets;
     {
         const Fr z0 = f_load(Q.z[0] + i);
-        v = f_add(f_mul(v, Q.y), f_mul(f_sub(one, z0), l0));
+        v = f_mul2_add(v, Q.y, f_sub(one, z0), l0);
         const Fr zl = f_load(Q.z[ns - 1] + i);
-        v = f_add(f_mul(v, Q.y), f_mul(f_sub(f_sqr(zl), zl), l_last));
+        v = f_mul2_add(v, Q.y, f_sub(f_sqr(zl), zl), l_last);
     }
-    for (uint32_t s = 1; s < ns; ++s) v = f_add(f_mul(v, Q.y), f_mul(f_sub(f_load(Q.z[s] + i), f_load(Q.z[s - 1] + r_last)), l0));
+    for (uint32_t s = 1; s < ns; ++s) v = f_mul2_add(v, Q.y, f_sub(f_load(Q.z[s] + i), f_load(Q.z[s - 1] + r_last)), l0);
     // beta·zeta·omega_ext^i, then ·delta per column
     Fr current_delta = f_mul(Q.beta_zeta, omega_pow_from_table(Q.table, Q.table_log, Q.k + 2, (uint32_t)i));
     for (uint32_t s = 0; s < ns; ++s) {
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(256) h_permutation_kernel(QuotientArgs Q, Fr* 
             right = f_mul(right, f_add(f_add(val, current_delta), Q.gamma));
             current_delta = f_mul(current_delta, Q.delta);
         }
-        v = f_add(f_mul(v, Q.y), f_mul(f_sub(left, right), l_active));
+        v = f_mul2_add(v, Q.y, f_sub(left, right), l_active);
     }
     if (final_scale) v = f_mul(v, f_load_ro(Q.t_inv + (i & 3)));
     f_store(h + i, v);
@@ -75,14 +75,14 @@ __global__ void __launch_bounds__(256) h_lookup_kernel(QuotientArgs Q, LookupCos
     const Fr table_value = f_mul(f_add(f_load(Lk.input + i), Q.beta), f_add(f_load(Lk.table + i), Q.gamma));
     const Fr a_minus_s = f_sub(a, sp);
     Fr v = f_load(h + i);
-    v = f_add(f_mul(v, Q.y), f_mul(f_sub(one, z), l0));
-    v = f_add(f_mul(v, Q.y), f_mul(f_sub(f_sqr(z), z), l_last));
+    v = f_mul2_add(v, Q.y, f_sub(one, z), l0);
+    v = f_mul2_add(v, Q.y, f_sub(f_sqr(z), z), l_last);
     {
         const Fr lhs = f_mul(f_mul(f_load(Lk.z + r_next), f_add(a, Q.beta)), f_add(sp, Q.gamma));
-        v = f_add(f_mul(v, Q.y), f_mul(f_sub(lhs, f_mul(z, table_value)), l_active));
+        v = f_mul2_add(v, Q.y, f_sub(lhs, f_mul(z, table_value)), l_active);
     }
-    v = f_add(f_mul(v, Q.y), f_mul(a_minus_s, l0));
-    v = f_add(f_mul(v, Q.y), f_mul(f_mul(a_minus_s, f_sub(a, f_load(Lk.a + r_prev))), l_active));
+    v = f_mul2_add(v, Q.y, a_minus_s, l0);
+    v = f_mul2_add(v, Q.y, f_mul(a_minus_s, f_sub(a, f_load(Lk.a + r_prev))), l_active);
     if (final_scale) v = f_mul(v, f_load_ro(Q.t_inv + (i & 3)));
     f_store(h + i, v);
 }

@@ -73,6 +73,10 @@ B200ZK_API unsigned long long b200zk_launch_count(void);
  * MPI all-gather) and return 0. All ranks must issue the same MSM calls in the same order. world = 1 disables it. */
 typedef int (*b200zk_allgather_fn)(void* user, const void* send, size_t bytes, void* recv);
 B200ZK_API int b200zk_set_allgather(b200zk_ctx* ctx, int rank, int world, b200zk_allgather_fn fn, void* user);
+/* Brings up the library's own NCCL communicator now (collective: every rank must call it; the 128-byte id travels through
+ * the callback above — its only use from then on). create_proof does this on first use; a host that only calls the MSM
+ * entry points calls it once so that the partial sums go over NVLink inside the library instead of through the callback. */
+B200ZK_API int b200zk_comm_init(b200zk_ctx* ctx);
 /* Upstream details that change proof BYTES and that could not be checked against halo2-axiom's source (no Rust sources in
  * the build image; SURVEY.md §8c items 1–4). Each is one switch, mirrored by the CPU oracle; 0 / 0 = the defaults (classic
  * PSE-halo2 behaviour). If a proof ever differs from the Rust prover's, flipping a bit here is the fix:

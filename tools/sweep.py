@@ -1,6 +1,8 @@
 """BASELINE.json configs [2] and [3]: G1 MSM sweep (uniform / advice-like / sorted-lookup scalars) and Fr NTT sweep
 (forward, lagrange_to_coeff, coeff_to_extended, extended_to_coeff; batches 17 and 29), device-resident inputs, CUDA events on the
-library's stream. Under torchrun the MSM sweep is sharded by point range across the ranks (partial sums over NCCL).
+library's stream. Under torchrun the MSM sweep is sharded by point range across the ranks (partial sums over NCCL inside
+the library) and the NTT sweep deals the columns of a batch round-robin to the ranks (no exchange: aggregate throughput,
+time = the slowest rank).
 
     python tools/sweep.py [--max-k 26] [--out gpurun_out/sweep.json]
 """
@@ -37,6 +39,7 @@ ctx = b200zk.Context(local_rank)
 stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
 if world > 1:
     ctx.set_allgather(rank, world, b200zk.torch_allgather(dist, torch.device("cuda", local_rank)))
+    ctx.comm_init()
 HBM = 6541.8
 try:
     HBM = float(json.load(open(os.path.join(R, "MEASURED_PEAKS.json")))["hbm_gbs"])
@@ -108,7 +111,7 @@ for k in range(args.min_k, kmax + 1, 2):
         if rank == 0:
             print("msm", k, kind, round(ms, 3), "ms", round(n / ms / 1e3, 1), "Mpts/s", flush=True)
         del buf
-if not args.no_ntt and world == 1:
+if not args.no_ntt:
     root = np.array([[0xd34f1ed960c37c9c, 0x3215cf6dd39329c8, 0x98865ea93dd31f74, 0x03ddb9f5166d18b7]], dtype=np.uint64)
     cases = [(k, B) for B in (17, 29) for k in range(args.min_k, min(kmax, 22) + 1, 2)]  # S20-bn's and S22-gl's A+L
     if kmax >= 24:
@@ -116,6 +119,10 @@ if not args.no_ntt and world == 1:
     for k, batch in cases:
         n = 1 << k
         col = rng.integers(0, 1 << 62, size=(n, 4), dtype=np.uint64)
+        total_batch = batch
+        batch = len(range(rank, total_batch, world))  # this rank's columns of the batch (round-robin)
+        if batch == 0:
+            batch = 1  # keeps the collective timing calls in step; not counted (total_batch < world never happens here)
         buf = torch.empty(batch * n * 4, dtype=torch.int64, device="cuda")
         for b in range(batch):
             ctx.h2d(buf.data_ptr() + 32 * n * b, col)
@@ -124,8 +131,9 @@ if not args.no_ntt and world == 1:
             w = ctx.field_vec_op(0, 2, w, w)
         omega = w[0].copy()
         ms_f = timed(lambda: ctx.ntt_dev(buf.data_ptr(), k, omega, batch, n), 5)
-        row = {"batch": batch, "forward_ms": ms_f, "forward_GBps_64nB": 64.0 * n * batch / ms_f / 1e6, "forward_frac_hbm": 64.0 * n * batch / ms_f / 1e6 / HBM,
-               "Gbutterfly_s": batch * (n // 2) * k / ms_f / 1e6}
+        row = {"batch": total_batch, "columns_on_slowest_rank": len(range(0, total_batch, world)), "forward_ms": ms_f,
+               "forward_GBps_64nB": 64.0 * n * total_batch / ms_f / 1e6, "forward_frac_hbm": 64.0 * n * total_batch / ms_f / 1e6 / (HBM * world),
+               "Gbutterfly_s": total_batch * (n // 2) * k / ms_f / 1e6}
         ms_l = timed(lambda: ctx.lagrange_to_coeff_dev(k, buf.data_ptr(), batch, n), 5)
         row["lagrange_to_coeff_ms"] = ms_l
         ext = torch.empty(4 * n * 4, dtype=torch.int64, device="cuda")
@@ -137,12 +145,14 @@ if not args.no_ntt and world == 1:
         row["extended_to_coeff_ms"] = ms_e
         row["extended_to_coeff_GBps_224n"] = 224.0 * n / ms_e / 1e6
         del ext, out3
-        res["ntt"][f"2^{k}/B{batch}"] = row
-        print("ntt", k, {a: (round(b, 3) if isinstance(b, float) else b) for a, b in row.items()}, flush=True)
+        res["ntt"][f"2^{k}/B{total_batch}"] = row
+        if rank == 0:
+            print("ntt", k, {a: (round(b, 3) if isinstance(b, float) else b) for a, b in row.items()}, flush=True)
         del buf
 if rank == 0:
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     json.dump(res, open(args.out, "w"), indent=1)
+ctx.close()
 if dist is not None:
     dist.barrier()
-os._exit(0)
+    dist.destroy_process_group()

@@ -420,6 +420,19 @@ class ProvingKey:
         except Exception:
             pass
 
+    def set_gates(self, calcs, constants=(), results=()):
+        """b200zk_pk_set_gates. `calcs`: list of (op, a, b) with a, b = (kind, index, rotation) (b may be None for unary
+        calculations); `constants`: field elements (uint64[4] each); `results`: indices of the gate intermediates. An empty
+        `calcs` restores the built-in halo2-base gates."""
+        arr = np.zeros((len(calcs), 7), dtype=np.uint32)
+        for j, (op, a, b) in enumerate(calcs):
+            b = b if b is not None else (0, 0, 0)
+            arr[j] = [op, a[0], a[1], np.int32(a[2]).astype(np.uint32), b[0], b[1], np.int32(b[2]).astype(np.uint32)]
+        cs = _c(np.asarray(constants, dtype=np.uint64).reshape(-1, 4)) if len(constants) else None
+        rs = np.ascontiguousarray(results, dtype=np.uint32)
+        self.ctx._check(lib().b200zk_pk_set_gates(self.ctx._h, self._h, _p(arr) if len(calcs) else None, ctypes.c_size_t(len(calcs)), _p(cs),
+                                                  ctypes.c_size_t(0 if cs is None else len(cs)), _p(rs) if len(rs) else None, ctypes.c_size_t(len(rs))))
+
     def commitments(self):
         k, A, L, F = self.shape
         fc = np.empty((F + 1 + A, 8), dtype=np.uint64)
@@ -482,6 +495,32 @@ class ProvingKey:
         if timings:
             return proof, dict(zip(TIMING_KEYS, tm.tolist()))
         return proof
+
+
+RNG_FILL_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint8), ctypes.c_size_t)
+
+
+def create_proof_rng(pk, advice, fill):
+    """b200zk_create_proof_rng: `fill(nbytes) -> bytes` plays the host generator's RngCore::fill_bytes."""
+    k, A, L, F = pk.shape
+    advice = _c(advice)
+    assert advice.size == (A + L) * (1 << k) * 4
+
+    def trampoline(user, out, nbytes):
+        try:
+            data = fill(int(nbytes))
+            if len(data) != nbytes:
+                return -1
+            ctypes.memmove(out, data, nbytes)
+            return 0
+        except Exception:  # never unwind into C
+            return -2
+
+    cb = RNG_FILL_FN(trampoline)
+    buf = np.empty(pk.proof_size(), dtype=np.uint8)
+    plen = ctypes.c_size_t(0)
+    pk.ctx._check(lib().b200zk_create_proof_rng(pk.ctx._h, pk._h, _p(advice), cb, None, _p(buf), ctypes.byref(plen), None))
+    return buf[: plen.value].tobytes()
 
 
 def synth_circuit(k, A, L, F, seed=0):

@@ -752,6 +752,20 @@ int b200zk_pk_free(b200zk_ctx* ctx, b200zk_pk* pk) {
     delete pk;
     API_END(ctx)
 }
+static_assert(sizeof(b200zk_value_source) == sizeof(GateSrc) && sizeof(b200zk_calculation) == sizeof(GateCalc), "gate program ABI");
+int b200zk_pk_set_gates(b200zk_ctx* ctx, b200zk_pk* pk, const b200zk_calculation* calcs, size_t ncalcs, const b200zk_fr* constants,
+                        size_t nconstants, const uint32_t* results, size_t nresults) {
+    if (ctx && pk && !pk->peers.empty() && !tls_group_worker) {
+        if (pk->peers.size() != ctx->peers.size()) return B200ZK_EINVAL;
+        return group_call(ctx, [&](b200zk_ctx* rctx, int rank) -> int {
+            return b200zk_pk_set_gates(rctx, const_cast<b200zk_pk*>(pk->rank_pk(rank)), calcs, ncalcs, constants, nconstants, results, nresults);
+        });
+    }
+    API_BEGIN(ctx)
+    if (!pk) throw std::invalid_argument("null pk");
+    pk_set_gates(ctx->c, *pk->pk, (const GateCalc*)calcs, ncalcs, (const Fr*)constants, nconstants, results, nresults);
+    API_END(ctx)
+}
 int b200zk_pk_commitments(b200zk_ctx* ctx, const b200zk_pk* pk, b200zk_g1_affine* fixed_out, b200zk_g1_affine* perm_out) {
     API_BEGIN(ctx)
     if (!pk) throw std::invalid_argument("null pk");
@@ -883,6 +897,22 @@ int b200zk_evaluate_h(b200zk_ctx* ctx, const b200zk_pk* pk, const b200zk_fr* adv
 uint32_t b200zk_num_sets(uint32_t A, uint32_t L, uint32_t F) {
     Shape sh{1, A, L, F};
     return sh.num_sets();
+}
+int b200zk_create_proof_rng(b200zk_ctx* ctx, const b200zk_pk* pk, const b200zk_fr* advice, b200zk_rng_fill_fn fill, void* user, uint8_t* proof_out,
+                            size_t* proof_len, double* timings) {
+    if (ctx && !ctx->peers.empty()) return B200ZK_EINVAL;  // one generator cannot feed several ranks in lockstep
+    API_BEGIN(ctx)
+    if (!pk || !advice || !proof_out || !proof_len || !fill) throw std::invalid_argument("create_proof_rng: null argument");
+    host::FrRandomStream rng = host::FrRandomStream::from_callback(fill, user);
+    ProofTimings tm;
+    std::vector<uint8_t> proof = create_proof(ctx->c, *pk->pk, (const Fr*)advice, false, rng, timings ? &tm : nullptr);
+    memcpy(proof_out, proof.data(), proof.size());
+    *proof_len = proof.size();
+    if (timings) {
+        const double t[10] = {tm.upload, tm.msm, tm.ntt, tm.lookup, tm.products, tm.quotient, tm.evals, tm.shplonk, tm.other, tm.comm};
+        memcpy(timings, t, sizeof(t));
+    }
+    API_END(ctx)
 }
 int b200zk_create_proof(b200zk_ctx* ctx, const b200zk_pk* pk, const b200zk_fr* advice, uint64_t rng_seed, uint8_t* proof_out, size_t* proof_len,
                         double* timings) {

@@ -3,6 +3,7 @@
 // Fr::random. Serial and byte-oriented — a patched halo2_proofs keeps its own Rust versions; these C++ mirrors exist
 // so that the C ABI can run create_proof end to end. They share no code with oracle/.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <stdexcept>
@@ -169,6 +170,22 @@ class FrRandomStream {
     uint32_t key[8];
     int rounds;
     uint64_t pos = 0;
+    // external source (b200zk_create_proof_rng): the host's own RngCore::fill_bytes; the ChaCha fields are unused then and
+    // every draw — including the n draws of the random polynomial — is pulled through the callback
+    int (*fill_fn)(void* user, uint8_t* out, size_t nbytes) = nullptr;
+    void* fill_user = nullptr;
+    bool external() const { return fill_fn != nullptr; }
+    static FrRandomStream from_callback(int (*fn)(void*, uint8_t*, size_t), void* user) {
+        FrRandomStream r;
+        memset(r.key, 0, sizeof(r.key));
+        r.rounds = 0;
+        r.fill_fn = fn;
+        r.fill_user = user;
+        return r;
+    }
+    void pull(uint8_t* out, size_t nbytes) {
+        if (fill_fn(fill_user, out, nbytes) != 0) throw std::runtime_error("create_proof: the random source callback failed");
+    }
     bool aligned() const { return pos % 16 == 0; }
     uint64_t block_index() const { return pos / 16; }
 
@@ -208,6 +225,11 @@ class FrRandomStream {
     }
     // the next `count` keystream words
     void words(uint32_t* out, size_t count) {
+        if (fill_fn) {
+            pull((uint8_t*)out, 4 * count);
+            pos += count;
+            return;
+        }
         uint32_t blk[16];
         uint64_t have = ~0ull;
         for (size_t i = 0; i < count; ++i, ++pos) {
@@ -228,7 +250,17 @@ class FrRandomStream {
         words(w, 8);
         memcpy(out, w, 32);
     }
-    void skip(uint64_t n) { pos += 16 * n; }
+    void skip(uint64_t n) {
+        if (fill_fn) {  // the draws have to be made to advance the host's generator
+            uint8_t buf[4096];
+            for (uint64_t left = 64 * n; left > 0;) {
+                const size_t take = (size_t)std::min<uint64_t>(left, sizeof(buf));
+                pull(buf, take);
+                left -= take;
+            }
+        }
+        pos += 16 * n;
+    }
 };
 
 }  // namespace host

@@ -760,24 +760,57 @@ G1Affine msm_run_srs(Context& ctx, int basis, const Fr* scalars, size_t n) {
 }
 
 // T[w][i] = 2^(c·w)·P_i as affine points, w < W: built once per SRS
+// Each thread takes TABLE_PTS points (a stride of n / TABLE_PTS apart, so a warp's accesses stay coalesced) and shares ONE
+// field inversion among them (Montgomery's trick): c doublings ≈ 160 products per point, against 380 for a Fermat inversion
+// per point — the table build (13 rows × 2 bases at k=20) halves.
+constexpr int TABLE_PTS = 4;
 __global__ void __launch_bounds__(128) msm_table_step_kernel(const G1Affine* prev, G1Affine* next, size_t n, uint32_t c) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    G1Affine p;
-    p.x = f_load(&prev[i].x);
-    p.y = f_load(&prev[i].y);
-    G1X a = g1x_from_affine(p);
-    for (uint32_t d = 0; d < c; ++d) a = g1x_dbl(a);
-    const G1Affine r = g1x_to_affine(a);
-    f_store(&next[i].x, r.x);
-    f_store(&next[i].y, r.y);
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x, per = (n + TABLE_PTS - 1) / TABLE_PTS;
+    if (t >= per) return;
+    G1X a[TABLE_PTS];
+    Fq d[TABLE_PTS], pref[TABLE_PTS];
+    Fq run = f_one<FqCfg>();
+#pragma unroll
+    for (int j = 0; j < TABLE_PTS; ++j) {
+        const size_t i = t + (size_t)j * per;
+        a[j] = g1x_identity();
+        if (i < n) {
+            G1Affine p;
+            p.x = f_load(&prev[i].x);
+            p.y = f_load(&prev[i].y);
+            a[j] = g1x_from_affine(p);
+            for (uint32_t q = 0; q < c; ++q) a[j] = g1x_dbl(a[j]);
+        }
+        d[j] = g1_is_identity(a[j]) ? f_one<FqCfg>() : f_mul(a[j].zz, a[j].zzz);  // identity: a harmless factor of one
+        pref[j] = run;
+        run = f_mul(run, d[j]);
+    }
+    Fq inv = f_inv(run);
+#pragma unroll
+    for (int j = TABLE_PTS - 1; j >= 0; --j) {
+        const size_t i = t + (size_t)j * per;
+        const Fq dinv = f_mul(inv, pref[j]);  // 1 / (zz·zzz) of point j
+        inv = f_mul(inv, d[j]);
+        if (i >= n) continue;
+        G1Affine r;
+        if (g1_is_identity(a[j])) {
+            r.x = f_zero<FqCfg>();
+            r.y = f_zero<FqCfg>();
+        } else {
+            r.x = f_mul(a[j].x, f_mul(dinv, a[j].zzz));  // X / ZZ
+            r.y = f_mul(a[j].y, f_mul(dinv, a[j].zz));   // Y / ZZZ
+        }
+        f_store(&next[i].x, r.x);
+        f_store(&next[i].y, r.y);
+    }
 }
 void msm_build_table(Context& ctx, const G1Affine* bases, size_t n, uint32_t c, DevBuf<G1Affine>& table) {
     const uint32_t W = (255 + c - 1) / c;
     table.alloc_persistent((size_t)W * n, ctx.stream);
     CUDA_CHECK(cudaMemcpyAsync(table.get(), bases, n * sizeof(G1Affine), cudaMemcpyDeviceToDevice, ctx.stream));
     for (uint32_t w = 1; w < W; ++w) {
-        msm_table_step_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx.stream>>>(table.get() + (size_t)(w - 1) * n, table.get() + (size_t)w * n, n, c);
+        const size_t per = (n + TABLE_PTS - 1) / TABLE_PTS;
+        msm_table_step_kernel<<<(unsigned)((per + 127) / 128), 128, 0, ctx.stream>>>(table.get() + (size_t)(w - 1) * n, table.get() + (size_t)w * n, n, c);
         ++g_launch_count;
     }
     CUDA_CHECK(cudaGetLastError());

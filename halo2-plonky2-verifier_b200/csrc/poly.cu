@@ -474,6 +474,25 @@ __global__ void random_stream_kernel(Fr* out, size_t n, ChaChaKey key, unsigned 
     for (int j = 0; j < 16; ++j) x[j] += in[j];
     f_store(out + i, f_from_u512<FrCfg>(x));
 }
+// out[i] = from_u512(words[16 i .. 16 i + 16)) for host-supplied random words (an external RngCore); in place is fine
+// (`words` may alias the first half of a 64·n-byte buffer whose prefix is `out`? no: separate buffers)
+__global__ void from_u512_kernel(Fr* out, const uint32_t* words, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w[16];
+    const uint4* q = reinterpret_cast<const uint4*>(words + 16 * i);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint4 v = q[j];
+        w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
+    }
+    f_store(out + i, f_from_u512<FrCfg>(w));
+}
+void fr_from_u512(Fr* out, const uint32_t* words_dev, size_t n, cudaStream_t s) {
+    if (!n) return;
+    from_u512_kernel<<<nblocks(n, 128), 128, 0, s>>>(out, words_dev, n);
+    LAUNCHED(1);
+}
 void fr_random_stream(Fr* out, size_t n, const uint32_t key[8], uint64_t counter0, int rounds, cudaStream_t s) {
     if (!n) return;
     ChaChaKey k;

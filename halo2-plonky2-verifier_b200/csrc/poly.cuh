@@ -45,6 +45,8 @@ int lookup_permute(Context& ctx, const Fr* input, const Fr* table, Fr* a_out, Fr
 
 // ---- Fr::random stream: element j of a rand_chacha BlockRng stream = from_u512 of ChaCha block (counter0 + j) ---------
 void fr_random_stream(Fr* out, size_t n, const uint32_t key[8], uint64_t counter0, int rounds, cudaStream_t s);
+// out[i] = Fr::from_u512 of the i-th 64-byte group of host-supplied random words (device buffer of 16·n words)
+void fr_from_u512(Fr* out, const uint32_t* words_dev, size_t n, cudaStream_t s);
 
 // ---- sigma columns from the permutation mapping: sigma[i] = delta^col(i) * omega^row(i) ------------------------------
 void sigma_from_mapping(Fr* sigma, const uint32_t* map_col, const uint32_t* map_row, const Fr* delta_pows_dev, const Fr* table,

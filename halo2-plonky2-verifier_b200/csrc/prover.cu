@@ -169,6 +169,65 @@ std::unique_ptr<ProvingKeyDev> keygen(Context& ctx, const Shape& sh, const Fr* f
     return pk;
 }
 
+void pk_set_gates(Context& ctx, ProvingKeyDev& pk, const GateCalc* calcs, size_t ncalcs, const Fr* constants, size_t nconstants,
+                  const uint32_t* results, size_t nresults) {
+    const Shape& sh = pk.shape;
+    cudaStream_t s = ctx.stream;
+    if (ncalcs == 0) {  // back to the specialised kernel
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        pk.gate_calcs.release();
+        pk.gate_constants.release();
+        pk.gate_results.release();
+        return;
+    }
+    if (!calcs || !results || (nconstants && !constants)) throw std::invalid_argument("set_gates: null argument");
+    if (ncalcs > GATE_MAX_CALCS || nconstants > GATE_MAX_CONSTANTS || nresults == 0 || nresults > GATE_MAX_RESULTS)
+        throw std::invalid_argument("set_gates: program too large (128 calculations, 64 constants, 64 gates)");
+    std::vector<uint32_t> degree(ncalcs, 0);
+    auto src_degree = [&](const GateSrc& v, size_t j) -> uint32_t {
+        switch (v.kind) {
+            case GATE_SRC_CONSTANT:
+                if (v.index >= nconstants) throw std::invalid_argument("set_gates: constant index out of range");
+                return 0;
+            case GATE_SRC_INTERMEDIATE:
+                if (v.index >= j) throw std::invalid_argument("set_gates: an intermediate may only refer to an earlier calculation");
+                return degree[v.index];
+            case GATE_SRC_FIXED:
+                if (v.index >= sh.num_fixed() || v.rotation != 0) throw std::invalid_argument("set_gates: fixed columns are queried at rotation 0 only");
+                return 1;
+            case GATE_SRC_ADVICE:
+                // the proof opens gate columns at rotations 0..3 and lookup columns at 0: a program must stay inside that query set
+                if (v.index >= sh.num_advice() || v.rotation < 0 || v.rotation > (v.index < sh.A ? 3 : 0))
+                    throw std::invalid_argument("set_gates: advice rotation outside the proof's query set (gate columns 0..3, lookup columns 0)");
+                return 1;
+            default: throw std::invalid_argument("set_gates: unknown value source");
+        }
+    };
+    for (size_t j = 0; j < ncalcs; ++j) {
+        const GateCalc& c = calcs[j];
+        const uint32_t da = src_degree(c.a, j);
+        switch (c.op) {
+            case GATE_ADD: case GATE_SUB: degree[j] = std::max(da, src_degree(c.b, j)); break;
+            case GATE_MUL: degree[j] = da + src_degree(c.b, j); break;
+            case GATE_SQUARE: degree[j] = 2 * da; break;
+            case GATE_DOUBLE: case GATE_NEGATE: case GATE_STORE: degree[j] = da; break;
+            default: throw std::invalid_argument("set_gates: unknown calculation");
+        }
+    }
+    for (size_t g = 0; g < nresults; ++g) {
+        if (results[g] >= ncalcs) throw std::invalid_argument("set_gates: result index out of range");
+        if (degree[results[g]] > Shape::degree) throw std::invalid_argument("set_gates: gate degree exceeds the constraint system's degree (4)");
+    }
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    pk.gate_calcs.alloc_persistent(ncalcs, s);
+    pk.gate_constants.alloc_persistent(std::max<size_t>(nconstants, 1), s);
+    pk.gate_results.alloc_persistent(nresults, s);
+    CUDA_CHECK(cudaMemcpyAsync(pk.gate_calcs.get(), calcs, ncalcs * sizeof(GateCalc), cudaMemcpyHostToDevice, s));
+    if (nconstants) CUDA_CHECK(cudaMemcpyAsync(pk.gate_constants.get(), constants, nconstants * sizeof(Fr), cudaMemcpyHostToDevice, s));
+    CUDA_CHECK(cudaMemcpyAsync(pk.gate_results.get(), results, nresults * 4, cudaMemcpyHostToDevice, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
 // ---- SHPLONK bookkeeping (host) -----------------------------------------------------------------------------------------
 struct Query {
     size_t poly;
@@ -344,7 +403,8 @@ static void evaluate_h_dev(Context& ctx, Sharder& shard, const ProvingKeyDev& pk
     const size_t rows_per_rank = shard.on() ? en / ctx.world : en;
     Q.row_begin = shard.on() ? rows_per_rank * ctx.rank : 0;
     Q.row_end = Q.row_begin + rows_per_rank;
-    h_gates(Q, h, s);
+    if (pk.gate_calcs.size()) h_gates_program(Q, pk.gate_program(), h, s);
+    else h_gates(Q, h, s);
     h_permutation(Q, h, L == 0, s);
     lap(tm ? &tm->quotient : nullptr);
     if (L) {
@@ -696,7 +756,32 @@ static std::vector<uint8_t> create_proof_body(Context& ctx, const ProvingKeyDev&
     }
     // step 7: vanishing::commit (D.7): n sequential Fr::random draws = n consecutive ChaCha blocks, generated in place
     DevBuf<Fr> random_poly(n, s);
-    if (ctx.compat.random_poly_chunks == 0) {  // [UNVERIFIED-3] n sequential draws = n consecutive blocks of the main stream
+    if (rng.external()) {
+        // the host's own RngCore: the n draws are pulled through its fill_bytes (64 bytes each, in chunks), uploaded and
+        // reduced on the device; the chunk-seeded variant pulls its seeds the same way and expands them on the device
+        if (shard.on()) throw std::invalid_argument("create_proof: an external random source cannot be shared by several ranks; use the seeded entry point");
+        if (ctx.compat.random_poly_chunks == 0) {
+            const size_t piece = (size_t)1 << 16;  // draws per upload
+            std::vector<uint32_t> host(16 * std::min(piece, n));
+            DevBuf<uint32_t> words(16 * std::min(piece, n), s);
+            for (size_t lo = 0; lo < n; lo += piece) {
+                const size_t cnt = std::min(piece, n - lo);
+                rng.words(host.data(), 16 * cnt);
+                CUDA_CHECK(cudaMemcpyAsync(words.get(), host.data(), 64 * cnt, cudaMemcpyHostToDevice, s));
+                fr_from_u512(random_poly.get() + lo, words.get(), cnt, s);
+                CUDA_CHECK(cudaStreamSynchronize(s));  // `host` is refilled next
+            }
+        } else {
+            const size_t T = std::min<size_t>(ctx.compat.random_poly_chunks, n), chunk = n / T, n_chunks = T + (n % T != 0 ? 1 : 0);
+            for (size_t c = 0; c < n_chunks; ++c) {
+                uint8_t seed[32];
+                rng.fill_bytes32(seed);
+                const host::FrRandomStream sub = host::FrRandomStream::chacha20_from_seed(seed);
+                const size_t lo = c * chunk, hi = std::min(n, (c + 1) * chunk);
+                fr_random_stream(random_poly.get() + lo, hi - lo, sub.key, 0, sub.rounds, s);
+            }
+        }
+    } else if (ctx.compat.random_poly_chunks == 0) {  // [UNVERIFIED-3] n sequential draws = n consecutive blocks of the main stream
         if (!rng.aligned()) throw std::logic_error("create_proof: random stream not block aligned");
         fr_random_stream(random_poly.get(), n, rng.key, rng.block_index(), rng.rounds, s);
         rng.skip(n);

@@ -40,7 +40,24 @@ struct ProvingKeyDev {
     DevBuf<Fr> l_polys;                                  // l0, l_last, l_active_row on the extended domain [3][4n]
     std::vector<G1Affine> fixed_commitments, perm_commitments;
     Fr transcript_repr;
+    // optional generic gate program (b200zk_pk_set_gates); empty = the specialised halo2-base gate kernel
+    DevBuf<GateCalc> gate_calcs;
+    DevBuf<Fr> gate_constants;
+    DevBuf<uint32_t> gate_results;
+    GateProgramDev gate_program() const {
+        GateProgramDev p;
+        p.calcs = gate_calcs.get();
+        p.constants = gate_constants.get();
+        p.results = gate_results.get();
+        p.ncalcs = (uint32_t)gate_calcs.size();
+        p.nresults = (uint32_t)gate_results.size();
+        return p;
+    }
 };
+// validates and installs a gate program (throws std::invalid_argument): indices in range, advice rotations within the
+// proof's query set (gate columns 0..3, lookup columns 0; fixed columns 0), total degree <= Shape::degree
+void pk_set_gates(Context& ctx, ProvingKeyDev& pk, const GateCalc* calcs, size_t ncalcs, const Fr* constants, size_t nconstants,
+                  const uint32_t* results, size_t nresults);
 
 // wall-clock split of one create_proof call (seconds, stream synchronised at each boundary)
 struct ProofTimings {

@@ -31,6 +31,41 @@ __global__ void __launch_bounds__(256) h_gates_kernel(QuotientArgs Q, Fr* h) {
     f_store(h + i, v);
 }
 
+// the interpreter: one thread per extended row, intermediates in local memory (L1-resident), program and constants read
+// through the read-only path (every thread reads the same words)
+__global__ void __launch_bounds__(128) h_gates_program_kernel(QuotientArgs Q, GateProgramDev P, Fr* h) {
+    const size_t en = (size_t)4 << Q.k;
+    const size_t i = Q.row_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Q.row_end) return;
+    Fr vals[GATE_MAX_CALCS];
+    auto fetch = [&](const GateSrc& src, const Fr* done) -> Fr {
+        switch (src.kind) {
+            case GATE_SRC_CONSTANT: return f_load_ro(P.constants + src.index);
+            case GATE_SRC_INTERMEDIATE: return done[src.index];
+            case GATE_SRC_FIXED: return f_load(Q.fixed[src.index] + rot_idx(i, src.rotation, en));
+            default: return f_load(Q.advice[src.index] + rot_idx(i, src.rotation, en));
+        }
+    };
+    for (uint32_t j = 0; j < P.ncalcs; ++j) {
+        const GateCalc c = P.calcs[j];
+        const Fr a = fetch(c.a, vals);
+        Fr r;
+        switch (c.op) {
+            case GATE_ADD: r = f_add(a, fetch(c.b, vals)); break;
+            case GATE_SUB: r = f_sub(a, fetch(c.b, vals)); break;
+            case GATE_MUL: r = f_mul(a, fetch(c.b, vals)); break;
+            case GATE_SQUARE: r = f_sqr(a); break;
+            case GATE_DOUBLE: r = f_dbl(a); break;
+            case GATE_NEGATE: r = f_neg(a); break;
+            default: r = a; break;  // GATE_STORE
+        }
+        vals[j] = r;
+    }
+    Fr v = f_zero<FrCfg>();
+    for (uint32_t g = 0; g < P.nresults; ++g) v = f_add(f_mul(v, Q.y), vals[__ldg(P.results + g)]);
+    f_store(h + i, v);
+}
+
 __global__ void __launch_bounds__(256) h_permutation_kernel(QuotientArgs Q, Fr* h, int final_scale) {
     const size_t en = (size_t)4 << Q.k;
     const size_t i = Q.row_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -91,6 +126,13 @@ void h_gates(const QuotientArgs& Q, Fr* h, cudaStream_t s) {
     const size_t en = Q.row_end - Q.row_begin;
     const int prof_h = prof_begin(PROF_QUOTIENT, s, (double)en);
     h_gates_kernel<<<(unsigned)((en + 255) / 256), 256, 0, s>>>(Q, h);
+    prof_end(prof_h, s);
+    LAUNCHED(1);
+}
+void h_gates_program(const QuotientArgs& Q, const GateProgramDev& P, Fr* h, cudaStream_t s) {
+    const size_t en = Q.row_end - Q.row_begin;
+    const int prof_h = prof_begin(PROF_QUOTIENT, s, (double)en);
+    h_gates_program_kernel<<<(unsigned)((en + 127) / 128), 128, 0, s>>>(Q, P, h);
     prof_end(prof_h, s);
     LAUNCHED(1);
 }

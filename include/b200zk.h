@@ -187,6 +187,21 @@ typedef struct b200zk_pk b200zk_pk;
 B200ZK_API int b200zk_keygen(b200zk_ctx* ctx, uint32_t k, uint32_t A, uint32_t L, uint32_t F, const b200zk_fr* fixed, const uint32_t* copies,
                              size_t ncopies, b200zk_pk** out);
 B200ZK_API int b200zk_pk_free(b200zk_ctx* ctx, b200zk_pk* pk);
+/* Generic custom gates (halo2_proofs::plonk::evaluation::{GraphEvaluator, Calculation, ValueSource}):
+ * calculation j produces intermediate j from its value sources; the intermediates listed in `results` are the gate
+ * polynomials, folded into h(X) by Horner in the challenge y in list order. Installing a program replaces the built-in
+ * halo2-base gates (one `q·(a + b·c − d)` per gate column) in evaluate_h / create_proof for this key; ncalcs = 0 restores
+ * them. Column indices are those of b200zk_keygen (fixed: F constants, table, A selectors; advice: A gate, L lookup columns).
+ * The proof's query set is unchanged, so advice sources may use rotations 0..3 on gate columns and 0 on lookup columns,
+ * fixed sources rotation 0; the total degree of every gate must be <= 4 (the constraint system's degree). Limits: 128
+ * calculations, 64 constants, 64 gates. The permutation and lookup arguments are unaffected. */
+enum { B200ZK_SRC_CONSTANT = 0, B200ZK_SRC_INTERMEDIATE = 1, B200ZK_SRC_FIXED = 2, B200ZK_SRC_ADVICE = 3 };
+enum { B200ZK_CALC_ADD = 0, B200ZK_CALC_SUB = 1, B200ZK_CALC_MUL = 2, B200ZK_CALC_SQUARE = 3, B200ZK_CALC_DOUBLE = 4,
+       B200ZK_CALC_NEGATE = 5, B200ZK_CALC_STORE = 6 };
+typedef struct { uint32_t kind; uint32_t index; int32_t rotation; } b200zk_value_source;
+typedef struct { uint32_t op; b200zk_value_source a, b; } b200zk_calculation;  /* b is ignored by unary calculations */
+B200ZK_API int b200zk_pk_set_gates(b200zk_ctx* ctx, b200zk_pk* pk, const b200zk_calculation* calcs, size_t ncalcs,
+                                   const b200zk_fr* constants, size_t nconstants, const uint32_t* results, size_t nresults);
 /* vk.fixed_commitments (num_fixed points) and vk.permutation.commitments (num_perm points); either may be NULL */
 B200ZK_API int b200zk_pk_commitments(b200zk_ctx* ctx, const b200zk_pk* pk, b200zk_g1_affine* fixed_out, b200zk_g1_affine* perm_out);
 /* vk.transcript_repr: read, or override with the value the Rust side computed (opaque 32-byte scalar) */
@@ -202,6 +217,13 @@ B200ZK_API size_t b200zk_proof_size(uint32_t k, uint32_t A, uint32_t L, uint32_t
  * the stages before it — inside collectives (transfer plus waiting for the slowest peer). */
 B200ZK_API int b200zk_create_proof(b200zk_ctx* ctx, const b200zk_pk* pk, const b200zk_fr* advice, uint64_t rng_seed, uint8_t* proof_out,
                                    size_t* proof_len, double* timings);
+/* The same for ANY `RngCore` the host holds (create_proof is generic in `R: RngCore`; halo2-base passes StdRng, the seeded
+ * entry point above): `fill` is the generator's `fill_bytes` — it must write `nbytes` random bytes and return 0. Every draw,
+ * including the 2^k Fr::random draws of the random polynomial (64 bytes each), is pulled through it in upstream's order, so
+ * the proof equals the one the Rust prover makes with that generator. Single-GPU contexts only. */
+typedef int (*b200zk_rng_fill_fn)(void* user, uint8_t* out, size_t nbytes);
+B200ZK_API int b200zk_create_proof_rng(b200zk_ctx* ctx, const b200zk_pk* pk, const b200zk_fr* advice, b200zk_rng_fill_fn fill, void* user,
+                                       uint8_t* proof_out, size_t* proof_len, double* timings);
 /* same with the advice columns already resident in device memory (the witness upload excluded) */
 B200ZK_API int b200zk_create_proof_dev(b200zk_ctx* ctx, const b200zk_pk* pk, const b200zk_fr* advice_dev, uint64_t rng_seed, uint8_t* proof_out,
                                        size_t* proof_len, double* timings);

@@ -286,6 +286,22 @@ EXPORT void* oracle_keygen(void* params, uint32_t k, uint32_t A, uint32_t L, uin
     }
 }
 EXPORT void oracle_pk_free(void* pk) { delete (ProvingKey*)pk; }
+// custom gates for this key (same encoding as b200zk_pk_set_gates: 7 uint32 per calculation); ncalcs = 0 clears them
+EXPORT void oracle_pk_set_gates(void* pkp, const uint32_t* calcs, size_t ncalcs, const u64* constants, size_t nconstants, const uint32_t* results,
+                                size_t nresults) {
+    GateProgram& g = ((ProvingKey*)pkp)->vk.gates;
+    g = GateProgram();
+    for (size_t j = 0; j < ncalcs; ++j) {
+        const uint32_t* w = calcs + 7 * j;
+        g.calcs.push_back(GateCalculation{w[0], GateSource{w[1], w[2], (int32_t)w[3]}, GateSource{w[4], w[5], (int32_t)w[6]}});
+    }
+    for (size_t j = 0; j < nconstants; ++j) {
+        Fr c;
+        memcpy(c.l, constants + 4 * j, 32);
+        g.constants.push_back(c);
+    }
+    g.results.assign(results, results + nresults);
+}
 EXPORT void oracle_pk_transcript_repr(void* pk, u64* out) { memcpy(out, ((ProvingKey*)pk)->vk.transcript_repr.l, 32); }
 // which: 0 fixed commitments, 1 permutation commitments, 2 sigma values column j (n Fr), 3 fixed coset i, 4 sigma coset j,
 //        5 l0, 6 l_last, 7 l_active_row

@@ -82,10 +82,57 @@ struct Assembly {
     }
 };
 
+// Generic gate program (upstream evaluation::{GraphEvaluator, Calculation, ValueSource}): calculation j
+// produces intermediate j; the intermediates listed in `results` are the gate polynomials, folded by Horner in y in list
+// order. Same encoding as the product's b200zk_calculation. Empty = the halo2-base gates q·(a + b·c − d).
+struct GateSource {
+    uint32_t kind, index;  // 0 constant, 1 intermediate, 2 fixed column, 3 advice column
+    int32_t rotation;
+};
+struct GateCalculation {
+    uint32_t op;  // 0 add, 1 sub, 2 mul, 3 square, 4 double, 5 negate, 6 store
+    GateSource a, b;
+};
+struct GateProgram {
+    std::vector<GateCalculation> calcs;
+    std::vector<Fr> constants;
+    std::vector<uint32_t> results;
+    bool empty() const { return calcs.empty(); }
+    // v <- fold of the gate values into v; `fixed(col, rot)` / `advice(col, rot)` supply the column values at this row / point
+    template <class FixedFn, class AdviceFn>
+    Fr fold(Fr v, const Fr& y, FixedFn&& fixed, AdviceFn&& advice) const {
+        std::vector<Fr> vals(calcs.size());
+        auto fetch = [&](const GateSource& s) -> Fr {
+            switch (s.kind) {
+                case 0: return constants[s.index];
+                case 1: return vals[s.index];
+                case 2: return fixed(s.index, s.rotation);
+                default: return advice(s.index, s.rotation);
+            }
+        };
+        for (size_t j = 0; j < calcs.size(); ++j) {
+            const GateCalculation& c = calcs[j];
+            const Fr a = fetch(c.a);
+            switch (c.op) {
+                case 0: vals[j] = a + fetch(c.b); break;
+                case 1: vals[j] = a - fetch(c.b); break;
+                case 2: vals[j] = a * fetch(c.b); break;
+                case 3: vals[j] = a.sqr(); break;
+                case 4: vals[j] = a + a; break;
+                case 5: vals[j] = -a; break;
+                default: vals[j] = a; break;
+            }
+        }
+        for (uint32_t g : results) v = v * y + vals[g];
+        return v;
+    }
+};
+
 struct VerifyingKey {
     Shape shape;
     std::vector<G1Affine> fixed_commitments, perm_commitments;
     Fr transcript_repr;
+    GateProgram gates;  // optional custom gates (part of the constraint system, hence of the vk)
 };
 
 struct ProvingKey {
@@ -386,6 +433,11 @@ inline Poly evaluate_h(const ProvingKey& pk, const Domain& dom, const std::vecto
     parallel_chunks(en, [&](size_t b, size_t e, int) {
         for (size_t i = b; i < e; ++i) {
             Fr v = h[i];
+            if (!pk.vk.gates.empty()) {
+                h[i] = pk.vk.gates.fold(v, ch.y, [&](uint32_t col, int r) { return pk.fixed_cosets[col][rot(i, r)]; },
+                                        [&](uint32_t col, int r) { return advice_cosets[col][rot(i, r)]; });
+                continue;
+            }
             for (uint32_t c = 0; c < sh.A; ++c) {
                 const Poly& a = advice_cosets[c];
                 Fr g = pk.fixed_cosets[sh.selector_col(c)][i] * (a[i] + a[rot(i, 1)] * a[rot(i, 2)] - a[rot(i, 3)]);
@@ -814,8 +866,11 @@ inline std::string verify_proof(const Params& params, const VerifyingKey& vk, co
         auto advice_eval = [&](uint32_t col, int r) -> const Fr& { return col < sh.A ? advice_e[4 * col + r] : advice_e[4 * sh.A + (col - sh.A)]; };
         Fr acc = Fr::zero();
         auto push = [&](const Fr& e) { acc = acc * y + e; };
-        for (uint32_t c = 0; c < sh.A; ++c)
-            push(fixed_e[sh.selector_col(c)] * (advice_eval(c, 0) + advice_eval(c, 1) * advice_eval(c, 2) - advice_eval(c, 3)));
+        if (!vk.gates.empty())
+            acc = vk.gates.fold(acc, y, [&](uint32_t col, int) { return fixed_e[col]; }, [&](uint32_t col, int r) { return advice_eval(col, r); });
+        else
+            for (uint32_t c = 0; c < sh.A; ++c)
+                push(fixed_e[sh.selector_col(c)] * (advice_eval(c, 0) + advice_eval(c, 1) * advice_eval(c, 2) - advice_eval(c, 3)));
         uint32_t ns = sh.num_sets();
         push(l_0 * (Fr::one() - z_e[0].e));
         push((z_e[ns - 1].e.sqr() - z_e[ns - 1].e) * l_last);

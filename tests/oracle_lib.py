@@ -258,6 +258,17 @@ class ProvingKey:
         lib().oracle_pk_transcript_repr(ctypes.c_void_p(self.h), ptr(out))
         return out
 
+    def set_gates(self, calcs, constants=(), results=()):
+        """Custom gates (same encoding as b200zk's ProvingKey.set_gates); used by evaluate_h, create_proof and verify."""
+        arr = np.zeros((len(calcs), 7), dtype=np.uint32)
+        for j, (op, a, b) in enumerate(calcs):
+            b = b if b is not None else (0, 0, 0)
+            arr[j] = [op, a[0], a[1], np.int32(a[2]).astype(np.uint32), b[0], b[1], np.int32(b[2]).astype(np.uint32)]
+        cs = np.ascontiguousarray(np.asarray(constants, dtype=np.uint64).reshape(-1, 4)) if len(constants) else np.zeros((0, 4), dtype=np.uint64)
+        rs = np.ascontiguousarray(results, dtype=np.uint32)
+        lib().oracle_pk_set_gates(ctypes.c_void_p(self.h), ptr(arr), ctypes.c_size_t(len(calcs)), ptr(cs), ctypes.c_size_t(len(cs)), ptr(rs),
+                                  ctypes.c_size_t(len(rs)))
+
     def create_proof(self, advice, rng_seed=0):
         advice = np.ascontiguousarray(advice, dtype=np.uint64)
         size = lib().oracle_proof_size(*self.shape)

@@ -88,6 +88,40 @@ def test_lookup_failure_is_reported(ctx):
     assert e.value.code == b200zk.ESYNTH
 
 
+def test_external_rng_callback_reproduces_the_seeded_proof(ctx):
+    """b200zk_create_proof_rng serves any host RngCore through its fill_bytes. Fed with the StdRng::seed_from_u64 keystream
+    (ChaCha12, from the oracle's generator) it must reproduce the seeded entry point byte for byte — every draw, including
+    the n draws of the random polynomial, is made in the same order — under both random-polynomial variants."""
+    import ctypes
+
+    k, A, L, F = 8, 3, 1, 1
+    fixed, advice, copies = b200zk.synth_circuit(k, A, L, F, seed=5)
+    setup(ctx, k)
+    pk = ctx.keygen(k, A, L, F, fixed, copies)
+    seed = np.zeros(32, dtype=np.uint8)
+    O.lib().oracle_std_rng_seed(ctypes.c_uint64(9), O.ptr(seed))
+    nwords = 16 * ((1 << k) + 4096)
+    words = np.zeros(nwords, dtype=np.uint32)
+    O.lib().oracle_chacha_words(seed.tobytes(), 12, ctypes.c_size_t(nwords), O.ptr(words))
+    stream = words.tobytes()
+    try:
+        for chunks in (0, 3):
+            ctx.set_compat(0, chunks)
+            pos = [0]
+
+            def fill(nbytes):
+                out = stream[pos[0] : pos[0] + nbytes]
+                pos[0] += nbytes
+                return out
+
+            got = b200zk.create_proof_rng(pk, advice, fill)
+            assert got == pk.create_proof(advice, 9), chunks
+            assert pos[0] > 64 * (1 << k) or chunks  # the random polynomial's draws went through the callback
+    finally:
+        ctx.set_compat(0, 0)
+    pk.close()
+
+
 def test_unsatisfied_witness_proof_is_rejected(ctx):
     """The prover does not check satisfiability (like upstream); the verifier must reject."""
     k, A, L, F = 8, 2, 1, 1

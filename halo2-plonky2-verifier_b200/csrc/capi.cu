@@ -864,9 +864,10 @@ static int create_proof_impl(b200zk_ctx* ctx, const b200zk_pk* pk, const b200zk_
                 if (cudaMemcpyPeer(ctx->group_advice[r - 1], rc->c.device, advice, ctx->c.device, bytes) != cudaSuccess) return B200ZK_ECUDA;
                 adv[r] = (const b200zk_fr*)ctx->group_advice[r - 1];
             }
+        std::vector<std::vector<double>> tms(N, std::vector<double>(10, 0.0));  // every rank runs in the same (timed or untimed) mode
         return group_call(ctx, [&](b200zk_ctx* rctx, int rank) -> int {
             return create_proof_impl(rctx, pk->rank_pk(rank), adv[rank], on_device, rng_seed, rank == 0 ? proof_out : proofs[rank].data(),
-                                     rank == 0 ? proof_len : &lens[rank], rank == 0 ? timings : nullptr);
+                                     rank == 0 ? proof_len : &lens[rank], !timings ? nullptr : rank == 0 ? timings : tms[rank].data());
         });
     }
     API_BEGIN(ctx)

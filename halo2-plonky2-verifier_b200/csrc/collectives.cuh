@@ -170,9 +170,9 @@ struct Sharder {
     // NVSwitch) — only the payload moves and nothing is staged. Even ownership: one all-gather over an owner-major staging
     // buffer (stage[r][j] = the j-th column owned by rank r = column first(r) + j·world).
     // `st` = the stream the collective runs on (the context's stream, or its comm stream for an overlapped exchange).
-    void allgather_columns_on(cudaStream_t st, Fr* base, size_t ncols, size_t len, size_t off) {
+    void allgather_columns_on(cudaStream_t st, Fr* base, size_t ncols, size_t len, size_t off, bool broadcasts) {
         Nccl& nc = nccl();
-        if (ncols % ctx.world != 0 || st != ctx.stream) {
+        if (ncols % ctx.world != 0 || broadcasts) {  // NB: the choice must not depend on anything rank-local (e.g. tracing)
             nc.check(nc.GroupStart(), "GroupStart");
             for (size_t c = 0; c < ncols; ++c)
                 nc.check(nc.Broadcast(base + c * len, base + c * len, len * sizeof(Fr), 1, owner(c, off), nc.comm, st), "Broadcast");
@@ -194,7 +194,7 @@ struct Sharder {
     void allgather_columns(Fr* base, size_t ncols, size_t len, size_t off = 0) {
         if (!on() || ncols == 0) return;
         CommSpan span(ctx);
-        allgather_columns_on(ctx.stream, base, ncols, len, off);
+        allgather_columns_on(ctx.stream, base, ncols, len, off, false);
     }
     // The same exchange on the context's comm stream: it starts once everything queued on the main stream so far is done and
     // runs beside the kernels launched afterwards; the main stream must not touch the columns until async_wait(). Several
@@ -202,13 +202,14 @@ struct Sharder {
     // bracketed span.)
     void allgather_columns_async(Fr* base, size_t ncols, size_t len, size_t off = 0) {
         if (!on() || ncols == 0) return;
-        if (ctx.comm_trace || !ctx.comm_stream) {
-            allgather_columns(base, ncols, len, off);
+        if (ctx.comm_trace || !ctx.comm_stream) {  // same collectives (grouped broadcasts), on the main stream
+            CommSpan span(ctx);
+            allgather_columns_on(ctx.stream, base, ncols, len, off, true);
             return;
         }
         CUDA_CHECK(cudaEventRecord(ctx.comm_fork, ctx.stream));
         CUDA_CHECK(cudaStreamWaitEvent(ctx.comm_stream, ctx.comm_fork, 0));
-        allgather_columns_on(ctx.comm_stream, base, ncols, len, off);
+        allgather_columns_on(ctx.comm_stream, base, ncols, len, off, true);
         ctx.comm_pending = true;
     }
     void async_wait() {

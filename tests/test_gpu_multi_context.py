@@ -63,6 +63,8 @@ def test_group_context_matches_single_gpu_and_oracle(ndev, shape):
         got = pk2.create_proof(advice, 7)
         assert got == want
         assert pk2.create_proof(advice, 7) == want  # and again: arenas, communicators and staging buffers are reusable
+        timed, stages = pk2.create_proof(advice, 7, timings=True)  # the timed mode (collectives bracketed) on every rank alike
+        assert timed == want and stages["msm"] > 0
         params = O.Params.setup(k)
         opk = O.ProvingKey(params, k, A, L, F, fixed, copies)
         assert got == opk.create_proof(advice, 7)

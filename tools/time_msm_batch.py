@@ -41,4 +41,4 @@ for name in ("uniform", "small21"):
         print(name, "batch", B, res[f"{name}/B{B}"], flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/time_msm_batch.json", "w"), indent=1)
-os._exit(0)
+ctx.close()

@@ -191,6 +191,18 @@ struct Sharder {
                 CUDA_CHECK(cudaMemcpyAsync(base + c * len, stage.get() + (r * per + j) * len, len * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx.stream));
         }
     }
+    // rank r holds columns [ncols·r/world, ncols·(r+1)/world) of base: afterwards every rank holds all of them
+    void broadcast_blocks(Fr* base, size_t ncols, size_t len) {
+        if (!on() || ncols == 0) return;
+        CommSpan span(ctx);
+        Nccl& nc = nccl();
+        nc.check(nc.GroupStart(), "GroupStart");
+        for (int r = 0; r < ctx.world; ++r) {
+            const size_t lo = ncols * (size_t)r / ctx.world, hi = ncols * (size_t)(r + 1) / ctx.world;
+            if (hi > lo) nc.check(nc.Broadcast(base + lo * len, base + lo * len, (hi - lo) * len * sizeof(Fr), 1, r, nc.comm, ctx.stream), "Broadcast");
+        }
+        nc.check(nc.GroupEnd(), "GroupEnd");
+    }
     void allgather_columns(Fr* base, size_t ncols, size_t len, size_t off = 0) {
         if (!on() || ncols == 0) return;
         CommSpan span(ctx);

@@ -589,10 +589,12 @@ static std::vector<uint8_t> create_proof_body(Context& ctx, const ProvingKeyDev&
     // stream while that quarter is being committed
     const uint32_t ahead = (!advice_on_device && !shard.on() && ctx.copy_stream && NA >= 8) ? NA / 4 : NA;
     if (shard.on() && !advice_on_device) {
-        // every rank holds the host witness: each uploads only its share of the columns over PCIe and the rest arrives over NVLink
-        for (uint32_t c = 0; c < NA; ++c)
-            if (shard.mine(c)) upload(c, c + 1, s, true);
-        shard.allgather_columns(advice.get(), NA, n);
+        // every rank holds the host witness: each uploads only its share over PCIe — ONE contiguous block of columns, so a
+        // pageable buffer goes through a single staged upload — and the rest arrives over NVLink (in-place broadcasts of the
+        // blocks, one NCCL group)
+        const uint32_t c_lo = (uint32_t)((uint64_t)NA * ctx.rank / ctx.world), c_hi = (uint32_t)((uint64_t)NA * (ctx.rank + 1) / ctx.world);
+        upload(c_lo, c_hi, s, true);
+        shard.broadcast_blocks(advice.get(), NA, n);
         blind_rows(0, NA, s);
         fork_advice_transforms(nullptr);
     } else if (ahead < NA) {

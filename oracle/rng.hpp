@@ -2,7 +2,7 @@
 // rand_core::SeedableRng::seed_from_u64 (PCG32 expansion) and halo2curves `Fr::random`
 // (SURVEY.md Appendix A.1). Callers upstream: halo2-base `gen_srs` (ChaCha20, seed [0;32]) and
 // `gen_proof` (StdRng::seed_from_u64(0) = ChaCha12), reached from verifier/src/stark/mod.rs:543,593.
-// KAT: ChaCha20 zero-key block 0 (RFC 7539 §A.1 vector 1) in tests/test_oracle_host.py.
+// KAT: ChaCha20 zero-key block 0 (RFC 7539 §A.1 vector 1) in tests/test_oracle_kat.py.
 #pragma once
 #include "field.hpp"
 

@@ -1,7 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY. Restatement of halo2_proofs::transcript::{Blake2bWrite,
 // Blake2bRead, Challenge255} over a from-scratch BLAKE2b
 // (RFC 7693) with personalisation. KAT: Python hashlib.blake2b(digest_size=64,
-// person=b"Halo2-Transcript") in tests/test_oracle_host.py.
+// person=b"Halo2-Transcript") in tests/test_oracle_kat.py.
 #pragma once
 #include <stdexcept>
 

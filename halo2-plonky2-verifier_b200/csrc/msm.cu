@@ -30,6 +30,7 @@
 namespace b200zk {
 
 constexpr uint32_t INVALID_KEY = 0xffffffffu;
+constexpr int MSM_AFFINE_ROUNDS_DEFAULT = 0;  // batched-affine pre-reduction rounds for dense columns (see below)
 
 struct MsmConfig {
     uint32_t c, W, B;   // window bits, windows, buckets per window (2^(c-1))
@@ -222,11 +223,22 @@ constexpr int ACC_T_MIN = 16, ACC_T_MAX = 64;  // entries per thread, level 1 (c
 constexpr int COMB_T = 32;       // fan-in of the head combine levels (one warp per COMB_T partial sums)
 constexpr int ACC_THREADS = 128;
 
+// `entries` == nullptr: the list is `bases` itself (entry p = point p, no sign) — the output of the batched-affine rounds;
+// `total_dev` != nullptr: the list length is read from the device (the host only knows an upper bound, which sizes the grid)
 __global__ void __launch_bounds__(ACC_THREADS) msm_accumulate_kernel(const G1Affine* bases, const uint32_t* entries, const uint32_t* offsets,
                                                                      uint32_t nb, uint32_t total, uint32_t chunk, G1X* bucket_sums, G1X* heads,
-                                                                     uint32_t* head_keys) {
+                                                                     uint32_t* head_keys, const uint32_t* total_dev) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t p0l = (uint64_t)t * chunk;
+    if (total_dev) {
+        const uint32_t actual = __ldg(total_dev);
+        if (p0l >= total) return;   // beyond the grid's nominal range: no head slot either
+        if (p0l >= actual) {        // inside the nominal range but past the real end: an empty head slot
+            head_keys[t] = INVALID_KEY;
+            return;
+        }
+        total = actual;
+    }
     if (p0l >= total) return;
     const uint32_t p0 = (uint32_t)p0l;
     const uint32_t p1 = total - p0 > chunk ? p0 + chunk : total;
@@ -237,13 +249,13 @@ __global__ void __launch_bounds__(ACC_THREADS) msm_accumulate_kernel(const G1Aff
     G1X acc = g1x_identity();
     // software pipeline: the entry and the 64-byte base of the NEXT addition are requested before the current one starts —
     // the base is a random gather from the window table (mostly DRAM) and would otherwise sit in front of every addition
-    uint32_t e_next = __ldg(entries + p0);
+    uint32_t e_next = entries ? __ldg(entries + p0) : p0;
     G1Affine b_next = g1a_load_ro(bases + (e_next & 0x7fffffffu));
     for (uint32_t p = p0; p < p1; ++p) {
         const uint32_t e = e_next;
         G1Affine b = b_next;
         if (p + 1 < p1) {
-            e_next = __ldg(entries + p + 1);
+            e_next = entries ? __ldg(entries + p + 1) : p + 1;
             b_next = g1a_load_ro(bases + (e_next & 0x7fffffffu));
         }
         if (p == end) {
@@ -259,6 +271,139 @@ __global__ void __launch_bounds__(ACC_THREADS) msm_accumulate_kernel(const G1Aff
         acc = g1x_add_affine(acc, b);
     }
     g1x_store(started_before ? heads + t : bucket_sums + cur, acc);
+}
+
+// ---- batched-affine pre-reduction ----------------------------------------------------------------------------------------
+// Before the XYZZ accumulation, R rounds of pairwise AFFINE additions shrink every bucket's run of the sorted list:
+// round r adds elements 2i and 2i+1 of each bucket (an odd last element is copied), so a bucket of c entries has
+// ceil(c / 2^R) afterwards and (1 − 2^-R) of all additions are done at 5 products + 1 square + a share of ONE inversion
+// instead of the ≈ 9.2 product-equivalents of an XYZZ mixed addition. The inversions of a round are batched over the whole
+// column (Montgomery's trick, two levels): kernel A walks K outputs per thread, multiplies up the denominators x2 − x1
+// (prefix products to scratch, the thread's product to `roots`), the roots are inverted by strided groups with one
+// Fermat inversion per group (all lanes busy), kernel C walks the same outputs backwards, peels off each denominator's
+// inverse and writes the sums. Bucket runs stay contiguous: off_dst = scan(ceil(cnt_src / 2)).
+// Affine addition has no identity and no doubling: an identity operand or equal x-coordinates (P + P, P − P: impossible
+// for distinct SRS points, possible for caller-supplied bases) raise `flag` and the column is redone on the XYZZ path.
+// number of rounds (0 = off): B200ZK_MSM_AFFINE overrides the default
+static int msm_affine_rounds() {
+    static const int rounds = [] {
+        const char* e = getenv("B200ZK_MSM_AFFINE");
+        const int v = e ? atoi(e) : MSM_AFFINE_ROUNDS_DEFAULT;
+        return v < 0 ? 0 : (v > 6 ? 6 : v);
+    }();
+    return rounds;
+}
+constexpr int BA_K = 16;        // outputs per thread
+constexpr int BA_THREADS = 128;
+__global__ void ba_counts_kernel(const uint32_t* off_src, uint32_t nb, uint32_t* cnt_dst) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > nb) return;
+    cnt_dst[b] = b == nb ? 0u : (off_src[b + 1] - off_src[b] + 1u) >> 1;
+}
+struct BaSrc {
+    const G1Affine* pts;       // round >= 2: the previous round's points; round 1: the (window-table) bases
+    const uint32_t* entries;   // round 1: sorted entries (index | sign << 31); nullptr afterwards
+};
+DEV G1Affine ba_fetch(const BaSrc& S, uint32_t s) {
+    if (!S.entries) return g1a_load_ro(S.pts + s);
+    const uint32_t e = __ldg(S.entries + s);
+    G1Affine p = g1a_load_ro(S.pts + (e & 0x7fffffffu));
+    if (e >> 31) p.y = f_neg(p.y);
+    return p;
+}
+DEV Fq ba_fetch_x(const BaSrc& S, uint32_t s) {
+    if (!S.entries) return f_load_ro(&S.pts[s].x);
+    return f_load_ro(&S.pts[__ldg(S.entries + s) & 0x7fffffffu].x);
+}
+// kernel A: prefix products of the denominators of this thread's outputs
+__global__ void __launch_bounds__(BA_THREADS) ba_prefix_kernel(BaSrc S, const uint32_t* off_src, const uint32_t* off_dst, uint32_t nb, Fq* pref, Fq* roots,
+                                                               uint32_t* flag) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t L = __ldg(off_dst + nb);
+    const uint64_t j0l = (uint64_t)t * BA_K;
+    if (j0l >= L) return;
+    const uint32_t j0 = (uint32_t)j0l, j1 = L - j0 > (uint32_t)BA_K ? j0 + BA_K : L;
+    uint32_t b = find_bucket(off_dst, nb, j0), end = __ldg(off_dst + b + 1), dbase = __ldg(off_dst + b), sbase = __ldg(off_src + b),
+             scnt = __ldg(off_src + b + 1) - sbase;
+    Fq run = f_one<FqCfg>();
+    uint32_t bad = 0;
+    for (uint32_t j = j0; j < j1; ++j) {
+        if (j == end) {
+            b = find_bucket(off_dst, nb, j);
+            end = __ldg(off_dst + b + 1);
+            dbase = __ldg(off_dst + b);
+            sbase = __ldg(off_src + b);
+            scnt = __ldg(off_src + b + 1) - sbase;
+        }
+        const uint32_t i2 = 2 * (j - dbase);
+        f_store(pref + j, run);
+        if (i2 + 1 < scnt) {
+            const Fq x1 = ba_fetch_x(S, sbase + i2), x2 = ba_fetch_x(S, sbase + i2 + 1);
+            const Fq dx = f_sub(x2, x1);
+            if (f_is_zero(dx)) bad = 1;          // P + P or P − P (or two identities)
+            else run = f_mul(run, dx);
+        }
+    }
+    f_store(roots + t, run);
+    if (bad) atomicOr(flag, 1u);
+}
+// strided batch inversion of the roots (nonzero by construction): thread g owns roots g, g + G, ...
+__global__ void __launch_bounds__(128) ba_invert_roots_kernel(Fq* roots, Fq* scratch, const uint32_t* off_dst, uint32_t nb, uint32_t G) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t L = __ldg(off_dst + nb), n = (L + BA_K - 1) / BA_K;
+    if (g >= G || g >= n) return;
+    Fq acc = f_one<FqCfg>();
+    for (uint32_t i = g; i < n; i += G) {
+        f_store(scratch + i, acc);
+        acc = f_mul(acc, f_load(roots + i));
+    }
+    acc = f_inv(acc);
+    const uint32_t cnt = (n - g + G - 1) / G;
+    for (uint32_t q = cnt; q-- > 0;) {
+        const uint32_t i = g + q * G;
+        const Fq v = f_load(roots + i);
+        f_store(roots + i, f_mul(acc, f_load(scratch + i)));
+        acc = f_mul(acc, v);
+    }
+}
+// kernel C: the sums (outputs walked backwards: inverse of denominator j = inv_run · pref[j], inv_run ·= dx_j)
+__global__ void __launch_bounds__(BA_THREADS) ba_add_kernel(BaSrc S, const uint32_t* off_src, const uint32_t* off_dst, uint32_t nb, const Fq* pref,
+                                                            const Fq* roots_inv, G1Affine* dst, uint32_t* flag) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t L = __ldg(off_dst + nb);
+    const uint64_t j0l = (uint64_t)t * BA_K;
+    if (j0l >= L) return;
+    const uint32_t j0 = (uint32_t)j0l, j1 = L - j0 > (uint32_t)BA_K ? j0 + BA_K : L;
+    uint32_t b = find_bucket(off_dst, nb, j1 - 1), dbase = __ldg(off_dst + b), sbase = __ldg(off_src + b), scnt = __ldg(off_src + b + 1) - sbase;
+    Fq inv_run = f_load(roots_inv + t);
+    uint32_t bad = 0;
+    for (uint32_t j = j1; j-- > j0;) {
+        if (j < dbase) {
+            b = find_bucket(off_dst, nb, j);
+            dbase = __ldg(off_dst + b);
+            sbase = __ldg(off_src + b);
+            scnt = __ldg(off_src + b + 1) - sbase;
+        }
+        const uint32_t i2 = 2 * (j - dbase);
+        const G1Affine p1 = ba_fetch(S, sbase + i2);
+        if (g1_is_identity(p1)) bad = 1;
+        G1Affine o = p1;
+        if (i2 + 1 < scnt) {
+            const G1Affine p2 = ba_fetch(S, sbase + i2 + 1);
+            if (g1_is_identity(p2)) bad = 1;
+            const Fq dx = f_sub(p2.x, p1.x);
+            if (!f_is_zero(dx)) {
+                const Fq inv = f_mul(inv_run, f_load(pref + j));
+                inv_run = f_mul(inv_run, dx);
+                const Fq lam = f_mul(f_sub(p2.y, p1.y), inv);
+                o.x = f_sub(f_sub(f_sqr(lam), p1.x), p2.x);
+                o.y = f_sub(f_mul(lam, f_sub(p1.x, o.x)), p1.y);
+            }
+        }
+        f_store(&dst[j].x, o.x);
+        f_store(&dst[j].y, o.y);
+    }
+    if (bad) atomicOr(flag, 1u);
 }
 
 // Segmented sum of a key-sorted list of partial sums (INVALID_KEY entries are holes), one entry per lane: a 5-step shuffle
@@ -426,7 +571,22 @@ struct MsmSlot {
     bool empty = false;              // the column in flight has no points on this rank
     DevBuf<uint32_t> counters, offsets, entries, keys_a, keys_b;
     DevBuf<G1X> heads_a, heads_b;
-    void alloc(Context& ctx, uint32_t nb, size_t max_entries) {
+    // batched-affine rounds (optional): ping-pong offsets and points, prefix products, per-thread roots, exception flag
+    int affine_rounds = 0;
+    DevBuf<uint32_t> ba_off[2];
+    DevBuf<G1Affine> ba_pts[2];
+    DevBuf<Fq> ba_pref, ba_roots, ba_rscratch;
+    void alloc(Context& ctx, uint32_t nb, size_t max_entries, int rounds) {
+        affine_rounds = rounds;
+        if (rounds > 0) {
+            const size_t l2 = (max_entries + nb) / 2 + 2, l3 = (l2 + nb) / 2 + 2;
+            for (auto& o : ba_off) o.alloc(nb + 1, ctx.stream);
+            ba_pts[0].alloc(l2, ctx.stream);
+            if (rounds > 1) ba_pts[1].alloc(l3, ctx.stream);
+            ba_pref.alloc(l2, ctx.stream);
+            ba_roots.alloc(l2 / BA_K + 2, ctx.stream);
+            ba_rscratch.alloc(l2 / BA_K + 2, ctx.stream);
+        }
         const size_t t1 = (max_entries + ACC_T_MIN - 1) / ACC_T_MIN + 1, t2 = (t1 + COMB_T - 1) / COMB_T + 1;
         counters.alloc(nb + 1, ctx.stream);
         offsets.alloc(nb + 1, ctx.stream);
@@ -450,7 +610,9 @@ static void msm_issue_count(MsmSlot& sl, const Fr* scalars, size_t n, const MsmC
     CUDA_CHECK(cudaMemcpyAsync(sl.counters.get(), sl.offsets.get(), (nb + 1) * 4, cudaMemcpyDeviceToDevice, s));
     CUDA_CHECK(cudaEventRecord(sl.ev, s));
 }
-static void msm_issue_accumulate(MsmSlot& sl, const G1Affine* bases, const Fr* scalars, size_t n, const MsmConfig& cfg, G1X* bucket_sums) {
+// `flag_dev`: where the affine rounds report an exceptional pair for this column (nullptr: XYZZ path only)
+static void msm_issue_accumulate(MsmSlot& sl, const G1Affine* bases, const Fr* scalars, size_t n, const MsmConfig& cfg, G1X* bucket_sums,
+                                 uint32_t* flag_dev) {
     cudaStream_t s = sl.st;
     const uint32_t nb = cfg.groups * cfg.B;
     if (sl.empty) return;
@@ -459,14 +621,47 @@ static void msm_issue_accumulate(MsmSlot& sl, const G1Affine* bases, const Fr* s
     if (total == 0) return;
     msm_digits_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(scalars, n, cfg, sl.counters.get(), sl.entries.get(), 1);
     ++g_launch_count;
+    // dense columns (>= 8 entries per bucket on average) first go through the batched-affine rounds
+    const G1Affine* acc_bases = bases;
+    const uint32_t* acc_entries = sl.entries.get();
+    const uint32_t* acc_offsets = sl.offsets.get();
+    const uint32_t* acc_total_dev = nullptr;
+    uint32_t acc_total = total;
+    const bool affine = flag_dev != nullptr && sl.affine_rounds > 0 && (uint64_t)total >= (uint64_t)8 * nb;
+    const int prof_h = prof_begin(PROF_MSM_ACCUMULATE, s, (double)total);
+    if (affine) {
+        BaSrc src{bases, sl.entries.get()};
+        const uint32_t* off_src = sl.offsets.get();
+        uint64_t lub = total;
+        for (int r = 0; r < sl.affine_rounds; ++r) {
+            uint32_t* off_dst = sl.ba_off[r & 1].get();
+            G1Affine* dst = sl.ba_pts[r & 1].get();
+            lub = (lub + nb) / 2 + 1;  // upper bound of the round's output length (the exact one stays on the device)
+            ba_counts_kernel<<<(nb + 1 + 255) / 256, 256, 0, s>>>(off_src, nb, sl.counters.get());
+            ++g_launch_count;
+            exclusive_scan_u32(sl.counters.get(), off_dst, nb + 1, s);
+            const uint32_t nt = (uint32_t)((lub + BA_K - 1) / BA_K), G = std::max<uint32_t>(1, nt / 64);
+            ba_prefix_kernel<<<(nt + BA_THREADS - 1) / BA_THREADS, BA_THREADS, 0, s>>>(src, off_src, off_dst, nb, sl.ba_pref.get(), sl.ba_roots.get(), flag_dev);
+            ba_invert_roots_kernel<<<(G + 127) / 128, 128, 0, s>>>(sl.ba_roots.get(), sl.ba_rscratch.get(), off_dst, nb, G);
+            ba_add_kernel<<<(nt + BA_THREADS - 1) / BA_THREADS, BA_THREADS, 0, s>>>(src, off_src, off_dst, nb, sl.ba_pref.get(), sl.ba_roots.get(), dst, flag_dev);
+            g_launch_count += 3;
+            CUDA_CHECK(cudaGetLastError());
+            src = BaSrc{dst, nullptr};
+            off_src = off_dst;
+        }
+        acc_bases = src.pts;
+        acc_entries = nullptr;
+        acc_offsets = off_src;
+        acc_total_dev = off_src + nb;
+        acc_total = (uint32_t)lub;
+    }
     // chunk length: long chunks halve the head list for big columns, short ones keep small columns (1–2 M entries) wide
     // enough to fill 148 SMs
     uint32_t chunk = ACC_T_MAX;
-    while (chunk > (uint32_t)ACC_T_MIN && (uint64_t)total / chunk < (uint64_t)148 * 16 * 32) chunk >>= 1;
-    const uint32_t nthreads = (uint32_t)(((uint64_t)total + chunk - 1) / chunk);
-    const int prof_h = prof_begin(PROF_MSM_ACCUMULATE, s, (double)total);
-    msm_accumulate_kernel<<<(nthreads + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, s>>>(bases, sl.entries.get(), sl.offsets.get(), nb, total, chunk, bucket_sums,
-                                                                                              sl.heads_a.get(), sl.keys_a.get());
+    while (chunk > (uint32_t)ACC_T_MIN && (uint64_t)acc_total / chunk < (uint64_t)148 * 16 * 32) chunk >>= 1;
+    const uint32_t nthreads = (uint32_t)(((uint64_t)acc_total + chunk - 1) / chunk);
+    msm_accumulate_kernel<<<(nthreads + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, s>>>(acc_bases, acc_entries, acc_offsets, nb, acc_total, chunk, bucket_sums,
+                                                                                              sl.heads_a.get(), sl.keys_a.get(), acc_total_dev);
     prof_end(prof_h, s);
     ++g_launch_count;
     CUDA_CHECK(cudaGetLastError());
@@ -624,11 +819,15 @@ static void msm_batch_core(Context& ctx, const G1Affine* const* col_bases, const
                     cudaStreamSynchronize(c.stream);
                 }
             } drain{ctx, nslots};
+            // batched-affine rounds for dense columns (merged-table configurations; B200ZK_MSM_AFFINE=0 switches them off)
+            const int affine_rounds = cfg.merged ? msm_affine_rounds() : 0;
+            DevBuf<uint32_t> col_flags(affine_rounds ? nc : 0, s);
+            if (affine_rounds) CUDA_CHECK(cudaMemsetAsync(col_flags.get(), 0, nc * 4, s));
             for (int q = 0; q < nslots; ++q) {
                 slots[q].st = q == 0 ? s : ctx.aux_streams[q - 1];
                 slots[q].ev = ctx.msm_events[q];
                 slots[q].total_host = ctx.pinned_u32 + q;
-                slots[q].alloc(ctx, nb, max_len * cfg.W);
+                slots[q].alloc(ctx, nb, max_len * cfg.W, affine_rounds);
             }
             if (nslots > 1) {  // the aux streams may touch the buffers only after everything queued so far on the main stream
                 CUDA_CHECK(cudaEventRecord(ctx.msm_fork, s));
@@ -639,7 +838,8 @@ static void msm_batch_core(Context& ctx, const G1Affine* const* col_bases, const
             for (size_t j = 0; j < nc; ++j) {
                 MsmSlot& sl = slots[j % nslots];
                 const size_t col = c0 + j;
-                msm_issue_accumulate(sl, col_bases[col] + lo_of(col), cols[col] + lo_of(col), len_of(col), cfg, bucket_sums.get() + j * nb);
+                msm_issue_accumulate(sl, col_bases[col] + lo_of(col), cols[col] + lo_of(col), len_of(col), cfg, bucket_sums.get() + j * nb,
+                                     affine_rounds ? col_flags.get() + j : nullptr);
                 if (j + nslots < nc) count(sl, col + nslots);
             }
             for (int q = 1; q < nslots; ++q) {  // main stream (reduce, frees) continues after the aux streams have drained
@@ -647,6 +847,19 @@ static void msm_batch_core(Context& ctx, const G1Affine* const* col_bases, const
                 CUDA_CHECK(cudaStreamWaitEvent(s, ctx.msm_join[q - 1], 0));
             }
             CUDA_CHECK(cudaStreamSynchronize(s));  // slot buffers are released below: nothing may still be using them
+            if (affine_rounds) {
+                // a column whose affine rounds met an identity operand or equal x-coordinates is redone on the XYZZ path
+                std::vector<uint32_t> flags(nc);
+                CUDA_CHECK(cudaMemcpy(flags.data(), col_flags.get(), nc * 4, cudaMemcpyDeviceToHost));
+                for (size_t j = 0; j < nc; ++j) {
+                    if (!flags[j]) continue;
+                    const size_t col = c0 + j;
+                    CUDA_CHECK(cudaMemsetAsync(bucket_sums.get() + j * nb, 0, (size_t)nb * sizeof(G1X), s));
+                    count(slots[0], col);
+                    msm_issue_accumulate(slots[0], col_bases[col] + lo_of(col), cols[col] + lo_of(col), len_of(col), cfg, bucket_sums.get() + j * nb, nullptr);
+                    CUDA_CHECK(cudaStreamSynchronize(s));
+                }
+            }
             drain.armed = false;
         }
         std::vector<G1X> ws;

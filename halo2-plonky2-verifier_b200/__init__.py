@@ -169,6 +169,10 @@ class Context:
         """The [UNVERIFIED-1..4] switches of SURVEY.md §8c (include/b200zk.h); (0, 0) = defaults."""
         self._check(lib().b200zk_set_compat(self._h, ctypes.c_uint32(flags), ctypes.c_uint32(random_poly_chunks)))
 
+    def set_msm_affine_rounds(self, rounds=0):
+        """Batched-affine pre-reduction rounds for dense MSM columns (0 = off, the default: measured slower on B200)."""
+        self._check(lib().b200zk_set_msm_affine_rounds(self._h, int(rounds)))
+
     def set_msm_tables(self, on=True):
         self._check(lib().b200zk_set_msm_tables(self._h, int(bool(on))))
 

@@ -355,6 +355,13 @@ int b200zk_set_compat(b200zk_ctx* ctx, uint32_t flags, uint32_t random_poly_chun
     c.random_poly_chunks = random_poly_chunks;
     API_END(ctx)
 }
+int b200zk_set_msm_affine_rounds(b200zk_ctx* ctx, int rounds) {
+    GROUP_DISPATCH(ctx, b200zk_set_msm_affine_rounds(rctx, rounds))
+    API_BEGIN(ctx)
+    if (rounds < 0 || rounds > 6) throw std::invalid_argument("set_msm_affine_rounds: 0..6");
+    ctx->c.msm_affine_rounds = rounds;
+    API_END(ctx)
+}
 int b200zk_set_msm_tables(b200zk_ctx* ctx, int on) {
     GROUP_DISPATCH(ctx, b200zk_set_msm_tables(rctx, on))
     API_BEGIN(ctx)

@@ -136,6 +136,7 @@ struct Context {
     unsigned comm_calls = 0;
     double exchange_seconds = 0;  // host time spent in the cross-rank exchange of partial MSM sums (reported under "other")
     bool msm_tables_enabled = true;
+    int msm_affine_rounds = 0;  // batched-affine pre-reduction rounds of dense MSM columns (msm.cu; measured slower: off)
     std::shared_ptr<struct Nccl> nccl;  // collectives.cuh: created on first use from the bootstrap callback (one process per
                                         // GPU), or installed by b200zk_create_multi (one process, one thread per GPU)
     // this context is one rank of a multi-GPU job

@@ -30,7 +30,6 @@
 namespace b200zk {
 
 constexpr uint32_t INVALID_KEY = 0xffffffffu;
-constexpr int MSM_AFFINE_ROUNDS_DEFAULT = 0;  // batched-affine pre-reduction rounds for dense columns (see below)
 
 struct MsmConfig {
     uint32_t c, W, B;   // window bits, windows, buckets per window (2^(c-1))
@@ -284,12 +283,18 @@ __global__ void __launch_bounds__(ACC_THREADS) msm_accumulate_kernel(const G1Aff
 // inverse and writes the sums. Bucket runs stay contiguous: off_dst = scan(ceil(cnt_src / 2)).
 // Affine addition has no identity and no doubling: an identity operand or equal x-coordinates (P + P, P − P: impossible
 // for distinct SRS points, possible for caller-supplied bases) raise `flag` and the column is redone on the XYZZ path.
-// number of rounds (0 = off): B200ZK_MSM_AFFINE overrides the default
-static int msm_affine_rounds() {
+// MEASURED on B200 (S20-bn, profiles/bench_r02_affine_rounds.json): bit-exact, but every round ADDS ≈ 8 ms per proof
+// (accumulate phase 53.9 ms with 0 rounds, 68.1 / 76.1 / 84.2 ms with 2 / 3 / 4): a round streams the column's points
+// through HBM twice more (the x-coordinates for the denominators, the points for the sums — in round 1 both are random
+// 64-byte gathers from the window table) plus 96 bytes of prefix / output per pair, pays a serial 380-product inversion
+// per group of roots, and crosses a bucket boundary every few outputs in the later rounds; together that costs more than
+// the ≈ 3 products per addition it saves on this part. The rounds therefore stay OFF by default
+// (b200zk_set_msm_affine_rounds / B200ZK_MSM_AFFINE switch them on; tests/test_gpu_msm.py keeps the path bit-exact).
+static int msm_affine_rounds_env() {
     static const int rounds = [] {
         const char* e = getenv("B200ZK_MSM_AFFINE");
-        const int v = e ? atoi(e) : MSM_AFFINE_ROUNDS_DEFAULT;
-        return v < 0 ? 0 : (v > 6 ? 6 : v);
+        const int v = e ? atoi(e) : -1;
+        return v > 6 ? 6 : v;
     }();
     return rounds;
 }
@@ -820,7 +825,7 @@ static void msm_batch_core(Context& ctx, const G1Affine* const* col_bases, const
                 }
             } drain{ctx, nslots};
             // batched-affine rounds for dense columns (merged-table configurations; B200ZK_MSM_AFFINE=0 switches them off)
-            const int affine_rounds = cfg.merged ? msm_affine_rounds() : 0;
+            const int affine_rounds = cfg.merged ? (msm_affine_rounds_env() >= 0 ? msm_affine_rounds_env() : ctx.msm_affine_rounds) : 0;
             DevBuf<uint32_t> col_flags(affine_rounds ? nc : 0, s);
             if (affine_rounds) CUDA_CHECK(cudaMemsetAsync(col_flags.get(), 0, nc * 4, s));
             for (int q = 0; q < nslots; ++q) {

@@ -92,6 +92,10 @@ B200ZK_API int b200zk_set_compat(b200zk_ctx* ctx, uint32_t flags, uint32_t rando
 /* Precomputed window tables 2^(c·w)·P_i for the SRS bases (one bucket set per MSM, no host fold; costs W× SRS memory).
  * On by default; switch off before loading a large SRS to save memory. */
 B200ZK_API int b200zk_set_msm_tables(b200zk_ctx* ctx, int on);
+/* Batched-affine pre-reduction of dense MSM columns: `rounds` (0..6) rounds of pairwise affine additions with column-wide
+ * batched inversions shrink every bucket's run before the XYZZ accumulation. Bit-exact; measured SLOWER than the XYZZ path
+ * alone on B200 (≈ +8 ms per round and proof at k=20), so the default is 0. Kept as a tested alternative. */
+B200ZK_API int b200zk_set_msm_affine_rounds(b200zk_ctx* ctx, int rounds);
 /* per-kernel-family CUDA-event timing (off by default). ids: 0 msm_accumulate, 1 (reserved), 2 ntt_pass, 3 quotient.
  * profile_get synchronises, sums the spans recorded since the last reset and clears them. */
 B200ZK_API int b200zk_profile_enable(b200zk_ctx* ctx, int on);

@@ -129,3 +129,47 @@ def test_msm_batch_matches_single(ctx):
     assert np.array_equal(ctx.msm_batch_dev(ptrs, n, 1)[0], O.msm(cols[0], gl))
     for p in ptrs:
         ctx.dev_free(p)
+
+
+@pytest.mark.parametrize("rounds", [1, 2, 3, 5])
+def test_batched_affine_rounds_are_bit_exact(ctx, srs, rounds):
+    """The batched-affine pre-reduction (b200zk_set_msm_affine_rounds; measured slower than XYZZ alone, hence off by default)
+    must give the same commitments as the default path for every scalar distribution, alone and in a batch."""
+    params, g, gl = srs
+    rng = np.random.default_rng(200 + rounds)
+    n = 1 << K
+    sets = scalar_sets(rng, n, K)
+    want = {name: ctx.msm(sc, 1) for name, sc in sets.items()}
+    try:
+        ctx.set_msm_affine_rounds(rounds)
+        for name, sc in sets.items():
+            assert np.array_equal(ctx.msm(sc, 1), want[name]), name
+        assert np.array_equal(ctx.msm(sets["uniform"], 0), O.msm(sets["uniform"], g))
+        got = ctx.msm_batch(list(sets.values()), 1)
+        for i, name in enumerate(sets):
+            assert np.array_equal(got[i], want[name]), name
+    finally:
+        ctx.set_msm_affine_rounds(0)
+
+
+def test_batched_affine_falls_back_on_exceptional_pairs(ctx):
+    """Affine addition has no doubling and no identity: bases with repeated points (P + P inside a bucket), opposite points
+    and identities must make the rounds hand the column back to the XYZZ path — same result as without the rounds."""
+    k = 10
+    n = 1 << k
+    G = O.g1_generator()
+    P5 = O.g1_mul(G, O.to_mont(5))
+    neg = P5.copy()
+    neg[4:] = O.field_op(1, 4, P5[4:])  # −y
+    pts = np.stack([P5 if i % 3 == 0 else (neg if i % 3 == 1 else np.zeros(8, dtype=np.uint64)) for i in range(n)])
+    rng = np.random.default_rng(8)
+    scalars = O.random_fr(rng, n)
+    try:
+        ctx.srs_load(k, pts, pts)
+        want = ctx.msm(scalars, 0)
+        assert np.array_equal(want, O.msm(scalars, pts))
+        ctx.set_msm_affine_rounds(3)
+        assert np.array_equal(ctx.msm(scalars, 0), want)
+        assert np.array_equal(ctx.msm(scalars, 1), want)
+    finally:
+        ctx.set_msm_affine_rounds(0)

@@ -16,7 +16,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__)) if "__file__" in globals() else os.getcwd()
 if os.path.basename(_HERE) == "b200zk":  # executed through the alias package
     _HERE = os.path.join(os.path.dirname(_HERE), "halo2-plonky2-verifier_b200")
-LIB_PATH = os.path.join(_HERE, "libb200zk.so")
+LIB_PATH = os.environ.get("B200ZK_LIB") or os.path.join(_HERE, "libb200zk.so")  # B200ZK_LIB: an experimental build for A/B runs
 CSRC = os.path.join(_HERE, "csrc")
 
 OK, ENODEV, EINVAL, ECUDA, ESTATE, ESYNTH = 0, -1, -2, -3, -4, -5

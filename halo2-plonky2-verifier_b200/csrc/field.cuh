@@ -582,9 +582,22 @@ inline Field<C> f_mul_host64(const Field<C>& a, const Field<C>& b) {
     }
     return f_reduce_once<C>(r, (uint32_t)t[4]);
 }
+#if defined(B200ZK_NOINLINE_MUL) && defined(__CUDACC__)
+// experiment: out-of-line multiplier bodies (smaller kernels, friendlier to the instruction caches) — see DESIGN.md §3.3
+template <class C>
+__device__ __noinline__ Field<C> f_mul_chains_ool(Field<C> a, Field<C> b) {
+    return f_mul_chains<C>(a, b);
+}
+template <class C>
+__device__ __noinline__ Field<C> f_sqr_comba_ool(Field<C> a) {
+    return f_sqr_comba<C>(a);
+}
+#endif
 template <class C>
 HD Field<C> f_mul(const Field<C>& a, const Field<C>& b) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(B200ZK_NOINLINE_MUL)
+    return f_mul_chains_ool<C>(a, b);
+#elif defined(__CUDA_ARCH__)
 #if defined(B200ZK_MUL_U29)  // measured alternative: 43–45 G mul/s (profiles/README.md)
     return f_mul_u29<C>(a, b);
 #elif defined(B200ZK_MUL_COMBA)  // measured alternative: 65 G mul/s (profiles/microbench_r02.json)
@@ -599,7 +612,9 @@ HD Field<C> f_mul(const Field<C>& a, const Field<C>& b) {
 // squaring: the product-scanning form needs 108 instead of 138 multiply-adds — 79 G/s against 67 G/s for f_mul(a, a)
 template <class C>
 HD Field<C> f_sqr(const Field<C>& a) {
-#if defined(__CUDA_ARCH__) && !defined(B200ZK_MUL_U29) && !defined(B200ZK_SQR_BY_MUL)
+#if defined(__CUDA_ARCH__) && defined(B200ZK_NOINLINE_MUL)
+    return f_sqr_comba_ool<C>(a);
+#elif defined(__CUDA_ARCH__) && !defined(B200ZK_MUL_U29) && !defined(B200ZK_SQR_BY_MUL)
     return f_sqr_comba<C>(a);
 #else
     return f_mul<C>(a, a);

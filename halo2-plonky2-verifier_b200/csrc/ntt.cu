@@ -51,7 +51,10 @@ struct PassParams {
     uint32_t skip2;  // first pass of a 4x zero-padded input: stages 1-2 only replicate each non-zero element 4 times
 };
 
-constexpr int NTT_THREADS = 256;
+#ifndef B200ZK_NTT_THREADS
+#define B200ZK_NTT_THREADS 256
+#endif
+constexpr int NTT_THREADS = B200ZK_NTT_THREADS;
 constexpr int NTT_MAX_R = 8;
 constexpr int NTT_MAX_LOGC = 3;
 constexpr int SMEM_PAD = 4;  // uint4 units between the low-half and high-half planes (bank offset 16)
@@ -123,6 +126,47 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(PassParams P) {
         const uint32_t half = 1u << (t - 1);
         const uint32_t s = P.s0 + t;
         const bool trivial = P.first && t == 1;  // all twiddles are w^0
+#if defined(B200ZK_NTT_ILP2)
+        // two butterflies per iteration: both operand pairs and both twiddles are requested before either product starts
+        auto bfly_addr = [&](uint32_t b, uint32_t& i0, uint32_t& i1, uint32_t& idx) {
+            const uint32_t c = b & (C - 1), mm = b >> P.logC;
+            const uint32_t j = mm & (half - 1);
+            const uint32_t m0 = ((mm >> (t - 1)) << t) + j, m1 = m0 + half;
+            i0 = swz(m0, c, P.logC);
+            i1 = swz(m1, c, P.logC);
+            const uint32_t lo = P.first ? 0 : lo_base + c;
+            idx = (((j << P.s0) + lo) << (P.L - s)) << P.table_shift;
+        };
+        auto twiddle = [&](uint32_t idx) -> Fr {
+            if (!P.inverse) return f_load_ro(P.table + idx);
+            if (idx == 0) return f_one<FrCfg>();
+            return f_neg(f_load_ro(P.table + (P.half_table - idx)));
+        };
+        for (uint32_t b = tid; b < T / 2; b += 2 * NTT_THREADS) {
+            const uint32_t b2 = b + NTT_THREADS;
+            const bool two = b2 < T / 2;
+            uint32_t i0, i1, idx, k0 = 0, k1 = 0, kdx = 0;
+            bfly_addr(b, i0, i1, idx);
+            if (two) bfly_addr(b2, k0, k1, kdx);
+            Fr w = trivial ? f_one<FrCfg>() : twiddle(idx), w2 = (trivial || !two) ? f_one<FrCfg>() : twiddle(kdx);
+            Fr u = tile_get(slo, shi, i0), v = tile_get(slo, shi, i1);
+            Fr u2 = u, v2 = v;
+            if (two) {
+                u2 = tile_get(slo, shi, k0);
+                v2 = tile_get(slo, shi, k1);
+            }
+            if (!trivial) {
+                v = f_mul(v, w);
+                if (two) v2 = f_mul(v2, w2);
+            }
+            tile_put(slo, shi, i0, f_add(u, v));
+            tile_put(slo, shi, i1, f_sub(u, v));
+            if (two) {
+                tile_put(slo, shi, k0, f_add(u2, v2));
+                tile_put(slo, shi, k1, f_sub(u2, v2));
+            }
+        }
+#else
         for (uint32_t b = tid; b < T / 2; b += NTT_THREADS) {
             const uint32_t c = b & (C - 1), mm = b >> P.logC;
             const uint32_t j = mm & (half - 1);
@@ -146,6 +190,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(PassParams P) {
             tile_put(slo, shi, i0, f_add(u, v));
             tile_put(slo, shi, i1, f_sub(u, v));
         }
+#endif
         __syncthreads();
     }
     // ---- store ----

@@ -136,6 +136,7 @@ def test_batched_affine_rounds_are_bit_exact(ctx, srs, rounds):
     """The batched-affine pre-reduction (b200zk_set_msm_affine_rounds; measured slower than XYZZ alone, hence off by default)
     must give the same commitments as the default path for every scalar distribution, alone and in a batch."""
     params, g, gl = srs
+    ctx.srs_load(K, g, gl)  # earlier tests of this module may have loaded other bases
     rng = np.random.default_rng(200 + rounds)
     n = 1 << K
     sets = scalar_sets(rng, n, K)

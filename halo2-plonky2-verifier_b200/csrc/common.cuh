@@ -200,6 +200,7 @@ struct NttPlan {
     size_t in_len = 0;                // input elements at index >= in_len read as zero (0 = full)
     const Fr* post_scale3 = nullptr;  // 3 factors applied to output element i by (i mod 3) (divisor folded in)
     size_t out_len = 0;               // outputs at index >= out_len are not stored (0 = full)
+    size_t in_stride = 1, in_offset = 0;  // input element i is read at in[i·in_stride + in_offset] (a strided subsequence)
 };
 void build_twiddle_table(Fr* table, const Fr& omega, uint32_t log_n, cudaStream_t stream);
 int ntt_num_passes(uint32_t log_n);

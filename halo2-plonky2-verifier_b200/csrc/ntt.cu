@@ -44,7 +44,7 @@ struct PassParams {
     const Fr* table;
     const Fr* pre3;
     const Fr* post3;
-    unsigned long long in_len, out_len, batch_stride_in, batch_stride_out;
+    unsigned long long in_len, out_len, batch_stride_in, batch_stride_out, in_stride, in_offset;
     uint32_t L, s0, r, logC;
     uint32_t table_shift, half_table;
     uint32_t inverse, first, last;
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(PassParams P) {
         if (P.in_len && src >= P.in_len) {
             v = f_zero<FrCfg>();
         } else {
-            v = f_load(in + src);
+            v = f_load(in + (P.first ? src * P.in_stride + P.in_offset : src));
             if (P.pre3) {
                 const uint32_t k3 = (uint32_t)(src % 3);
                 if (k3) v = f_mul(v, f_load_ro(P.pre3 + k3));
@@ -252,6 +252,8 @@ void ntt_run_batch(const NttPlan& plan, const Fr* in, Fr* out, Fr* scratch, uint
         P.r = r;
         const uint32_t avail = P.first ? L - r : s0;  // log2 of the number of columns that exist
         P.logC = avail < (uint32_t)NTT_MAX_LOGC ? avail : NTT_MAX_LOGC;
+        P.in_stride = plan.in_stride;
+        P.in_offset = plan.in_offset;
         P.pre3 = P.first ? plan.pre_scale3 : nullptr;
         P.in_len = P.first ? plan.in_len : 0;
         // zero-padded to 4x (coeff_to_extended): positions with (m & 3) != 0 hold zeros after the bit reversal, so the first two

@@ -446,6 +446,39 @@ int lookup_permute(Context& ctx, const Fr* input, const Fr* table, Fr* a_out, Fr
     return 0;
 }
 
+// ---- radix-4 combine of four size-n inverse transforms into extended_to_coeff's output --------------------------------------
+// x (4n values on the extended domain) = four stride-4 subsequences x_j[m] = x[4m + j]; with Y_j = the plain inverse
+// transform of x_j (root ω⁻¹ = W⁴, W = ω_ext⁻¹, no 1/n), the size-4n inverse transform is
+//   X[k + q·n] = Σ_j W^{j(k + qn)} Y_j[k] = Σ_j (I⁴_q)^j · (W^{jk} Y_j[k]),  I = W^n (a primitive fourth root of unity),
+// so with z_j = W^{jk}·Y_j[k]:  X[k] = z0+z1+z2+z3,  X[k+n] = (z0−z2) + I·(z1−z3),  X[k+2n] = (z0+z2) − (z1+z3)
+// (X[k+3n] is dropped by extended_to_coeff's truncation to 3n). The post factors (1/4n)·ζ^(−i mod 3) are applied here.
+__global__ void e2c_combine_kernel(const Fr* Y, Fr* out, size_t n, size_t k_lo, size_t k_hi, const Fr* table, uint32_t table_log, uint32_t ext_k, Fr I,
+                                   const Fr* post3) {
+    const size_t k = k_lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= k_hi) return;
+    const uint32_t en = 1u << ext_k;
+    auto w_inv = [&](uint32_t e) -> Fr {  // ω_ext^(−e), e < 4n
+        if (e == 0) return f_one<FrCfg>();
+        return omega_pow_from_table(table, table_log, ext_k, en - e);
+    };
+    const Fr z0 = f_load(Y + k);
+    const Fr z1 = f_mul(f_load(Y + n + k), w_inv((uint32_t)k));
+    const Fr z2 = f_mul(f_load(Y + 2 * n + k), w_inv((uint32_t)(2 * k)));
+    const Fr z3 = f_mul(f_load(Y + 3 * n + k), w_inv((uint32_t)(3 * k)));
+    const Fr s02 = f_add(z0, z2), d02 = f_sub(z0, z2), s13 = f_add(z1, z3), d13 = f_mul(f_sub(z1, z3), I);
+    const Fr x0 = f_add(s02, s13), x1 = f_add(d02, d13), x2 = f_sub(s02, s13);
+    const size_t i0 = k, i1 = k + n, i2 = k + 2 * n;
+    f_store(out + i0, f_mul(x0, f_load_ro(post3 + (uint32_t)(i0 % 3))));
+    f_store(out + i1, f_mul(x1, f_load_ro(post3 + (uint32_t)(i1 % 3))));
+    f_store(out + i2, f_mul(x2, f_load_ro(post3 + (uint32_t)(i2 % 3))));
+}
+void fr_e2c_combine(const Fr* Y, Fr* out, size_t n, size_t k_lo, size_t k_hi, const Fr* table, uint32_t table_log, uint32_t ext_k, const Fr& I, const Fr* post3,
+                    cudaStream_t s) {
+    if (k_hi <= k_lo) return;
+    e2c_combine_kernel<<<nblocks(k_hi - k_lo, 256), 256, 0, s>>>(Y, out, n, k_lo, k_hi, table, table_log, ext_k, I, post3);
+    LAUNCHED(1);
+}
+
 // ---- Fr::random stream (ChaCha) ------------------------------------------------------------------------------------------
 DEV uint32_t rotl32(uint32_t x, int n) { return (x << n) | (x >> (32 - n)); }
 struct ChaChaKey {

@@ -43,6 +43,11 @@ constexpr int LOOKUP_UNSUPPORTED = 1, LOOKUP_NOT_IN_TABLE = 2;
 // fill_from_end: ascending leftovers go to the repeated rows popped from the end (classic rule) or, false, in ascending order
 int lookup_permute(Context& ctx, const Fr* input, const Fr* table, Fr* a_out, Fr* s_out, size_t n, size_t usable, bool fill_from_end = true);
 
+// radix-4 combine of four plain size-n inverse transforms Y[j][k] (of the stride-4 subsequences of a 4n-point vector) into
+// extended_to_coeff's 3n outputs, for k in [k_lo, k_hi); I = ω_ext^(−n); post3 = the domain's extended_to_coeff factors
+void fr_e2c_combine(const Fr* Y, Fr* out, size_t n, size_t k_lo, size_t k_hi, const Fr* table, uint32_t table_log, uint32_t ext_k, const Fr& I, const Fr* post3,
+                    cudaStream_t s);
+
 // ---- Fr::random stream: element j of a rand_chacha BlockRng stream = from_u512 of ChaCha block (counter0 + j) ---------
 void fr_random_stream(Fr* out, size_t n, const uint32_t key[8], uint64_t counter0, int rounds, cudaStream_t s);
 // out[i] = Fr::from_u512 of the i-th 64-byte group of host-supplied random words (device buffer of 16·n words)

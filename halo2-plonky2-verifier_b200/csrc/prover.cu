@@ -853,7 +853,24 @@ static std::vector<uint8_t> create_proof_body(Context& ctx, const ProvingKeyDev&
                    h.get(), tm, lap);
     // step 10: vanishing::construct (D.9) — t_inv scaling already applied by the last h kernel
     DevBuf<Fr> h_coeff(3 * n, s);
-    dev_extended_to_coeff(ctx, sh.k, h.get(), h_coeff.get());
+    if (shard.on() && n % ctx.world == 0) {
+        // the 4n-point inverse transform of h across the ranks: the four stride-4 subsequences are transformed by (up to)
+        // four ranks (size n each), exchanged, and the radix-4 combine + scaling + truncation is done by slice of k
+        DevBuf<Fr> Y(4 * n, s);
+        NttPlan p = make_plan(ctx, sh.k, true);  // plain inverse transform: root ω⁻¹, no divisor
+        p.in_stride = 4;
+        for (uint32_t j = 0; j < 4; ++j)
+            if (shard.mine(j)) {
+                p.in_offset = j;
+                ntt_run_batch(p, h.get(), Y.get() + (size_t)j * n, ctx.get_scratch(n), 1, 0, 0, 0, s);
+            }
+        shard.allgather_columns(Y.get(), 4, n);
+        const size_t len = n / ctx.world, k_lo = len * ctx.rank;
+        fr_e2c_combine(Y.get(), h_coeff.get(), n, k_lo, k_lo + len, tw.t.get(), tw.log_n, sh.k + 2, f_pow_u64(dom.extended_omega_inv, n), dom.post_e2c(), s);
+        for (uint32_t q = 0; q < 3; ++q) shard.all_gather_inplace(h_coeff.get() + (size_t)q * n, len);
+    } else {
+        dev_extended_to_coeff(ctx, sh.k, h.get(), h_coeff.get());
+    }
     h.release();
     lap(tm ? &tm->ntt : nullptr);
     skip_unused_blinds(3);

@@ -268,6 +268,7 @@ int b200zk_destroy(b200zk_ctx* ctx) {
     if (ctx->c.ntt_done) cudaEventDestroy(ctx->c.ntt_done);
     if (ctx->c.comm_fork) cudaEventDestroy(ctx->c.comm_fork);
     if (ctx->c.comm_done) cudaEventDestroy(ctx->c.comm_done);
+    for (auto& e : ctx->c.column_events) cudaEventDestroy(e);
     if (ctx->c.copy_fork) cudaEventDestroy(ctx->c.copy_fork);
     if (ctx->c.copy_done) cudaEventDestroy(ctx->c.copy_done);
     if (ctx->c.pinned_u32) cudaFreeHost(ctx->c.pinned_u32);

@@ -1,5 +1,6 @@
 // Context of libb200zk: one CUDA device, one stream, cached twiddle tables / domains / SRS / proving keys.
 #pragma once
+#include <functional>
 #include <memory>
 
 #include "common.cuh"
@@ -102,8 +103,21 @@ struct Context {
     cudaStream_t stream = nullptr;
     cudaStream_t aux_streams[MSM_SLOTS - 1] = {};  // further MSM columns in flight (msm.cu)
     cudaEvent_t msm_events[MSM_SLOTS] = {}, msm_join[MSM_SLOTS - 1] = {}, msm_fork = nullptr;
-    cudaStream_t copy_stream = nullptr;    // witness upload overlapped with the first advice commitments (prover.cu)
+    cudaStream_t copy_stream = nullptr;    // witness upload overlapped with the advice commitments (prover.cu)
     cudaEvent_t copy_fork = nullptr, copy_done = nullptr;
+    // A commit batch may be issued while its columns are still arriving: before a column's first kernel is queued, the batch
+    // calls column_gate(column index, the stream that will read it) — the gate blocks the HOST until the column's copy has
+    // been queued and makes the stream wait for it (prover.cu: the witness upload). Empty = no gating.
+    std::function<void(size_t, cudaStream_t)> column_gate;
+    std::vector<cudaEvent_t> column_events;  // one per advice column, created on first use
+    cudaEvent_t column_event(size_t c) {
+        while (column_events.size() <= c) {
+            cudaEvent_t e;
+            CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            column_events.push_back(e);
+        }
+        return column_events[c];
+    }
     // transforms that do not depend on the transcript (the advice columns' lagrange_to_coeff / coeff_to_extended) run on this
     // stream beside the commit batches: the MSM kernels leave ≈ 20 % of the multiplier pipe idle (latency-bound phases), which
     // the NTT kernels fill (prover.cu)

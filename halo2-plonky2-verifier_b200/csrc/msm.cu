@@ -838,7 +838,10 @@ static void msm_batch_core(Context& ctx, const G1Affine* const* col_bases, const
                 CUDA_CHECK(cudaEventRecord(ctx.msm_fork, s));
                 for (int q = 1; q < nslots; ++q) CUDA_CHECK(cudaStreamWaitEvent(ctx.aux_streams[q - 1], ctx.msm_fork, 0));
             }
-            auto count = [&](MsmSlot& sl, size_t j) { msm_issue_count(sl, cols[j] + lo_of(j), len_of(j), cfg); };
+            auto count = [&](MsmSlot& sl, size_t j) {
+                if (ctx.column_gate) ctx.column_gate(j, sl.st);  // the column may still be on its way to the device
+                msm_issue_count(sl, cols[j] + lo_of(j), len_of(j), cfg);
+            };
             for (size_t j = 0; j < (size_t)nslots && j < nc; ++j) count(slots[j], c0 + j);
             for (size_t j = 0; j < nc; ++j) {
                 MsmSlot& sl = slots[j % nslots];

@@ -11,6 +11,7 @@
 #include "collectives.cuh"
 
 #include <algorithm>
+#include <condition_variable>
 #include <chrono>
 
 namespace b200zk {
@@ -565,6 +566,13 @@ static std::vector<uint8_t> create_proof_body(Context& ctx, const ProvingKeyDev&
     } copy_join{nullptr};
     // a pageable witness (a Rust Vec) goes through pinned staging chunks filled by worker threads (upload.cuh)
     const bool pageable = !advice_on_device && host_pointer_is_pageable(advice_in);
+    // (declared before the stager: its worker threads report into it and are joined by the stager's destructor)
+    struct ColumnsReady {  // which columns have been queued (with their event recorded): set by the uploaders, read by the gate
+        std::mutex mu;
+        std::condition_variable cv;
+        std::vector<uint8_t> ready;
+        bool failed = false;
+    } cols_ready;
     StagedUpload stager(ctx);
     // columns [c0, c1) from the caller's buffer, queued on `st`; with `wait` the call returns once everything is queued
     auto upload = [&](uint32_t c0, uint32_t c1, cudaStream_t st, bool wait) {
@@ -585,10 +593,59 @@ static std::vector<uint8_t> create_proof_body(Context& ctx, const ProvingKeyDev&
             CUDA_CHECK(cudaMemcpyAsync(advice.get() + (size_t)c * n + u, blind.data() + (size_t)c * (bf + 1), (bf + 1) * sizeof(Fr),
                                        cudaMemcpyHostToDevice, st));
     };
-    // host witness on one GPU: the first quarter of the columns goes up on the compute stream, the rest follows on the copy
-    // stream while that quarter is being committed
-    const uint32_t ahead = (!advice_on_device && !shard.on() && ctx.copy_stream && NA >= 8) ? NA / 4 : NA;
-    if (shard.on() && !advice_on_device) {
+    // host witness on one GPU: the columns go up on the copy stream one after the other, each followed by its blinding rows
+    // and an event; ONE commit batch is issued at once and each column's first kernel waits for that column only
+    // (Context::column_gate), so the commitments start when the first column has landed and the upload hides behind them
+    const bool streamed = !advice_on_device && !shard.on() && ctx.copy_stream != nullptr;
+    struct GateReset {  // the gate must not outlive this call
+        Context& c;
+        ~GateReset() { c.column_gate = nullptr; }
+    } gate_reset{ctx};
+    if (streamed) {
+        cols_ready.ready.assign(NA, 0);
+        for (uint32_t c = 0; c < NA; ++c) ctx.column_event(c);  // create the events before any worker thread needs one
+        CUDA_CHECK(cudaEventRecord(ctx.copy_fork, s));
+        CUDA_CHECK(cudaStreamWaitEvent(ctx.copy_stream, ctx.copy_fork, 0));
+        copy_join.st = ctx.copy_stream;
+        const int device = ctx.device;
+        // queued behind column c's data on the copy stream: its blinding rows, then the event the commit batch waits for
+        auto finish_column = [&, device](size_t c) {
+            bool ok = cudaSetDevice(device) == cudaSuccess;
+            ok = ok && cudaMemcpyAsync(advice.get() + c * n + u, blind.data() + c * (bf + 1), (bf + 1) * sizeof(Fr), cudaMemcpyHostToDevice,
+                                       ctx.copy_stream) == cudaSuccess;
+            ok = ok && cudaEventRecord(ctx.column_events[c], ctx.copy_stream) == cudaSuccess;
+            std::lock_guard<std::mutex> lk(cols_ready.mu);
+            cols_ready.ready[c] = 1;
+            cols_ready.failed = cols_ready.failed || !ok;
+            cols_ready.cv.notify_all();
+        };
+        if (pageable) {
+            stager.start(advice.get(), advice_in, (size_t)NA * n * sizeof(Fr), ctx.copy_stream, n * sizeof(Fr), finish_column);
+        } else {
+            for (uint32_t c = 0; c < NA; ++c) {
+                CUDA_CHECK(cudaMemcpyAsync(advice.get() + (size_t)c * n, advice_in + (size_t)c * n, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx.copy_stream));
+                finish_column(c);
+            }
+        }
+        ctx.column_gate = [&](size_t c, cudaStream_t st) {
+            std::unique_lock<std::mutex> lk(cols_ready.mu);
+            cols_ready.cv.wait(lk, [&] { return cols_ready.ready[c] != 0 || cols_ready.failed; });
+            if (cols_ready.failed) throw CudaError("witness upload failed");
+            lk.unlock();
+            CUDA_CHECK(cudaStreamWaitEvent(st, ctx.column_events[c], 0));
+        };
+        lap(tm ? &tm->upload : nullptr);
+        for (const G1Affine& cm : commit_batch(ctx, 1, advice.get(), n, NA, n)) tr.write_point(cm);
+        ctx.column_gate = nullptr;
+        stager.join();
+        CUDA_CHECK(cudaEventRecord(ctx.copy_done, ctx.copy_stream));
+        fork_advice_transforms(ctx.copy_done);
+        CUDA_CHECK(cudaStreamWaitEvent(s, ctx.copy_done, 0));
+    }
+    const uint32_t ahead = NA;
+    if (streamed) {
+        // done above
+    } else if (shard.on() && !advice_on_device) {
         // every rank holds the host witness: each uploads only its share over PCIe — ONE contiguous block of columns, so a
         // pageable buffer goes through a single staged upload — and the rest arrives over NVLink (in-place broadcasts of the
         // blocks, one NCCL group)
@@ -597,28 +654,15 @@ static std::vector<uint8_t> create_proof_body(Context& ctx, const ProvingKeyDev&
         shard.broadcast_blocks(advice.get(), NA, n);
         blind_rows(0, NA, s);
         fork_advice_transforms(nullptr);
-    } else if (ahead < NA) {
-        CUDA_CHECK(cudaEventRecord(ctx.copy_fork, s));
-        CUDA_CHECK(cudaStreamWaitEvent(ctx.copy_stream, ctx.copy_fork, 0));
-        copy_join.st = ctx.copy_stream;
-        upload(0, ahead, s, true);
-        blind_rows(0, ahead, s);
-        upload(ahead, NA, ctx.copy_stream, false);
     } else {
         upload(0, NA, s, true);
         blind_rows(0, NA, s);
         fork_advice_transforms(nullptr);
     }
-    CUDA_CHECK(cudaStreamSynchronize(s));
-    lap(tm ? &tm->upload : nullptr);
-    for (const G1Affine& cm : commit_batch(ctx, 1, advice.get(), n, ahead, n)) tr.write_point(cm);
-    if (ahead < NA) {
-        stager.join();
-        blind_rows(ahead, NA, ctx.copy_stream);
-        CUDA_CHECK(cudaEventRecord(ctx.copy_done, ctx.copy_stream));
-        fork_advice_transforms(ctx.copy_done);  // all columns and their blinding rows are up once copy_done has fired
-        CUDA_CHECK(cudaStreamWaitEvent(s, ctx.copy_done, 0));
-        for (const G1Affine& cm : commit_batch(ctx, 1, advice.get() + (size_t)ahead * n, n, NA - ahead, n)) tr.write_point(cm);
+    if (!streamed) {
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        lap(tm ? &tm->upload : nullptr);
+        for (const G1Affine& cm : commit_batch(ctx, 1, advice.get(), n, ahead, n)) tr.write_point(cm);
     }
     lap(tm ? &tm->msm : nullptr);
     const Fr theta = tr.squeeze_challenge();

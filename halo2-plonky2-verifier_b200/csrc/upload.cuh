@@ -6,6 +6,8 @@
 #pragma once
 #include <atomic>
 #include <cstring>
+#include <functional>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -29,10 +31,16 @@ public:
     explicit StagedUpload(Context& c) : ctx(c) {}
     StagedUpload(const StagedUpload&) = delete;
     ~StagedUpload() { join_nothrow(); }
-    // queue dst[0, bytes) <- src[0, bytes) on stream `st`; returns at once
-    void start(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    // queue dst[0, bytes) <- src[0, bytes) on stream `st`; returns at once. With `piece` > 0 the buffer is seen as pieces of
+    // `piece` bytes (columns) and on_piece(i) is called — from the worker thread that queued the last chunk overlapping
+    // piece i, i.e. stream-ordered behind all of the piece's copies — so that the caller can queue follow-up work and
+    // publish the piece as ready.
+    void start(void* dst, const void* src, size_t bytes, cudaStream_t st, size_t piece = 0, std::function<void(size_t)> on_piece = nullptr) {
         join();
         if (bytes == 0) return;
+        const size_t npieces = piece ? (bytes + piece - 1) / piece : 0;
+        remaining.reset(npieces ? new std::atomic<long long>[npieces] : nullptr);
+        for (size_t i = 0; i < npieces; ++i) remaining[i].store((long long)std::min(piece, bytes - i * piece));
         if (!ctx.stage_buf) {
             CUDA_CHECK(cudaHostAlloc((void**)&ctx.stage_buf, CHUNK * WORKERS * SLOTS, cudaHostAllocDefault));
             for (auto& e : ctx.stage_ev) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -55,6 +63,11 @@ public:
                     if (cudaMemcpyAsync((uint8_t*)dst + off, slot, len, cudaMemcpyHostToDevice, st) != cudaSuccess) failed = 1;
                     if (cudaEventRecord(ctx.stage_ev[idx], st) != cudaSuccess) failed = 1;
                     if (failed) return;
+                    if (piece)  // pieces whose last chunk this was
+                        for (size_t p = off / piece; p * piece < off + len; ++p) {
+                            const size_t lo = std::max(off, p * piece), hi = std::min(off + len, (p + 1) * piece);
+                            if (remaining[p].fetch_sub((long long)(hi - lo)) == (long long)(hi - lo) && on_piece) on_piece(p);
+                        }
                 }
             });
     }
@@ -73,6 +86,7 @@ private:
     Context& ctx;
     std::vector<std::thread> threads;
     std::atomic<int> failed{0};
+    std::unique_ptr<std::atomic<long long>[]> remaining;  // bytes of each piece not yet queued
 };
 
 }  // namespace b200zk

@@ -307,6 +307,25 @@ class Context:
         self._check(lib().b200zk_srs_read(self._h, _p(buf), ctypes.c_size_t(len(buf)), int(fmt)))
         self.srs_k = int.from_bytes(data[:4], "little")
 
+    def gen_srs(self, k, params_dir="params"):
+        """halo2-base `utils::fs::gen_srs(k)`: read `<params_dir>/kzg_bn254_<k>.srs` if it exists, else run
+        ParamsKZG::setup(k, ChaCha20Rng::from_seed([0;32])) and write the file (the reference keeps that directory out of
+        git: /root/reference/.gitignore:5 `params/`). The file is ParamsKZG::write in RawBytes form. Returns True when the
+        cached file was used. (The MSM window tables are rebuilt on the device either way: 0.11 s at k=20, less than
+        reading their 1.7 GB back from disk would take.)"""
+        path = os.path.join(params_dir, f"kzg_bn254_{k}.srs")
+        if os.path.exists(path):
+            with open(path, "rb") as f:
+                self.srs_read(f.read(), fmt=0)
+            return True
+        self.srs_setup(k)
+        os.makedirs(params_dir, exist_ok=True)
+        tmp = path + ".tmp"
+        with open(tmp, "wb") as f:
+            f.write(self.srs_write(fmt=0))
+        os.replace(tmp, path)
+        return False
+
     def srs_download(self):
         n = 1 << self.srs_k
         g = np.empty((n, 8), dtype=np.uint64)

@@ -138,8 +138,8 @@ struct Context {
     DevBuf<Fr> scratch;
     Arena arena;  // transient buffers of this context's stream
     std::unique_ptr<Srs> srs;
-    // multi-GPU: one process per GPU; MSMs are sharded by point range and partial window sums are exchanged through
-    // this callback (the host binds it to an NCCL all-gather) — SURVEY.md §8e
+    // multi-GPU: this context is rank `rank` of `world`. The host's all-gather callback carries the NCCL
+    // id once (collectives.cuh); without a communicator the MSM entry points exchange their partial sums through it
     int rank = 0, world = 1;
     AllGatherFn allgather = nullptr;
     void* allgather_user = nullptr;

@@ -883,7 +883,8 @@ static G1Affine msm_finish(const MsmConfig& cfg, const G1X* sums) {
 // Multi-GPU split of a batch (both levels of the north star). With `world` ranks and ncols = q·world + rem:
 // the first q·world columns are dealt out by COLUMN — rank r commits columns r, r+world, ... over the full point range —
 // and the remaining rem (< world) columns are split by POINT RANGE, every rank accumulating its contiguous shard. All of
-// a rank's work goes through ONE accumulate batch and one bucket reduction; one all-gather (host callback) then carries
+// a rank's work goes through ONE accumulate batch and one bucket reduction; one all-gather (ncclAllGather out of the
+// reduction's output buffer once the library's communicator is up, the host callback otherwise) then carries
 // the q finished sums and the rem partial window sums of every rank, and the partial ones are added on the host.
 static void msm_batch_distribute(Context& ctx, const G1Affine* const* col_bases, const Fr* const* cols, size_t ncols, size_t n, const MsmConfig& cfg,
                                  G1Affine* out) {

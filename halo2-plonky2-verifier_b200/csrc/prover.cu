@@ -337,7 +337,7 @@ static Fr vanishing_eval(const std::vector<Fr>& roots, const Fr& z) {
 }
 
 // evaluations of many polynomials at one point; when sharded, rank r evaluates polynomials r, r+world, ... (every rank
-// holds all coefficient forms) and the 32-byte results are all-gathered through the host callback
+// holds all coefficient forms) and the 32-byte results are all-gathered over NCCL (Sharder::host_allgather)
 static void eval_many_dist(Context& ctx, Sharder& shard, const std::vector<const Fr*>& polys, size_t n, const Fr& point, Fr* out) {
     const size_t m = polys.size(), world = ctx.world;
     if (!shard.on() || m < 2 * world) {

@@ -67,10 +67,14 @@ B200ZK_API void* b200zk_stream(b200zk_ctx* ctx);
 B200ZK_API int b200zk_sync(b200zk_ctx* ctx);
 /* kernels launched by this library since process start (bench.py "gpu_launches") */
 B200ZK_API unsigned long long b200zk_launch_count(void);
-/* Multi-GPU (one process per GPU): every MSM is sharded by contiguous point range — this rank handles
- * range `rank` of `world` — and the per-rank partial sums (one XYZZ point per bucket set, 128 B each) are exchanged through
- * `fn`, which must all-gather `bytes` bytes from every rank into recv[world][bytes] (host buffers; bind it to an NCCL or
- * MPI all-gather) and return 0. All ranks must issue the same MSM calls in the same order. world = 1 disables it. */
+/* Multi-GPU with one process per GPU (for one process driving all GPUs see b200zk_create_multi): this
+ * context is rank `rank` of `world`; all ranks must issue the same calls in the same order. Commit batches are dealt by
+ * column with the remainder split by point range, create_proof shards its other stages too. `fn` must
+ * all-gather `bytes` bytes from every rank into recv[world][bytes] (host buffers; bind it to an MPI / NCCL all-gather)
+ * and return 0: the library uses it ONCE, to carry the 128-byte id of its own NCCL communicator (b200zk_comm_init, or the
+ * first create_proof) — after that every exchange is an NCCL call on the library's stream. Without NCCL in the process the
+ * communicator stays down and the MSM entry points exchange their partial sums (128 B each) through `fn` itself.
+ * world = 1 disables sharding. */
 typedef int (*b200zk_allgather_fn)(void* user, const void* send, size_t bytes, void* recv);
 B200ZK_API int b200zk_set_allgather(b200zk_ctx* ctx, int rank, int world, b200zk_allgather_fn fn, void* user);
 /* Brings up the library's own NCCL communicator now (collective: every rank must call it; the 128-byte id travels through

@@ -1,4 +1,6 @@
 """GPU parity, row K: ParamsKZG::setup on the device vs the oracle (same ChaCha20 seed -> same trapdoor -> same bases)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -129,3 +131,19 @@ def test_srs_file_round_trip_and_g2(ctx):
     badp = bytearray(processed); badp[4 + 31] |= 0x3F
     with pytest.raises(Exception):
         ctx.srs_read(bytes(badp), 1)
+
+
+def test_gen_srs_caches_params_on_disk(ctx, tmp_path):
+    """halo2-base gen_srs: the first call generates and writes params/kzg_bn254_<k>.srs, the second reads it back; both
+    leave the same bases on the device, and commitments agree."""
+    k = 10
+    d = str(tmp_path / "params")
+    assert ctx.gen_srs(k, d) is False
+    g1, gl1 = ctx.srs_download()
+    assert os.path.exists(os.path.join(d, f"kzg_bn254_{k}.srs"))
+    ctx.srs_setup(k, seed=bytes([1] * 32))  # something else in between
+    assert ctx.gen_srs(k, d) is True
+    g2, gl2 = ctx.srs_download()
+    assert np.array_equal(g1, g2) and np.array_equal(gl1, gl2)
+    a = O.random_fr(np.random.default_rng(3), 1 << k)
+    assert np.array_equal(ctx.msm(a, 1), O.msm(a, gl1))

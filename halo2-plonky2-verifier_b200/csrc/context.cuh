@@ -96,7 +96,10 @@ struct Compat {
 };
 
 constexpr int MSM_SLOTS = 4;  // MSM columns in flight per commit batch
-constexpr int STAGE_WORKERS = 6, STAGE_SLOTS = 2;  // pinned staging of pageable uploads (upload.cuh)
+#ifndef B200ZK_STAGE_WORKERS
+#define B200ZK_STAGE_WORKERS 6
+#endif
+constexpr int STAGE_WORKERS = B200ZK_STAGE_WORKERS, STAGE_SLOTS = 2;  // pinned staging of pageable uploads (upload.cuh)
 
 struct Context {
     int device = 0;

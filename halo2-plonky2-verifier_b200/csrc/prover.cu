@@ -1033,6 +1033,10 @@ static std::vector<uint8_t> create_proof_body(Context& ctx, const ProvingKeyDev&
     construct_intermediate_sets(queries, sets, super);
     const Fr vch = tr.squeeze_challenge();
     DevBuf<Fr> h_x(n, s), buf_a(n, s), buf_b(n, s);
+    // single GPU: the y-combined polynomial of every rotation set (Σ_j y^j p_j) is kept, so that the final linear combination
+    // runs over the sets instead of over all ≈ 75 polynomials again
+    DevBuf<Fr> set_polys;
+    const bool keep_sets = !shard.on();
     CUDA_CHECK(cudaMemsetAsync(h_x.get(), 0, n * sizeof(Fr), s));
     std::vector<std::vector<std::vector<Fr>>> low(sets.size());
     {
@@ -1067,6 +1071,10 @@ static std::vector<uint8_t> create_proof_body(Context& ctx, const ProvingKeyDev&
             }
             if (!shard.on() || set_owner[i] == ctx.rank) {
                 fr_lincomb(buf_a.get(), ps, cs, n, false, s);
+                if (keep_sets) {
+                    if (!set_polys.size()) set_polys.alloc(sets.size() * n, s);
+                    CUDA_CHECK(cudaMemcpyAsync(set_polys.get() + i * n, buf_a.get(), n * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
+                }
                 fr_sub_low(buf_a.get(), r_comb.data(), (uint32_t)r_comb.size(), s);
                 Fr *src = buf_a.get(), *dst = buf_b.get();
                 for (auto& pt : rs.points) {
@@ -1108,9 +1116,15 @@ static std::vector<uint8_t> create_proof_body(Context& ctx, const ProvingKeyDev&
             z_diffs.push_back(z_i);
             const Fr sc = f_mul(z_i, vp);
             Fr yp = one;
+            if (keep_sets) {  // Σ_j (sc·y^j)·p_j = sc·(the set's kept y-combination): the same field elements
+                ps.push_back(set_polys.get() + i * n);
+                cs.push_back(sc);
+            }
             for (size_t j = 0; j < rs.polys.size(); ++j) {
-                ps.push_back(polys[rs.polys[j]]);
-                cs.push_back(f_mul(sc, yp));
+                if (!keep_sets) {
+                    ps.push_back(polys[rs.polys[j]]);
+                    cs.push_back(f_mul(sc, yp));
+                }
                 const_term = f_add(const_term, f_mul(f_mul(sc, yp), eval_small(low[i][j], uch)));
                 yp = f_mul(yp, ych);
             }

@@ -42,6 +42,29 @@ def test_header_is_plain_c(tmp_path):
     subprocess.check_call(["gcc", "-std=gnu99", "-I", os.path.join(ROOT, "include"), str(src), "-L", libdir, "-lb200zk", "-Wl,-rpath," + libdir, "-o", str(exe)])
 
 
+def test_plain_c_host_builds_and_fails_loudly_without_a_gpu(tmp_path):
+    """tools/prove_c.c — a C99 host of the library (SRS setup, keygen, create_proof through include/b200zk.h, no Python in
+    the process) — must compile and link; without a device it must fail at b200zk_create, not fall back to anything."""
+    import shutil
+    import subprocess
+
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    b200zk.synth_circuit(5, 1, 1, 1)  # makes sure workload/libfriworkload.so is built
+    exe = tmp_path / "prove_c"
+    libdir, wdir = os.path.join(ROOT, "halo2-plonky2-verifier_b200"), os.path.join(ROOT, "workload")
+    subprocess.check_call(["gcc", "-O1", "-std=gnu99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tools", "prove_c.c"),
+                           "-L", libdir, "-lb200zk", "-L", wdir, "-lfriworkload", "-Wl,-rpath," + libdir, "-Wl,-rpath," + wdir, "-o", str(exe)])
+    import torch
+
+    if torch.cuda.is_available():
+        out = subprocess.run([str(exe), "8", "2", "1", "1", "1", "2"], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0 and '"proof_bytes"' in out.stdout, out.stderr
+    else:
+        out = subprocess.run([str(exe), "6", "2", "1", "1", "1", "1"], capture_output=True, text=True, timeout=60)
+        assert out.returncode != 0 and "b200zk_create" in out.stderr
+
+
 def test_no_cpu_fallback():
     import torch
 

@@ -29,7 +29,6 @@
 
 namespace b200zk {
 
-constexpr uint32_t INVALID_KEY = 0xffffffffu;
 
 struct MsmConfig {
     uint32_t c, W, B;   // window bits, windows, buckets per window (2^(c-1))
@@ -199,7 +198,6 @@ DEV uint32_t find_bucket(const uint32_t* offsets, uint32_t nb, uint32_t p) {
 
 constexpr int ACC_T_MIN = 16, ACC_T_MAX = 64;  // entries per thread, level 1 (chosen per launch, see pick_chunk)
 constexpr int COMB_T = 32;       // fan-in of the head combine levels (one warp per COMB_T partial sums)
-constexpr int ACC_THREADS = 128;
 
 // `entries` == nullptr: the list is `bases` itself (entry p = point p, no sign) — the output of the batched-affine rounds;
 // `total_dev` != nullptr: the list length is read from the device (the host only knows an upper bound, which sizes the grid)
@@ -390,42 +388,6 @@ __global__ void __launch_bounds__(BA_THREADS) ba_add_kernel(BaSrc S, const uint3
     if (bad) atomicOr(flag, 1u);
 }
 
-// Segmented sum of a key-sorted list of partial sums (INVALID_KEY entries are holes), one entry per lane: a 5-step shuffle
-// scan leaves the total of every run of equal keys in the run's first lane. A run that starts inside the warp is added into
-// its bucket (one writer per bucket and launch); the part of a run that began in an earlier warp goes to the next level,
-// which is 32x shorter. Latency per level: at most 5 dependent additions.
-DEV G1X g1x_shfl_down(const G1X& v, uint32_t d) {
-    G1X r;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        r.x.l[i] = __shfl_down_sync(0xffffffffu, v.x.l[i], d);
-        r.y.l[i] = __shfl_down_sync(0xffffffffu, v.y.l[i], d);
-        r.zz.l[i] = __shfl_down_sync(0xffffffffu, v.zz.l[i], d);
-        r.zzz.l[i] = __shfl_down_sync(0xffffffffu, v.zzz.l[i], d);
-    }
-    return r;
-}
-__global__ void __launch_bounds__(ACC_THREADS) msm_combine_kernel(const G1X* pts, const uint32_t* keys, uint32_t n, G1X* bucket_sums, G1X* heads_out,
-                                                                  uint32_t* keys_out) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31, warp = p >> 5;
-    if ((p & ~31u) >= n) return;  // whole warps only
-    const uint32_t key = p < n ? __ldg(keys + p) : INVALID_KEY;
-    const bool live = key != INVALID_KEY;
-    G1X acc = live ? g1x_load(pts + p) : g1x_identity();
-    for (uint32_t d = 1; d < 32; d <<= 1) {
-        const uint32_t okey = __shfl_down_sync(0xffffffffu, key, d);
-        const G1X o = g1x_shfl_down(acc, d);
-        if (live && lane + d < 32 && okey == key) acc = g1x_add(acc, o);
-    }
-    uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
-    if (lane == 0) prev = p > 0 ? __ldg(keys + p - 1) : INVALID_KEY;
-    const bool run_start = live && (lane == 0 || prev != key);
-    const bool started_before = live && lane == 0 && prev == key;
-    if (started_before) g1x_store(heads_out + warp, acc);
-    else if (run_start) g1x_store(bucket_sums + key, g1x_add(g1x_load(bucket_sums + key), acc));
-    if (lane == 0) keys_out[warp] = started_before ? key : INVALID_KEY;
-}
-
 // Σ 2^(c·w)·S_w on the host (64-bit limb path of the shared field code)
 G1X msm_fold_windows(const G1X* window_sums, uint32_t W, uint32_t c) {
     G1X acc = g1x_identity();
@@ -550,9 +512,7 @@ static void msm_issue_accumulate(MsmSlot& sl, const G1Affine* bases, const Fr* s
         uint32_t* in_k = flip ? sl.keys_b.get() : sl.keys_a.get();
         G1X* out_p = flip ? sl.heads_a.get() : sl.heads_b.get();
         uint32_t* out_k = flip ? sl.keys_a.get() : sl.keys_b.get();
-        msm_combine_kernel<<<(len + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, s>>>(in_p, in_k, len, bucket_sums, out_p, out_k);
-        ++g_launch_count;
-        CUDA_CHECK(cudaGetLastError());
+        msm_launch_combine(in_p, in_k, len, bucket_sums, out_p, out_k, s);
         if (nt == 1) break;  // a single warp has no predecessor: nothing can be left in its head slot
         len = nt;
         flip = !flip;

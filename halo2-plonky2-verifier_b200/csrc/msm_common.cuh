@@ -25,6 +25,10 @@ DEV G1Affine g1a_load_ro(const G1Affine* p) {
     return r;
 }
 
+constexpr uint32_t INVALID_KEY = 0xffffffffu;
+constexpr int ACC_THREADS = 128;
+// one level of the head combine (msm_reduce.cu): segmented sum of a key-sorted list of partial sums, 32 per warp
+void msm_launch_combine(const G1X* pts, const uint32_t* keys, uint32_t n, G1X* bucket_sums, G1X* heads_out, uint32_t* keys_out, cudaStream_t s);
 // Phase B of a commit batch: F(set) = Σ_b (b+1)·bucket[b] for G bucket sets of B buckets (msm_reduce.cu)
 void msm_reduce_groups(Context& ctx, const G1X* bucket_sums, uint32_t G, uint32_t B, std::vector<G1X>& sums_host, int gather_ranks = 1);
 

@@ -12,6 +12,48 @@
 
 namespace b200zk {
 
+// Segmented sum of a key-sorted list of partial sums (INVALID_KEY entries are holes), one entry per lane: a 5-step shuffle
+// scan leaves the total of every run of equal keys in the run's first lane. A run that starts inside the warp is added into
+// its bucket (one writer per bucket and launch); the part of a run that began in an earlier warp goes to the next level,
+// which is 32x shorter. Latency per level: at most 5 dependent additions.
+DEV G1X g1x_shfl_down(const G1X& v, uint32_t d) {
+    G1X r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        r.x.l[i] = __shfl_down_sync(0xffffffffu, v.x.l[i], d);
+        r.y.l[i] = __shfl_down_sync(0xffffffffu, v.y.l[i], d);
+        r.zz.l[i] = __shfl_down_sync(0xffffffffu, v.zz.l[i], d);
+        r.zzz.l[i] = __shfl_down_sync(0xffffffffu, v.zzz.l[i], d);
+    }
+    return r;
+}
+__global__ void __launch_bounds__(ACC_THREADS) msm_combine_kernel(const G1X* pts, const uint32_t* keys, uint32_t n, G1X* bucket_sums, G1X* heads_out,
+                                                                  uint32_t* keys_out) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31, warp = p >> 5;
+    if ((p & ~31u) >= n) return;  // whole warps only
+    const uint32_t key = p < n ? __ldg(keys + p) : INVALID_KEY;
+    const bool live = key != INVALID_KEY;
+    G1X acc = live ? g1x_load(pts + p) : g1x_identity();
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+        const uint32_t okey = __shfl_down_sync(0xffffffffu, key, d);
+        const G1X o = g1x_shfl_down(acc, d);
+        if (live && lane + d < 32 && okey == key) acc = g1x_add(acc, o);
+    }
+    uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+    if (lane == 0) prev = p > 0 ? __ldg(keys + p - 1) : INVALID_KEY;
+    const bool run_start = live && (lane == 0 || prev != key);
+    const bool started_before = live && lane == 0 && prev == key;
+    if (started_before) g1x_store(heads_out + warp, acc);
+    else if (run_start) g1x_store(bucket_sums + key, g1x_add(g1x_load(bucket_sums + key), acc));
+    if (lane == 0) keys_out[warp] = started_before ? key : INVALID_KEY;
+}
+
+void msm_launch_combine(const G1X* pts, const uint32_t* keys, uint32_t n, G1X* bucket_sums, G1X* heads_out, uint32_t* keys_out, cudaStream_t s) {
+    msm_combine_kernel<<<(n + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, s>>>(pts, keys, n, bucket_sums, heads_out, keys_out);
+    ++g_launch_count;
+    CUDA_CHECK(cudaGetLastError());
+}
+
 // ---- bucket reduction: per window F(B) = sum_b (b+1)·B[b] ---------------------------------------------------
 // Chunks of m consecutive entries give tot_q = Σ_r (r+1)·X[qm+r] and run_q = Σ_r X[qm+r] with 2 additions per
 // entry; then F(X) = Σ_q tot_q + m·(F(run) − S), S = ΣX, so the same kernel recurses on the `run` list (÷m per

@@ -95,7 +95,10 @@ struct Compat {
     int point_sign_bit = 6;            // [4] y-sign flag bit of compressed G1 points (6 or 7; the identity flag takes the other)
 };
 
-constexpr int MSM_SLOTS = 4;  // MSM columns in flight per commit batch
+#ifndef B200ZK_MSM_SLOTS
+#define B200ZK_MSM_SLOTS 4
+#endif
+constexpr int MSM_SLOTS = B200ZK_MSM_SLOTS;  // MSM columns in flight per commit batch
 #ifndef B200ZK_STAGE_WORKERS
 #define B200ZK_STAGE_WORKERS 6
 #endif

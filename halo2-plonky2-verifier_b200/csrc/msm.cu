@@ -2,7 +2,7 @@
 // ParamsKZG::{commit, commit_lagrange} from create_proof — reference entry verifier/src/stark/mod.rs:543,593).
 //
 // Only the group element Σ sᵢ·Pᵢ matters (canonical affine at the boundary), so the decomposition is free:
-//   0. tables   : for the SRS bases T[w][i] = 2^(c·w)·P_i is built once (c = 20: 13 windows), so every window of a column
+//   0. tables   : for the SRS bases T[w][i] = 2^(c·w)·P_i is built once (c = 20: 13 windows; c = k−2 on 4+ GPUs), so every window of a column
 //                 lands in ONE set of 2^(c-1) buckets and no doubling chain is left; caller-supplied bases keep one bucket
 //                 set per window and a short host-side fold.
 //   1. digits   : scalars leave Montgomery form; each is cut into W signed c-bit digits dₗ ∈ [-2^(c-1), 2^(c-1)];
@@ -11,17 +11,20 @@
 //                 a bucket is irrelevant to the group sum, so the result stays deterministic.
 //   3. accumulate: the sorted entry list is cut into equal chunks of T entries, one thread each (perfect balance
 //                 whatever the bucket histogram: hot buckets simply span many chunks). A thread walks its chunk
-//                 with one XYZZ accumulator and mixed additions (8M+2S); runs that begin inside the chunk are
-//                 stored to their bucket, the run that began earlier goes to a "head" list, which is segment-summed
-//                 one partial per lane with a shuffle scan (fan-in 32 per level) until one warp covers it.
-//   4. reduce   : Σ b·B_b via recursive chunked running sums (2 additions per bucket, Horner in the chunk size) down to
-//                 1024 entries per set, then one tail launch (block-wide suffix scan); done ONCE for all columns of a
-//                 commit batch — its deep levels are latency bound.
+//                 with one XYZZ accumulator and mixed additions (6 products + 2 squares + 1 dual product); runs that begin
+//                 inside the chunk are stored to their bucket, the run that began earlier goes to a "head" list, which is
+//                 segment-summed one partial per lane with a shuffle scan (fan-in 32 per level; msm_reduce.cu) until one
+//                 warp covers it. Optional batched-affine pre-reduction rounds exist and are off (measured slower).
+//   4. reduce   : (msm_reduce.cu) Σ b·B_b via recursive chunked running sums (2 additions per bucket, Horner in the chunk
+//                 size) down to 1024 entries per set, then one tail launch (block-wide suffix scan); done ONCE for all
+//                 columns of a commit batch — its deep levels are latency bound.
 // Up to four columns of a batch are in flight on separate streams so that the latency-bound phases of one column
 // (atomics, scans, the entry-count read-back, short combine levels) hide under another column's accumulate.
-// A batch may mix the two SRS bases (a base pointer per column). Multi-GPU: q·world columns are dealt by column, the
-// remainder is split by point range (see msm_batch_distribute).
-// Bound: the FMA-heavy (IMAD) pipe — 80 % busy in msm_accumulate_kernel (profiles/ncu_summary_r01.md) — not HBM.
+// A batch may mix the two SRS bases (a base pointer per column) and may be issued while its columns are still arriving
+// (Context::column_gate). Multi-GPU: q·world columns are dealt by column, the remainder is split by point range and the
+// partial sums are all-gathered over NCCL straight from the reduction's output (see msm_batch_distribute).
+// Bound: the FMA-heavy (IMAD) pipe — 73 % busy in msm_accumulate_kernel, whose multiply-adds are mostly half-rate carry
+// forms (profiles/ncu_summary_r02.md) — not HBM.
 #include <algorithm>
 #include <chrono>
 

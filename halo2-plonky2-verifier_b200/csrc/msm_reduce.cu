@@ -60,7 +60,10 @@ void msm_launch_combine(const G1X* pts, const uint32_t* keys, uint32_t n, G1X* b
 // level) and the per-level sums T_l = Σ_q tot_q are combined by a short Horner in m: A = S; A = T_l + m·(A − S).
 constexpr int RED_LOG_M = 3;
 // lists are window-major: X[w·len + i]; outputs tot[w·(len/m) + q], run[w·(len/m) + q]
-__global__ void __launch_bounds__(128) msm_reduce_chunks_kernel(const G1X* X, uint32_t total_chunks, uint32_t m, G1X* tot_out, G1X* run_out) {
+#ifndef B200ZK_REDUCE_MIN_CTAS
+#define B200ZK_REDUCE_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(128, B200ZK_REDUCE_MIN_CTAS) msm_reduce_chunks_kernel(const G1X* X, uint32_t total_chunks, uint32_t m, G1X* tot_out, G1X* run_out) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= total_chunks) return;
     const G1X* b = X + (size_t)j * m;

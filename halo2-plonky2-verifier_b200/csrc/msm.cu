@@ -66,13 +66,17 @@ MsmConfig msm_config_merged(uint32_t c, size_t table_n) {
     m.table_n = table_n;
     return m;
 }
-// measured at S20-bn / S22-bn on one GPU: the msm stage is flat for caps 17..21 (fewer buckets trade against more windows)
-// and worse below 16; 20 keeps the table smallest. On 4 and more GPUs the accumulation of a column shrinks with the rank
-// count but its bucket reduction does not (every rank reduces a full bucket set for each column it touches), so two bits
-// fewer pay: S20-bn on 8 GPUs 47.4 ms (c=20) -> 43.7 ms (c=18), 44.1 ms at c=16 (profiles/bench_r02_8gpu_c*.json).
+// Window bits of the precomputed tables. The column's accumulation costs n·ceil(255/c) mixed additions, its bucket
+// reduction ≈ 2.3·2^(c-1) full additions whatever n is, so among the c with the same window count the smallest wins and the
+// best c follows k. Measured on one GPU at S20-bn (profiles/bench_r02_table_bits.json): c=17 (15 windows, 2^16 buckets)
+// 140.0 ms, c=18 140.4, c=20 (13 windows) 141.8, c=19 143.9, c=16 144.5, c=21 152.5 — k−3 up to k=20; at k=22 (S22-bn/-gl,
+// four times the points per bucket set) the cap of 20 stays. On 4 and more GPUs a column's accumulation shrinks with the rank
+// count but its reduction does not, which favoured small windows even more (S20-bn on 8 GPUs: c=20 47.4 ms, c=18 43.7 ms,
+// c=16 44.1 ms; profiles/bench_r02_8gpu_c*.json).
 uint32_t msm_table_window_bits(uint32_t k, int world) {
     uint32_t c = k < 8 ? 8 : (k > 20 ? 20 : k);
-    if (world >= 4 && c >= 12) c = std::min<uint32_t>(c, k >= 2 ? k - 2 : c);
+    if (c >= 12 && k <= 20) c = k - 3;
+    else if (world >= 4 && c >= 12) c = std::min<uint32_t>(c, k - 2);
     if (const char* e = getenv("B200ZK_TABLE_BITS")) {  // experiments: window bits of the precomputed tables
         const int v = atoi(e);
         if (v >= 8 && v <= 22) c = (uint32_t)v;

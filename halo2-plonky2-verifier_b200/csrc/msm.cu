@@ -2,9 +2,9 @@
 // ParamsKZG::{commit, commit_lagrange} from create_proof — reference entry verifier/src/stark/mod.rs:543,593).
 //
 // Only the group element Σ sᵢ·Pᵢ matters (canonical affine at the boundary), so the decomposition is free:
-//   0. tables   : for the SRS bases T[w][i] = 2^(c·w)·P_i is built once (c = 20: 13 windows; c = k−2 on 4+ GPUs), so every window of a column
-//                 lands in ONE set of 2^(c-1) buckets and no doubling chain is left; caller-supplied bases keep one bucket
-//                 set per window and a short host-side fold.
+//   0. tables   : for the SRS bases T[w][i] = 2^(c·w)·P_i is built once (c = k−3 up to k = 20: 15 windows at k = 20;
+//                 msm_table_window_bits), so every window of a column lands in ONE set of 2^(c-1) buckets and no doubling
+//                 chain is left; caller-supplied bases keep one bucket set per window and a short host-side fold.
 //   1. digits   : scalars leave Montgomery form; each is cut into W signed c-bit digits dₗ ∈ [-2^(c-1), 2^(c-1)];
 //                 zero digits create no work (advice-like scalars are mostly < 2^84, lookup columns < 2^(k-1)).
 //   2. sort     : counting sort by bucket: histogram with warp-aggregated atomics, exclusive scan, scatter. Order inside

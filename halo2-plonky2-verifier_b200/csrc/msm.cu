@@ -203,7 +203,10 @@ DEV uint32_t find_bucket(const uint32_t* offsets, uint32_t nb, uint32_t p) {
     return lo;
 }
 
-constexpr int ACC_T_MIN = 16, ACC_T_MAX = 64;  // entries per thread, level 1 (chosen per launch, see pick_chunk)
+#ifndef B200ZK_ACC_T_MAX
+#define B200ZK_ACC_T_MAX 128
+#endif
+constexpr int ACC_T_MIN = 16, ACC_T_MAX = B200ZK_ACC_T_MAX;  // entries per thread, level 1 (chosen per launch below)
 constexpr int COMB_T = 32;       // fan-in of the head combine levels (one warp per COMB_T partial sums)
 
 // `entries` == nullptr: the list is `bases` itself (entry p = point p, no sign) — the output of the batched-affine rounds;

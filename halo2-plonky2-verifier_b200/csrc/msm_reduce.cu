@@ -58,7 +58,10 @@ void msm_launch_combine(const G1X* pts, const uint32_t* keys, uint32_t n, G1X* b
 // Chunks of m consecutive entries give tot_q = Σ_r (r+1)·X[qm+r] and run_q = Σ_r X[qm+r] with 2 additions per
 // entry; then F(X) = Σ_q tot_q + m·(F(run) − S), S = ΣX, so the same kernel recurses on the `run` list (÷m per
 // level) and the per-level sums T_l = Σ_q tot_q are combined by a short Horner in m: A = S; A = T_l + m·(A − S).
-constexpr int RED_LOG_M = 3;
+#ifndef B200ZK_RED_LOG_M
+#define B200ZK_RED_LOG_M 3
+#endif
+constexpr int RED_LOG_M = B200ZK_RED_LOG_M;
 // lists are window-major: X[w·len + i]; outputs tot[w·(len/m) + q], run[w·(len/m) + q]
 #ifndef B200ZK_REDUCE_MIN_CTAS
 #define B200ZK_REDUCE_MIN_CTAS 1
